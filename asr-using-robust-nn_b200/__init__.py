@@ -1,0 +1,16 @@
+"""B200-native (sm_100a) MFCC front end, additive-noise mixing and dataset standardisation.
+
+Drop-in for the data-parallel hot path of fmazilu/ASR-using-robust-NN:
+
+* ``asr_b200.voice_digit.extract_features_construct_dataset`` / ``.attacks`` mirror
+  ``Voice digit recogniton/extract_features_construct_dataset.py`` / ``attacks.py``;
+* ``asr_b200.speaker.*`` mirror ``Speaker recognition/*``;
+* ``asr_b200.frontend`` is the batched array-in API they delegate to;
+* all arithmetic runs in ``libasr_b200.so`` (hand-written CUDA, C-ABI in ``include/asr_b200.h``).
+"""
+from ._lib import AsrError, LIB_PATH  # noqa: F401
+from .params import MfccParams, REF_VDR, REF_SR, C1, C3, C5, PRESETS  # noqa: F401
+from .frontend import (ClipBatch, Noise, MfccPlan, Standardizer, clip_power, snr_sigma_host,  # noqa: F401
+                       snr_sigma_device, mix_white, mix_mixture, mix_rows_white, mix_rows_mixture, randn)
+
+__version__ = "0.1.0"

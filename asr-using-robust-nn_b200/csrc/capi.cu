@@ -1,0 +1,582 @@
+// C-ABI of libasr_b200: plan construction (host tables in float64 -> float32 device blob),
+// the fused-MFCC launch and the host-buffer pipeline.  See include/asr_b200.h for the contract.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include "common.cuh"
+
+namespace asr {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return ASR_ERR_CUDA;
+}
+
+static inline int round4(int x) { return (x + 3) & ~3; }
+// smallest multiple of 4 >= x whose quarter is odd: float4 rows at this pitch are bank-conflict free
+static inline int pitch_odd4(int x) {
+  int p = round4(x);
+  if (((p / 4) & 1) == 0) p += 4;
+  return p;
+}
+
+static const double kPi = 3.141592653589793238462643383279502884;
+
+// ---- librosa.core.convert (Slaney mel scale) ------------------------------------------------------
+static double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+  const double logstep = std::log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+  const double logstep = std::log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+static std::vector<double> linspace(double a, double b, int n) {
+  std::vector<double> v(n);
+  if (n == 1) { v[0] = a; return v; }
+  const double step = (b - a) / (n - 1);
+  for (int i = 0; i < n; ++i) v[i] = a + i * step;
+  v[n - 1] = b;
+  return v;
+}
+
+// librosa.filters.mel(htk=False, norm='slaney', dtype=float32), row-major (n_mels, n_bins)
+static std::vector<float> mel_dense(const asr_mfcc_params& p, int n_bins) {
+  const double fmax = p.fmax > 0 ? static_cast<double>(p.fmax) : p.sr / 2.0;
+  std::vector<double> fftfreqs(n_bins);
+  if (p.fftfreq_mode == ASR_FFTFREQ_LINSPACE) {
+    fftfreqs = linspace(0.0, p.sr / 2.0, n_bins);
+  } else {
+    const double val = 1.0 / (p.n_fft * (1.0 / p.sr));
+    for (int k = 0; k < n_bins; ++k) fftfreqs[k] = k * val;
+  }
+  std::vector<double> mel_f = linspace(hz_to_mel(p.fmin), hz_to_mel(fmax), p.n_mels + 2);
+  for (double& m : mel_f) m = mel_to_hz(m);
+  std::vector<float> w(static_cast<size_t>(p.n_mels) * n_bins, 0.0f);
+  for (int i = 0; i < p.n_mels; ++i) {
+    const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+    const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+    for (int k = 0; k < n_bins; ++k) {
+      const double lower = -(mel_f[i] - fftfreqs[k]) / fd0;
+      const double upper = (mel_f[i + 2] - fftfreqs[k]) / fd1;
+      const float tri = static_cast<float>(std::max(0.0, std::min(lower, upper)));   // stored float32 ...
+      w[static_cast<size_t>(i) * n_bins + k] = static_cast<float>(static_cast<double>(tri) * enorm);  // ... *= enorm
+    }
+  }
+  return w;
+}
+
+// scipy.signal.savgol_coeffs(width, polyorder=order, deriv=order) as correlation taps
+static bool savgol_taps(int width, int order, double* taps) {
+  const int h = width / 2, m = order + 1;
+  double A[3][3] = {{0}}, inv[3][3] = {{0}};
+  for (int x = -h; x <= h; ++x)
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j) A[i][j] += std::pow(static_cast<double>(x), i + j);
+  // Gauss-Jordan inverse of the (m x m) normal matrix
+  double aug[3][6];
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < 2 * m; ++j) aug[i][j] = j < m ? A[i][j] : (j - m == i ? 1.0 : 0.0);
+  for (int c = 0; c < m; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < m; ++r)
+      if (std::fabs(aug[r][c]) > std::fabs(aug[piv][c])) piv = r;
+    if (std::fabs(aug[piv][c]) < 1e-300) return false;
+    for (int j = 0; j < 2 * m; ++j) std::swap(aug[c][j], aug[piv][j]);
+    const double d = aug[c][c];
+    for (int j = 0; j < 2 * m; ++j) aug[c][j] /= d;
+    for (int r = 0; r < m; ++r)
+      if (r != c) {
+        const double f = aug[r][c];
+        for (int j = 0; j < 2 * m; ++j) aug[r][j] -= f * aug[c][j];
+      }
+  }
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) inv[i][j] = aug[i][m + j];
+  double fact = 1.0;
+  for (int i = 2; i <= order; ++i) fact *= i;
+  for (int x = -h; x <= h; ++x) {
+    double t = 0.0;
+    for (int j = 0; j < m; ++j) t += inv[order][j] * std::pow(static_cast<double>(x), j);
+    taps[x + h] = fact * t;
+  }
+  return true;
+}
+
+struct FftShape { int M, G, P; };
+static bool fft_shape(int n_fft, FftShape* s) {
+  switch (n_fft) {
+    case 512: *s = {256, 16, 16}; return true;
+    case 1024: *s = {512, 16, 32}; return true;
+    case 2048: *s = {1024, 32, 32}; return true;
+    default: return false;
+  }
+}
+
+static int validate(const asr_mfcc_params& p) {
+  auto bad = [](const char* m) { set_error(std::string("asr_plan_create: ") + m); return ASR_ERR_INVALID; };
+  if (p.sr <= 0) return bad("sr must be positive");
+  if (p.n_fft < 8 || p.n_fft > 8192) return bad("n_fft must be in [8, 8192]");
+  if (p.win_length < 0 || p.win_length > p.n_fft) return bad("win_length must be in [0, n_fft]");
+  if (p.hop_length < 1) return bad("hop_length must be >= 1");
+  if (p.window != ASR_WIN_HANN && p.window != ASR_WIN_HAMMING) return bad("window must be hann or hamming");
+  if (p.pad_mode != ASR_PAD_REFLECT && p.pad_mode != ASR_PAD_CONSTANT) return bad("pad_mode must be reflect or constant");
+  if (p.fftfreq_mode != ASR_FFTFREQ_LINSPACE && p.fftfreq_mode != ASR_FFTFREQ_RFFTFREQ) return bad("bad fftfreq_mode");
+  if (p.n_mels < 1 || p.n_mels > 512) return bad("n_mels must be in [1, 512]");
+  if (p.n_mfcc < 1 || p.n_mfcc > p.n_mels) return bad("n_mfcc must be in [1, n_mels]");
+  if (p.fmin < 0 || (p.fmax > 0 && p.fmax <= p.fmin)) return bad("need 0 <= fmin < fmax");
+  if (!(p.amin > 0)) return bad("amin must be positive");
+  if (p.lifter < 0) return bad("lifter must be >= 0");
+  if (p.delta_orders < 0 || p.delta_orders > 2) return bad("delta_orders must be 0, 1 or 2");
+  if (p.delta_orders > 0 && (p.delta_width < 3 || (p.delta_width & 1) == 0 || p.delta_width > 63))
+    return bad("delta_width must be odd, in [3, 63]");
+  return ASR_OK;
+}
+
+}  // namespace asr
+
+using namespace asr;
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" int asr_version(void) { return ASR_B200_VERSION; }
+extern "C" const char* asr_last_error(void) { return g_last_error.c_str(); }
+extern "C" int asr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_out) {
+  if (!params || !plan_out) { set_error("asr_plan_create: null pointer"); return ASR_ERR_INVALID; }
+  *plan_out = nullptr;
+  const int vr = validate(*params);
+  if (vr != ASR_OK) return vr;
+  asr_plan* pl = new (std::nothrow) asr_plan();
+  if (!pl) { set_error("asr_plan_create: out of host memory"); return ASR_ERR_ALLOC; }
+  const asr_mfcc_params& p = *params;
+  pl->prm = p;
+  pl->win_length = p.win_length > 0 ? p.win_length : p.n_fft;
+  pl->pad = p.center ? p.n_fft / 2 : 0;
+  pl->n_bins = 1 + p.n_fft / 2;
+  FftShape fs{0, 0, 0};
+  pl->fft_path = fft_shape(p.n_fft, &fs) ? 1 : 0;
+  pl->fb = pl->fft_path ? kWarps * (32 / fs.G) : kWarps;
+  const int s_off = pl->fft_path ? 0 : round4(p.n_fft);
+  pl->frame_stride = pl->fft_path ? pitch_odd4(2 * (fs.M + fs.G)) : pitch_odd4(s_off + round4(pl->n_bins));
+  pl->chunk_cap = round4((pl->fb - 1) * p.hop_length + p.n_fft);
+  pl->lm_pitch = pitch_odd4(p.n_mels);
+  pl->dct_pitch = round4(p.n_mels);
+  pl->n_streams = kWarps * (32 / pl->fb);
+
+  // ---- window: scipy.signal.get_window(name, win_length, fftbins=True), centre-padded to n_fft ----
+  pl->h_window.assign(p.n_fft, 0.0f);
+  {
+    const int wl = pl->win_length, lpad = (p.n_fft - wl) / 2;
+    const double a0 = p.window == ASR_WIN_HANN ? 0.5 : 0.54, a1 = 1.0 - a0;
+    for (int n = 0; n < wl; ++n)
+      pl->h_window[lpad + n] = static_cast<float>(wl == 1 ? 1.0 : a0 - a1 * std::cos(2.0 * kPi * n / wl));
+  }
+  // ---- mel bank: dense float32 (librosa) -> contiguous supports -> float4 tasks ----
+  pl->h_mel_dense = mel_dense(p, pl->n_bins);
+  std::vector<MelTask> tasks;
+  std::vector<float> melw;
+  std::vector<int> ftasks(2 * p.n_mels, 0);
+  for (int i = 0; i < p.n_mels; ++i) {
+    const float* row = pl->h_mel_dense.data() + static_cast<size_t>(i) * pl->n_bins;
+    int lo = -1, hi = -1;
+    for (int k = 0; k < pl->n_bins; ++k)
+      if (row[k] != 0.0f) { if (lo < 0) lo = k; hi = k + 1; }
+    ftasks[2 * i] = static_cast<int>(tasks.size());
+    if (lo >= 0) {
+      const int a = lo & ~3;
+      const int quads = (hi - a + 3) / 4;
+      for (int q0 = 0; q0 < quads; q0 += kMelChunkQuads) {
+        MelTask t;
+        t.filter = i;
+        t.k_start = a + 4 * q0;
+        t.n_quads = std::min(kMelChunkQuads, quads - q0);
+        t.w_off = static_cast<int>(melw.size() / 4);
+        for (int k = t.k_start; k < t.k_start + 4 * t.n_quads; ++k) melw.push_back(k < pl->n_bins ? row[k] : 0.0f);
+        tasks.push_back(t);
+      }
+    }
+    ftasks[2 * i + 1] = static_cast<int>(tasks.size()) - ftasks[2 * i];
+  }
+  pl->n_tasks = static_cast<int>(tasks.size());
+  // longest-processing-time assignment of tasks to the sub-warp streams
+  std::vector<int> order(pl->n_tasks);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tasks[a].n_quads > tasks[b].n_quads; });
+  std::vector<std::vector<int>> per_stream(pl->n_streams);
+  std::vector<int> load(pl->n_streams, 0);
+  for (int t : order) {
+    const int s = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+    per_stream[s].push_back(t);
+    load[s] += tasks[t].n_quads + 1;
+  }
+  std::vector<int> sbeg(pl->n_streams + 1, 0), stasks;
+  for (int s = 0; s < pl->n_streams; ++s) {
+    std::sort(per_stream[s].begin(), per_stream[s].end());
+    sbeg[s] = static_cast<int>(stasks.size());
+    stasks.insert(stasks.end(), per_stream[s].begin(), per_stream[s].end());
+  }
+  sbeg[pl->n_streams] = static_cast<int>(stasks.size());
+  // ---- DCT-II ortho rows [0, n_mfcc) with the lifter folded in ----
+  pl->h_dct.assign(static_cast<size_t>(p.n_mfcc) * p.n_mels, 0.0f);
+  std::vector<float> dct_p(static_cast<size_t>(p.n_mfcc) * pl->dct_pitch, 0.0f);
+  for (int c = 0; c < p.n_mfcc; ++c) {
+    const double sc = c == 0 ? std::sqrt(1.0 / p.n_mels) : std::sqrt(2.0 / p.n_mels);
+    const double lift = p.lifter > 0 ? 1.0 + (p.lifter / 2.0) * std::sin(kPi * (c + 1) / p.lifter) : 1.0;
+    for (int n = 0; n < p.n_mels; ++n) {
+      const float v = static_cast<float>(sc * std::cos(kPi * c * (2 * n + 1) / (2.0 * p.n_mels)) * lift);
+      pl->h_dct[static_cast<size_t>(c) * p.n_mels + n] = v;
+      dct_p[static_cast<size_t>(c) * pl->dct_pitch + n] = v;
+    }
+  }
+  // ---- delta taps ----
+  pl->h_taps.assign(static_cast<size_t>(std::max(1, p.delta_orders)) * std::max(1, p.delta_width), 0.0f);
+  for (int o = 1; o <= p.delta_orders; ++o) {
+    std::vector<double> t(p.delta_width);
+    if (!savgol_taps(p.delta_width, o, t.data())) {
+      set_error("asr_plan_create: singular Savitzky-Golay system");
+      delete pl;
+      return ASR_ERR_INVALID;
+    }
+    for (int j = 0; j < p.delta_width; ++j) pl->h_taps[static_cast<size_t>(o - 1) * p.delta_width + j] = static_cast<float>(t[j]);
+  }
+  // ---- FFT twiddles ----
+  std::vector<float> twp, twu;
+  if (pl->fft_path) {
+    const int stride = 2 * fs.P + 4;
+    twp.assign(static_cast<size_t>(fs.G) * stride, 0.0f);
+    for (int n1 = 0; n1 < fs.G; ++n1)
+      for (int k2 = 0; k2 < fs.P; ++k2) {
+        const double ang = 2.0 * kPi * (static_cast<double>(n1) * k2) / fs.M;
+        twp[static_cast<size_t>(n1) * stride + 2 * k2] = static_cast<float>(std::cos(ang));
+        twp[static_cast<size_t>(n1) * stride + 2 * k2 + 1] = static_cast<float>(-std::sin(ang));
+      }
+    twu.assign(2 * (fs.M / 2 + 1), 0.0f);
+    for (int k = 0; k <= fs.M / 2; ++k) {
+      const double ang = 2.0 * kPi * k / p.n_fft;
+      twu[2 * k] = static_cast<float>(-0.5 * std::sin(ang));
+      twu[2 * k + 1] = static_cast<float>(-0.5 * std::cos(ang));
+    }
+  } else {
+    twu.assign(2 * static_cast<size_t>(p.n_fft), 0.0f);
+    for (int j = 0; j < p.n_fft; ++j) {
+      const double ang = 2.0 * kPi * j / p.n_fft;
+      twu[2 * j] = static_cast<float>(std::cos(ang));
+      twu[2 * j + 1] = static_cast<float>(std::sin(ang));
+    }
+  }
+  // ---- pack the blob (every section 16-byte aligned) ----
+  std::vector<float> blob;
+  auto put_f = [&](const float* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.insert(blob.end(), src, src + n);
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  auto put_i = [&](const int* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.resize(blob.size() + n);
+    if (n) std::memcpy(blob.data() + off, src, n * sizeof(int));
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  pl->off_window = put_f(pl->h_window.data(), pl->h_window.size());
+  pl->off_twp = put_f(twp.data(), twp.size());
+  pl->off_twu = put_f(twu.data(), twu.size());
+  pl->off_tasks = put_i(reinterpret_cast<const int*>(tasks.data()), tasks.size() * 4);
+  pl->off_melw = put_f(melw.data(), melw.size());
+  pl->off_sbeg = put_i(sbeg.data(), sbeg.size());
+  pl->off_stasks = put_i(stasks.data(), stasks.size());
+  pl->off_ftasks = put_i(ftasks.data(), ftasks.size());
+  pl->off_dct = put_f(dct_p.data(), dct_p.size());
+  pl->off_taps = put_f(pl->h_taps.data(), pl->h_taps.size());
+  pl->blob_floats = static_cast<int>(blob.size());
+
+  cudaError_t e = cudaGetDevice(&pl->device);
+  if (e == cudaSuccess) e = mfcc_kernel_init();
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&pl->blob_dev), blob.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(pl->blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (pl->blob_dev) cudaFree(pl->blob_dev);
+    delete pl;
+    return cuda_fail(e, "asr_plan_create (no usable CUDA device? there is no CPU fallback)");
+  }
+  *plan_out = pl;
+  return ASR_OK;
+}
+
+extern "C" void asr_plan_destroy(asr_plan* plan) {
+  if (!plan) return;
+  if (plan->blob_dev) cudaFree(plan->blob_dev);
+  delete plan;
+}
+
+extern "C" int32_t asr_plan_num_frames(const asr_plan* plan, int64_t length) {
+  if (!plan || length < 0) return 0;
+  if (plan->prm.pad_mode == ASR_PAD_REFLECT && plan->pad > 0 && length <= plan->pad) return 0;
+  const int64_t padded = length + 2 * static_cast<int64_t>(plan->pad);
+  if (padded < plan->prm.n_fft) return 0;
+  return static_cast<int32_t>(1 + (padded - plan->prm.n_fft) / plan->prm.hop_length);
+}
+
+extern "C" int32_t asr_plan_feature_rows(const asr_plan* plan) {
+  return plan ? plan->prm.n_mfcc * (1 + plan->prm.delta_orders) : 0;
+}
+
+extern "C" int32_t asr_plan_uses_fft(const asr_plan* plan) { return plan ? plan->fft_path : 0; }
+
+extern "C" int asr_plan_get_tables(const asr_plan* plan, float* window, float* mel_dense_out, float* dct,
+                                   float* delta_taps) {
+  if (!plan) { set_error("asr_plan_get_tables: null plan"); return ASR_ERR_INVALID; }
+  if (window) std::memcpy(window, plan->h_window.data(), plan->h_window.size() * sizeof(float));
+  if (mel_dense_out) std::memcpy(mel_dense_out, plan->h_mel_dense.data(), plan->h_mel_dense.size() * sizeof(float));
+  if (dct) std::memcpy(dct, plan->h_dct.data(), plan->h_dct.size() * sizeof(float));
+  if (delta_taps && plan->prm.delta_orders > 0)
+    std::memcpy(delta_taps, plan->h_taps.data(), sizeof(float) * plan->prm.delta_orders * plan->prm.delta_width);
+  return ASR_OK;
+}
+
+static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
+                         const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
+                         void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev, void* stream,
+                         int logmel_only, const char* who) {
+  auto bad = [&](const char* m) { set_error(std::string(who) + ": " + m); return ASR_ERR_INVALID; };
+  if (!plan) return bad("null plan");
+  if (n_clips < 0) return bad("negative n_clips");
+  if (n_clips == 0) return ASR_OK;
+  if (!audio_dev || !offsets_dev || !lengths_dev || !out_dev) return bad("null pointer");
+  if (dtype < ASR_I16 || dtype > ASR_F64) return bad("dtype must be ASR_I16, ASR_F32 or ASR_F64");
+  if (out_dtype != ASR_F32 && out_dtype != ASR_F64) return bad("out_dtype must be ASR_F32 or ASR_F64");
+  if (out_frames < 1) return bad("out_frames must be >= 1");
+  if (max_length < 0) return bad("negative max_length");
+  const asr_mfcc_params& p = plan->prm;
+  KParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.audio = audio_dev;
+  kp.offsets = reinterpret_cast<const long long*>(offsets_dev);
+  kp.lengths = lengths_dev;
+  kp.dtype = dtype;
+  kp.n_clips = n_clips;
+  kp.noise_mode = ASR_NOISE_NONE;
+  if (noise && noise->mode != ASR_NOISE_NONE) {
+    if (noise->mode == ASR_NOISE_WHITE) {
+      if (!noise->z_dev || !noise->sigma_dev) return bad("white noise needs z_dev and sigma_dev");
+    } else if (noise->mode == ASR_NOISE_MIXTURE) {
+      if (!noise->z_dev || !noise->z2_dev) return bad("mixture noise needs z_dev (selector) and z2_dev (carrier)");
+    } else {
+      return bad("unknown noise mode");
+    }
+    kp.noise_mode = noise->mode;
+    kp.z = noise->z_dev; kp.z2 = noise->z2_dev; kp.sigma = noise->sigma_dev;
+    kp.mix_p = noise->p; kp.mix_s0 = noise->sigma0; kp.mix_s1 = noise->sigma1;
+  }
+  kp.out = out_dev;
+  kp.out_f64 = out_dtype == ASR_F64;
+  kp.out_frames = out_frames;
+  kp.out_rows = p.n_mfcc * (1 + p.delta_orders);
+  kp.logmel_only = logmel_only;
+  kp.status = status_dev;
+  kp.n_fft = p.n_fft; kp.hop = p.hop_length; kp.pad = plan->pad; kp.pad_mode = p.pad_mode;
+  kp.n_bins = plan->n_bins; kp.n_mels = p.n_mels; kp.n_mfcc = p.n_mfcc;
+  kp.delta_orders = p.delta_orders; kp.delta_width = p.delta_width;
+  kp.top_db = p.top_db; kp.amin = p.amin; kp.preemph = p.preemph;
+  kp.lm_pitch = plan->lm_pitch; kp.dct_pitch = plan->dct_pitch;
+  kp.fft_path = plan->fft_path; kp.fb = plan->fb; kp.frame_stride = plan->frame_stride; kp.chunk_cap = plan->chunk_cap;
+  kp.n_tasks = plan->n_tasks; kp.n_streams = plan->n_streams;
+  kp.blob = reinterpret_cast<const float4*>(plan->blob_dev);
+  kp.blob_f4 = plan->blob_floats / 4;
+  kp.off_window = plan->off_window; kp.off_twp = plan->off_twp; kp.off_twu = plan->off_twu;
+  kp.off_tasks = plan->off_tasks; kp.off_melw = plan->off_melw; kp.off_sbeg = plan->off_sbeg;
+  kp.off_stasks = plan->off_stasks; kp.off_ftasks = plan->off_ftasks; kp.off_dct = plan->off_dct;
+  kp.off_taps = plan->off_taps;
+  // ---- cluster size + dynamic shared memory layout ----
+  // One CTA holds the log-mel rows of ceil(T/cs) frames; grow the cluster until that fits, then keep
+  // growing (up to 8) while the launch would leave most of the 148 SMs without a CTA.
+  const int t_all = std::max(1, asr_plan_num_frames(plan, max_length));
+  const int half = p.delta_orders > 0 ? p.delta_width / 2 : 0;
+  const bool want_cbuf = p.delta_orders > 0 && !logmel_only;
+  auto layout = [&](int cs, KParams& k) -> long long {
+    const int t_cap = (t_all + cs - 1) / cs;
+    int off = plan->blob_floats;
+    k.sm_audio = off; off += plan->chunk_cap;
+    k.sm_frames = off; off += plan->fb * plan->frame_stride;
+    k.sm_part = off; off += round4(std::max(1, plan->n_tasks) * plan->fb);
+    k.sm_lm = off; off += t_cap * plan->lm_pitch;
+    k.cbuf_pitch = round4(t_cap + 2 * half + 1);
+    k.sm_cbuf = off; off += want_cbuf ? p.n_mfcc * k.cbuf_pitch : 0;
+    k.sm_red = off; off += 32;
+    k.t_cap = t_cap;
+    k.cluster_size = cs;
+    return static_cast<long long>(off) * 4;
+  };
+  int cs = 1;
+  long long smem_bytes = layout(cs, kp);
+  while (smem_bytes > kMaxSmemBytes && cs < 16) { cs *= 2; smem_bytes = layout(cs, kp); }
+  if (smem_bytes > kMaxSmemBytes) {
+    set_error(std::string(who) + ": clip of " + std::to_string(max_length) + " samples (" + std::to_string(t_all) +
+              " frames) needs " + std::to_string(smem_bytes) + " bytes of shared memory per CTA even with a 16-CTA"
+              " cluster; limit is " + std::to_string(kMaxSmemBytes));
+    return ASR_ERR_TOO_LARGE;
+  }
+  while (cs < 8 && static_cast<long long>(n_clips) * cs < 4 * 148 && (t_all + 2 * cs - 1) / (2 * cs) >= 2 * plan->fb) {
+    cs *= 2;
+    smem_bytes = layout(cs, kp);
+  }
+  ASR_CUDA_TRY(launch_mfcc(kp, static_cast<int>(smem_bytes), as_stream(stream)));
+  return ASR_OK;
+}
+
+extern "C" int asr_mfcc_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
+                              const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
+                              void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev, void* stream) {
+  return launch_common(plan, audio_dev, dtype, offsets_dev, lengths_dev, n_clips, max_length, noise, out_dev,
+                       out_dtype, out_frames, status_dev, stream, 0, "asr_mfcc_batch");
+}
+
+extern "C" int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
+                                const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
+                                float* out_dev, int32_t out_frames, int32_t* status_dev, void* stream) {
+  return launch_common(plan, audio_dev, dtype, offsets_dev, lengths_dev, n_clips, max_length, noise, out_dev, ASR_F32,
+                       out_frames, status_dev, stream, 1, "asr_logmel_batch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer pipeline: clips are cut into chunks; chunk i+1's H2D copy overlaps chunk i's kernels
+// and chunk i-1's D2H copy (two streams, two sets of device buffers).
+namespace {
+struct Slot {
+  cudaStream_t st = nullptr;
+  void* audio = nullptr;
+  long long* offsets = nullptr;
+  int* lengths = nullptr;
+  void* out = nullptr;
+  int* status = nullptr;
+  float* power = nullptr;
+  double* sigma = nullptr;
+  double* z = nullptr;
+  void release() {
+    if (audio) cudaFree(audio);
+    if (offsets) cudaFree(offsets);
+    if (lengths) cudaFree(lengths);
+    if (out) cudaFree(out);
+    if (status) cudaFree(status);
+    if (power) cudaFree(power);
+    if (sigma) cudaFree(sigma);
+    if (z) cudaFree(z);
+    if (st) cudaStreamDestroy(st);
+  }
+};
+}  // namespace
+
+extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host, int32_t dtype,
+                                   const int64_t* offsets_host, const int32_t* lengths_host, int32_t n_clips,
+                                   int32_t snr_mode, float target_snr_db, uint64_t seed, void* out_host,
+                                   int32_t out_dtype, int32_t out_frames, int32_t* status_host) {
+  auto bad = [&](const char* m) { set_error(std::string("asr_mfcc_batch_host: ") + m); return ASR_ERR_INVALID; };
+  if (!plan) return bad("null plan");
+  if (n_clips < 0) return bad("negative n_clips");
+  if (n_clips == 0) return ASR_OK;
+  if (!audio_host || !offsets_host || !lengths_host || !out_host) return bad("null pointer");
+  if (dtype < ASR_I16 || dtype > ASR_F64) return bad("bad dtype");
+  if (out_dtype != ASR_F32 && out_dtype != ASR_F64) return bad("bad out_dtype");
+  if (out_frames < 1) return bad("out_frames must be >= 1");
+  if (snr_mode != 0 && snr_mode != 1) return bad("snr_mode must be 0 or 1");
+  if (snr_mode == 1 && dtype == ASR_F64) return bad("SNR mode needs ASR_I16 or ASR_F32 audio");
+  const size_t esz = dtype == ASR_I16 ? 2 : (dtype == ASR_F32 ? 4 : 8);
+  const size_t osz = out_dtype == ASR_F64 ? 8 : 4;
+  const int rows = asr_plan_feature_rows(plan);
+  const size_t out_per_clip = static_cast<size_t>(rows) * out_frames;
+  // chunks of consecutive clips: <= 64 MiB of samples and <= 4096 clips; offsets must be ascending & disjoint
+  const int64_t kChunkSamples = (64ll << 20) / static_cast<int64_t>(esz);
+  const int kChunkClips = 4096;
+  std::vector<int> cuts{0};
+  {
+    int64_t s = 0;
+    int c = 0;
+    for (int i = 0; i < n_clips; ++i) {
+      if (lengths_host[i] < 0) return bad("negative clip length");
+      if (i > 0 && offsets_host[i] < offsets_host[i - 1] + lengths_host[i - 1])
+        return bad("offsets must be ascending and clips must not overlap");
+      if (c > 0 && (c >= kChunkClips || s + lengths_host[i] > kChunkSamples)) { cuts.push_back(i); s = 0; c = 0; }
+      s += lengths_host[i];
+      ++c;
+    }
+    cuts.push_back(n_clips);
+  }
+  size_t max_span = 0;
+  int max_clips = 0, max_len = 0;
+  for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+    const int a = cuts[k], b = cuts[k + 1];
+    const size_t span = static_cast<size_t>(offsets_host[b - 1] + lengths_host[b - 1] - offsets_host[a]);
+    max_span = std::max(max_span, span);
+    max_clips = std::max(max_clips, b - a);
+  }
+  for (int i = 0; i < n_clips; ++i) max_len = std::max(max_len, lengths_host[i]);
+  Slot slots[2];
+  int rc = ASR_OK;
+  auto fail = [&](cudaError_t e, const char* what) { rc = cuda_fail(e, what); };
+  for (int s = 0; s < 2 && rc == ASR_OK; ++s) {
+    Slot& sl = slots[s];
+    cudaError_t e = cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.audio, std::max<size_t>(16, max_span * esz));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.offsets), sizeof(long long) * max_clips);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.lengths), sizeof(int) * max_clips);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.out, out_per_clip * osz * max_clips);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.status), sizeof(int) * max_clips);
+    if (e == cudaSuccess && snr_mode) {
+      e = cudaMalloc(reinterpret_cast<void**>(&sl.power), sizeof(float) * max_clips);
+      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.sigma), sizeof(double) * max_clips);
+      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.z), sizeof(double) * std::max<size_t>(1, max_span));
+    }
+    if (e != cudaSuccess) fail(e, "asr_mfcc_batch_host (allocation)");
+  }
+  for (size_t k = 0; k + 1 < cuts.size() && rc == ASR_OK; ++k) {
+    Slot& sl = slots[k & 1];
+    const int a = cuts[k], b = cuts[k + 1], nc = b - a;
+    const int64_t first = offsets_host[a];
+    const size_t span = static_cast<size_t>(offsets_host[b - 1] + lengths_host[b - 1] - first);
+    cudaError_t e = cudaStreamSynchronize(sl.st);   // slot free again
+    if (e != cudaSuccess) { fail(e, "stream sync"); break; }
+    std::vector<long long> reb(nc);
+    for (int i = 0; i < nc; ++i) reb[i] = offsets_host[a + i] - first;
+    e = cudaMemcpyAsync(sl.audio, static_cast<const char*>(audio_host) + first * esz, span * esz,
+                        cudaMemcpyHostToDevice, sl.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.offsets, reb.data(), sizeof(long long) * nc, cudaMemcpyHostToDevice, sl.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.lengths, lengths_host + a, sizeof(int) * nc, cudaMemcpyHostToDevice, sl.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sl.st);   // `reb` is a local pageable vector
+    if (e != cudaSuccess) { fail(e, "H2D copy"); break; }
+    asr_noise nz;
+    std::memset(&nz, 0, sizeof(nz));
+    if (snr_mode) {
+      rc = asr_clip_power(sl.audio, dtype, reinterpret_cast<const int64_t*>(sl.offsets), sl.lengths, nc, sl.power, sl.st);
+      if (rc == ASR_OK) rc = asr_snr_sigma(sl.power, target_snr_db, sl.sigma, nc, sl.st);
+      if (rc == ASR_OK) rc = asr_randn_f64(seed, static_cast<uint64_t>(first), static_cast<int64_t>(span), sl.z, sl.st);
+      if (rc != ASR_OK) break;
+      nz.mode = ASR_NOISE_WHITE; nz.z_dev = sl.z; nz.sigma_dev = sl.sigma;
+    }
+    rc = asr_mfcc_batch(plan, sl.audio, dtype, reinterpret_cast<const int64_t*>(sl.offsets), sl.lengths, nc, max_len,
+                        snr_mode ? &nz : nullptr, sl.out, out_dtype, out_frames, sl.status, sl.st);
+    if (rc != ASR_OK) break;
+    e = cudaMemcpyAsync(static_cast<char*>(out_host) + static_cast<size_t>(a) * out_per_clip * osz, sl.out,
+                        out_per_clip * osz * nc, cudaMemcpyDeviceToHost, sl.st);
+    if (e == cudaSuccess && status_host)
+      e = cudaMemcpyAsync(status_host + a, sl.status, sizeof(int) * nc, cudaMemcpyDeviceToHost, sl.st);
+    if (e != cudaSuccess) { fail(e, "D2H copy"); break; }
+  }
+  for (int s = 0; s < 2; ++s)
+    if (slots[s].st) {
+      const cudaError_t e = cudaStreamSynchronize(slots[s].st);
+      if (e != cudaSuccess && rc == ASR_OK) fail(e, "final sync");
+    }
+  for (int s = 0; s < 2; ++s) slots[s].release();
+  return rc;
+}

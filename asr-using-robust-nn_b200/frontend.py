@@ -1,0 +1,388 @@
+"""Batched, array-in host API over the C-ABI (device memory and streams through torch).
+
+This is the layer the reference-named entry points in ``voice_digit/`` and
+``speaker/`` delegate to after decoding audio: waveforms + lengths in, the
+reference's ``(N, n_mfcc*T)`` feature layout out.  torch is plumbing only
+(allocations, streams, ``torch.distributed``); all arithmetic runs in
+``libasr_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, AsrError, NoiseC
+from .params import MfccParams
+
+_DT = {torch.int16: _lib.ASR_I16, torch.float32: _lib.ASR_F32, torch.float64: _lib.ASR_F64}
+_NP2T = {np.dtype(np.int16): torch.int16, np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+
+
+_MATRIX_LAYOUTS: dict = {}
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise AsrError("no CUDA device: the asr_b200 path has no CPU fallback")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class ClipBatch:
+    """Packed clips on the device: ``audio[offsets[b] : offsets[b]+lengths[b]]`` is clip b."""
+    audio: torch.Tensor        # 1-D int16 / float32 / float64, device
+    offsets: torch.Tensor      # int64 [B], device
+    lengths: torch.Tensor      # int32 [B], device
+    max_length: int
+    offsets_host: np.ndarray   # int64 [B]
+    lengths_host: np.ndarray   # int32 [B]
+
+    @property
+    def n_clips(self) -> int:
+        return int(self.lengths_host.shape[0])
+
+    @property
+    def dtype_code(self) -> int:
+        return _DT[self.audio.dtype]
+
+    @staticmethod
+    def layout(lengths: Sequence[int], align: int = 8):
+        """Offsets for packing clips back to back, each start aligned to `align` elements."""
+        lengths = np.asarray(lengths, dtype=np.int64)
+        padded = (lengths + align - 1) // align * align
+        offsets = np.zeros(len(lengths), dtype=np.int64)
+        if len(lengths) > 1:
+            offsets[1:] = np.cumsum(padded[:-1])
+        total = int(padded.sum()) if len(lengths) else 0
+        return offsets, max(total, align)
+
+    @staticmethod
+    def from_arrays(clips: Sequence[np.ndarray], device="cuda", dtype=None) -> "ClipBatch":
+        """Pack a list of 1-D numpy waveforms (int16 / float32 / float64, all the same dtype)."""
+        _require_cuda()
+        clips = [np.ascontiguousarray(c) for c in clips]
+        if dtype is None:
+            dtype = clips[0].dtype if clips else np.dtype(np.float32)
+        dtype = np.dtype(dtype)
+        if dtype not in _NP2T:
+            raise TypeError(f"unsupported audio dtype {dtype}; use int16, float32 or float64")
+        lengths = np.array([c.shape[0] for c in clips], dtype=np.int32)
+        offsets, total = ClipBatch.layout(lengths)
+        host = torch.zeros(total, dtype=_NP2T[dtype]).pin_memory()
+        hv = host.numpy()
+        for c, o in zip(clips, offsets):
+            if c.ndim != 1:
+                raise ValueError("clips must be 1-D (mono) waveforms")
+            hv[o:o + c.shape[0]] = c.astype(dtype, copy=False)
+        return ClipBatch(host.to(device, non_blocking=True), torch.from_numpy(offsets).to(device),
+                         torch.from_numpy(lengths).to(device), int(lengths.max()) if len(lengths) else 0,
+                         offsets, lengths)
+
+    @staticmethod
+    def from_matrix(x: torch.Tensor) -> "ClipBatch":
+        """Equal-length clips already on the device as a contiguous (B, L) tensor (no copy)."""
+        if x.dim() != 2 or not x.is_contiguous() or x.dtype not in _DT:
+            raise ValueError("expected a contiguous (B, L) int16/float32/float64 tensor")
+        B, L = x.shape
+        key = (B, L, x.device)
+        hit = _MATRIX_LAYOUTS.get(key)
+        if hit is None:
+            offsets = np.arange(B, dtype=np.int64) * L
+            lengths = np.full(B, L, dtype=np.int32)
+            hit = (torch.from_numpy(offsets).to(x.device), torch.from_numpy(lengths).to(x.device), offsets, lengths)
+            if len(_MATRIX_LAYOUTS) > 64:
+                _MATRIX_LAYOUTS.clear()
+            _MATRIX_LAYOUTS[key] = hit
+        return ClipBatch(x.reshape(-1), hit[0], hit[1], L, hit[2], hit[3])
+
+    def like(self, data: torch.Tensor) -> "ClipBatch":
+        """Same layout, different payload (e.g. the float64 noisy signal of a mix)."""
+        return ClipBatch(data, self.offsets, self.lengths, self.max_length, self.offsets_host, self.lengths_host)
+
+    def unpack(self, data: Optional[torch.Tensor] = None):
+        """List of per-clip numpy arrays (of `data`, packed like the audio; default the audio itself)."""
+        h = (self.audio if data is None else data).cpu().numpy()
+        return [h[o:o + n].copy() for o, n in zip(self.offsets_host, self.lengths_host)]
+
+
+@dataclass
+class Noise:
+    """Additive noise fused in front of the MFCC (see ``asr_noise`` in include/asr_b200.h)."""
+    mode: int
+    z: Optional[torch.Tensor] = None        # white: z ; mixture: selector q   (float64, packed like the audio)
+    z2: Optional[torch.Tensor] = None       # mixture: carrier g
+    sigma: Optional[torch.Tensor] = None    # white: float64 [B]
+    p: float = 0.0
+    sigma0: float = 0.0
+    sigma1: float = 0.0
+
+    @staticmethod
+    def white(z: torch.Tensor, sigma: torch.Tensor) -> "Noise":
+        return Noise(_lib.ASR_NOISE_WHITE, z=z, sigma=sigma)
+
+    @staticmethod
+    def mixture(q: torch.Tensor, g: torch.Tensor, p: float, alpha: float) -> "Noise":
+        # add_noise: sigma0 = alpha ; sigma1 = 10 * alpha   (VDR/attacks.py:176-178)
+        return Noise(_lib.ASR_NOISE_MIXTURE, z=q, z2=g, p=float(p), sigma0=alpha, sigma1=10 * alpha)
+
+    def to_c(self) -> NoiseC:
+        for t in (self.z, self.z2, self.sigma):
+            if t is not None and (t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous()):
+                raise TypeError("noise streams / sigma must be contiguous float64 CUDA tensors")
+        return NoiseC(mode=self.mode, reserved=0, z_dev=_ptr(self.z), z2_dev=_ptr(self.z2), sigma_dev=_ptr(self.sigma),
+                      p=self.p, sigma0=self.sigma0, sigma1=self.sigma1)
+
+
+class MfccPlan:
+    """Immutable tables for one parameter set (wraps ``asr_plan``)."""
+
+    def __init__(self, params: MfccParams, device: Optional[int] = None):
+        _require_cuda()
+        self.params = params
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            pc = params.to_c()
+            check(lib.asr_plan_create(C.byref(pc), C.byref(self._h)), "asr_plan_create")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            lib.asr_plan_destroy(h)
+            self._h = None
+
+    @property
+    def feature_rows(self) -> int:
+        return lib.asr_plan_feature_rows(self._h)
+
+    @property
+    def uses_fft(self) -> bool:
+        return bool(lib.asr_plan_uses_fft(self._h))
+
+    def num_frames(self, length: int) -> int:
+        return lib.asr_plan_num_frames(self._h, int(length))
+
+    def tables(self) -> dict:
+        p = self.params
+        n_bins = 1 + p.n_fft // 2
+        window = np.zeros(p.n_fft, np.float32)
+        mel = np.zeros((p.n_mels, n_bins), np.float32)
+        dct = np.zeros((p.n_mfcc, p.n_mels), np.float32)
+        taps = np.zeros((max(p.delta_orders, 1), p.delta_width), np.float32)
+        check(lib.asr_plan_get_tables(self._h, window.ctypes.data, mel.ctypes.data, dct.ctypes.data, taps.ctypes.data),
+              "asr_plan_get_tables")
+        return {"window": window, "mel": mel, "dct": dct, "delta_taps": taps[:p.delta_orders]}
+
+    def _launch(self, fn, what, batch: ClipBatch, out_frames, noise, out, out_dtype, status, rows):
+        B = batch.n_clips
+        dev = batch.audio.device
+        if out is None:
+            out = torch.empty((B, rows, out_frames), dtype=out_dtype, device=dev)
+        elif out.shape != (B, rows, out_frames) or not out.is_contiguous() or not out.is_cuda:
+            raise ValueError(f"out must be a contiguous CUDA tensor of shape {(B, rows, out_frames)}")
+        if status is None:
+            status = torch.empty(B, dtype=torch.int32, device=dev)
+        nz = noise.to_c() if noise is not None else None
+        with torch.cuda.device(dev):
+            args = [self._h, batch.audio.data_ptr(), batch.dtype_code, batch.offsets.data_ptr(), batch.lengths.data_ptr(),
+                    B, batch.max_length, C.byref(nz) if nz is not None else None, out.data_ptr()]
+            if fn is lib.asr_mfcc_batch:
+                args.append(_DT[out.dtype])
+            args += [out_frames, status.data_ptr(), _stream()]
+            check(fn(*args), what)
+        return out, status
+
+    def mfcc(self, batch: ClipBatch, out_frames: Optional[int] = None, noise: Optional[Noise] = None,
+             out: Optional[torch.Tensor] = None, out_dtype=torch.float32, status: Optional[torch.Tensor] = None):
+        """Fused MFCC of every clip -> ``(B, rows, out_frames)`` (+ per-clip int32 status), asynchronous."""
+        if out_frames is None:
+            out_frames = max(1, self.num_frames(batch.max_length))
+        if out is not None:
+            out_dtype = out.dtype
+        return self._launch(lib.asr_mfcc_batch, "asr_mfcc_batch", batch, int(out_frames), noise, out, out_dtype, status,
+                            self.feature_rows)
+
+    def logmel(self, batch: ClipBatch, out_frames: Optional[int] = None, noise: Optional[Noise] = None):
+        """Stage probe: the clamped log-mel matrix ``(B, n_mels, out_frames)`` in float32."""
+        if out_frames is None:
+            out_frames = max(1, self.num_frames(batch.max_length))
+        return self._launch(lib.asr_logmel_batch, "asr_logmel_batch", batch, int(out_frames), noise, None, torch.float32,
+                            None, self.params.n_mels)
+
+    def mfcc_host(self, audio: np.ndarray, offsets: np.ndarray, lengths: np.ndarray, out_frames: int,
+                  snr_db: Optional[float] = None, seed: int = 0, out: Optional[np.ndarray] = None,
+                  out_dtype=np.float64):
+        """``asr_mfcc_batch_host``: host buffers in, reference-layout ``(N, rows*out_frames)`` host matrix out."""
+        audio = np.ascontiguousarray(audio)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        n = lengths.shape[0]
+        if out is None:
+            out = np.empty((n, self.feature_rows * out_frames), dtype=out_dtype)
+        status = np.zeros(n, dtype=np.int32)
+        code = {np.dtype(np.int16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}[audio.dtype]
+        ocode = {np.dtype(np.float32): 1, np.dtype(np.float64): 2}[out.dtype]
+        with torch.cuda.device(self.device):
+            check(lib.asr_mfcc_batch_host(self._h, audio.ctypes.data, code, offsets.ctypes.data, lengths.ctypes.data, n,
+                                          0 if snr_db is None else 1, 0.0 if snr_db is None else float(snr_db),
+                                          int(seed), out.ctypes.data, ocode, int(out_frames), status.ctypes.data),
+                  "asr_mfcc_batch_host")
+        return out, status
+
+
+# ---- noise path --------------------------------------------------------------------------------------
+def clip_power(batch: ClipBatch) -> torch.Tensor:
+    """``np.mean(sample**2)`` per clip in float32, numpy's pairwise order (bit-exact)."""
+    out = torch.empty(batch.n_clips, dtype=torch.float32, device=batch.audio.device)
+    with torch.cuda.device(batch.audio.device):
+        check(lib.asr_clip_power(batch.audio.data_ptr(), batch.dtype_code, batch.offsets.data_ptr(),
+                                 batch.lengths.data_ptr(), batch.n_clips, out.data_ptr(), _stream()), "asr_clip_power")
+    return out
+
+
+def snr_sigma_host(power: np.ndarray, target_snr_db) -> np.ndarray:
+    """The reference's own scalar lines (VDR/attacks.py:235-241) run on ``P``: bit-exact sigma.
+
+    ``power`` is the float32 vector from :func:`clip_power`; numpy scalar semantics keep every step in
+    float32 exactly as ``add_white_noise_with_snr`` does for float32 audio.
+    """
+    out = np.empty(power.shape[0], dtype=np.float64)
+    for i in range(power.shape[0]):
+        signal_avg_watts = power[i]                       # np.float32 scalar
+        signal_avg_db = 10 * np.log10(signal_avg_watts)
+        noise_avg_db = signal_avg_db - target_snr_db
+        noise_avg_watts = 10 ** (noise_avg_db / 10)
+        out[i] = float(np.sqrt(noise_avg_watts))
+    return out
+
+
+def snr_sigma_device(power: torch.Tensor, target_snr_db: float) -> torch.Tensor:
+    """Same chain evaluated on the device (float64 evaluation rounded to float32 at each step)."""
+    out = torch.empty(power.shape[0], dtype=torch.float64, device=power.device)
+    with torch.cuda.device(power.device):
+        check(lib.asr_snr_sigma(power.data_ptr(), float(target_snr_db), out.data_ptr(), power.shape[0], _stream()),
+              "asr_snr_sigma")
+    return out
+
+
+def mix_white(batch: ClipBatch, z: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+    """``float64(x) + sigma[b]*z`` packed like the audio (two roundings, bit-exact with numpy)."""
+    out = torch.zeros(batch.audio.shape[0], dtype=torch.float64, device=batch.audio.device)
+    with torch.cuda.device(batch.audio.device):
+        check(lib.asr_mix_white(batch.audio.data_ptr(), batch.dtype_code, batch.offsets.data_ptr(),
+                                batch.lengths.data_ptr(), batch.n_clips, z.data_ptr(), sigma.data_ptr(), out.data_ptr(),
+                                _stream()), "asr_mix_white")
+    return out
+
+
+def mix_mixture(batch: ClipBatch, q: torch.Tensor, g: torch.Tensor, p: float, alpha: float) -> torch.Tensor:
+    out = torch.zeros(batch.audio.shape[0], dtype=torch.float64, device=batch.audio.device)
+    with torch.cuda.device(batch.audio.device):
+        check(lib.asr_mix_mixture(batch.audio.data_ptr(), batch.dtype_code, batch.offsets.data_ptr(),
+                                  batch.lengths.data_ptr(), batch.n_clips, q.data_ptr(), g.data_ptr(), float(p),
+                                  alpha, 10 * alpha, out.data_ptr(), _stream()), "asr_mix_mixture")
+    return out
+
+
+def mix_rows_white(x: torch.Tensor, z: torch.Tensor, sigma: float) -> torch.Tensor:
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.asr_mix_rows_white(x.data_ptr(), x.numel(), z.data_ptr(), float(sigma), out.data_ptr(), _stream()),
+              "asr_mix_rows_white")
+    return out
+
+
+def mix_rows_mixture(x: torch.Tensor, q: torch.Tensor, g: torch.Tensor, p: float, alpha: float) -> torch.Tensor:
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.asr_mix_rows_mixture(x.data_ptr(), x.numel(), q.data_ptr(), g.data_ptr(), float(p), alpha, 10 * alpha,
+                                       out.data_ptr(), _stream()), "asr_mix_rows_mixture")
+    return out
+
+
+def randn(seed: int, first_index: int, n: int, device="cuda") -> torch.Tensor:
+    """Seeded float64 standard-normal stream; element i depends only on (seed, first_index + i)."""
+    _require_cuda()
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    with torch.cuda.device(out.device):
+        check(lib.asr_randn_f64(int(seed), int(first_index), int(n), out.data_ptr(), _stream()), "asr_randn_f64")
+    return out
+
+
+# ---- standardisation ---------------------------------------------------------------------------------
+class Standardizer:
+    """``StandardScaler().fit_transform`` over row blocks that may live on several GPUs.
+
+    ``fit`` runs sklearn's two passes on this rank's row blocks and - when a
+    ``torch.distributed`` process group is given - all-reduces the float64
+    accumulators (``[n, sum x]`` then ``[sum (x-mean), sum (x-mean)^2]``) over
+    NCCL/NVLink between the passes, so every rank ends with the statistics of the
+    whole dataset (``standardize_dataset``, VDR/attacks.py:48-69).
+    """
+
+    def __init__(self, n_cols: int, device="cuda", group=None, distributed: bool = False):
+        self.n_cols = int(n_cols)
+        self.device = torch.device(device)
+        self.group = group
+        self.distributed = distributed
+        self.mean = self.var = self.scale = None
+        self.n_total = 0
+
+    def _allreduce(self, t: torch.Tensor) -> None:
+        if self.distributed:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    @staticmethod
+    def _mat(x: torch.Tensor):
+        if x.dim() != 2 or x.stride(1) != 1 or x.dtype not in (torch.float32, torch.float64):
+            raise ValueError("row blocks must be 2-D float32/float64 with unit column stride")
+        return x.data_ptr(), _DT[x.dtype], x.shape[0], x.shape[1], x.stride(0)
+
+    def fit(self, blocks: Sequence[torch.Tensor], n_total: Optional[int] = None) -> "Standardizer":
+        """`n_total` (rows over ALL ranks) may be given when the caller knows it; that avoids the one
+        device->host read of the all-reduced count and keeps the whole fit asynchronous."""
+        D = self.n_cols
+        blocks = [x for x in blocks if x.shape[0] > 0]
+        with torch.cuda.device(self.device):
+            acc1 = torch.zeros(D + 1, dtype=torch.float64, device=self.device)   # [sum x (D), n]
+            for x in blocks:
+                p, dt, r, c, ld = self._mat(x)
+                assert c == D
+                check(lib.asr_cmvn_colsum(p, dt, r, c, ld, acc1.data_ptr(), _stream()), "asr_cmvn_colsum")
+                acc1[D] += r
+            self._allreduce(acc1)
+            self.n_total = int(round(acc1[D].item())) if n_total is None else int(n_total)
+            self.mean = torch.empty(D, dtype=torch.float64, device=self.device)
+            check(lib.asr_cmvn_mean(acc1.data_ptr(), self.n_total, D, self.mean.data_ptr(), _stream()), "asr_cmvn_mean")
+            acc2 = torch.zeros(2 * D, dtype=torch.float64, device=self.device)
+            for x in blocks:
+                p, dt, r, c, ld = self._mat(x)
+                check(lib.asr_cmvn_colsum_centered(p, dt, r, c, ld, self.mean.data_ptr(), acc2.data_ptr(), _stream()),
+                      "asr_cmvn_colsum_centered")
+            self._allreduce(acc2)
+            self.var = torch.empty(D, dtype=torch.float64, device=self.device)
+            self.scale = torch.empty(D, dtype=torch.float64, device=self.device)
+            check(lib.asr_cmvn_finalize(acc2.data_ptr(), self.mean.data_ptr(), self.n_total, D, self.var.data_ptr(),
+                                        self.scale.data_ptr(), _stream()), "asr_cmvn_finalize")
+        return self
+
+    def transform(self, x: torch.Tensor, out_dtype=torch.float64) -> torch.Tensor:
+        p, dt, r, c, ld = self._mat(x)
+        out = torch.empty((r, c), dtype=out_dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.asr_cmvn_apply(p, dt, r, c, ld, self.mean.data_ptr(), self.scale.data_ptr(), out.data_ptr(),
+                                     _DT[out_dtype], _stream()), "asr_cmvn_apply")
+        return out

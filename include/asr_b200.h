@@ -1,0 +1,216 @@
+/*
+ * asr_b200.h - C-ABI of the B200-native (sm_100a) MFCC / noise-mix / standardisation path.
+ *
+ * The reference (fmazilu/ASR-using-robust-NN) is pure Python and has no FFI of its
+ * own; its boundary for this path is a handful of module-level Python functions.
+ * Each entry point below names the reference function (file:line) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes stub a maintainer adds on the reference
+ * side.  Abbreviations: VDR = "Voice digit recogniton/", SR = "Speaker recognition/".
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures: device and host buffers are `void*`
+ *     or typed pointers, the stream is a `void*` holding a `cudaStream_t` (NULL = default).
+ *   - every buffer is CALLER-allocated; the library never frees caller memory.
+ *   - `*_dev` arguments are device pointers on the current CUDA device; launches are
+ *     asynchronous and ordered on the given stream.  `asr_*_host` entry points take
+ *     host pointers and are synchronous.
+ *   - every function returns an `asr_status` (0 = ok, negative = error); the message
+ *     of the last error on the calling thread is `asr_last_error()`.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point
+ *     returns ASR_ERR_CUDA.
+ */
+#ifndef ASR_B200_H_
+#define ASR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASR_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum asr_status {
+  ASR_OK = 0,
+  ASR_ERR_INVALID = -1,     /* bad argument / unsupported parameter combination */
+  ASR_ERR_CUDA = -2,        /* CUDA runtime error (see asr_last_error) */
+  ASR_ERR_TOO_LARGE = -3,   /* a clip needs more shared memory than one SM has */
+  ASR_ERR_ALLOC = -4
+} asr_status;
+
+/* per-clip status written by asr_mfcc_batch (the reference raises a Python exception) */
+enum {
+  ASR_CLIP_OK = 0,
+  ASR_CLIP_TOO_SHORT = 1,        /* reflect padding needs len > n_fft/2 (np.pad raises) */
+  ASR_CLIP_TOO_FEW_FRAMES = 2    /* deltas need >= delta_width frames (librosa.feature.delta raises) */
+};
+
+typedef enum asr_dtype { ASR_I16 = 0, ASR_F32 = 1, ASR_F64 = 2 } asr_dtype;
+typedef enum asr_window { ASR_WIN_HANN = 0, ASR_WIN_HAMMING = 1 } asr_window;
+typedef enum asr_pad_mode { ASR_PAD_REFLECT = 0, ASR_PAD_CONSTANT = 1 } asr_pad_mode;
+typedef enum asr_fftfreq_mode { ASR_FFTFREQ_LINSPACE = 0, ASR_FFTFREQ_RFFTFREQ = 1 } asr_fftfreq_mode;
+
+/*
+ * Every keyword of librosa.feature.mfcc / melspectrogram / stft that the reference's
+ * call sites fix (VDR/extract_features_construct_dataset.py:30 - all defaults;
+ * SR/extract_features_construct_dataset.py:227-228 - n_fft = win_length = 441,
+ * hop_length = 220) or BASELINE.json's configs vary.  htk=False, mel norm='slaney',
+ * power=2, ref=1, dct_type=2, dct norm='ortho' are fixed (the reference never
+ * changes them).
+ */
+typedef struct asr_mfcc_params {
+  int32_t sr;            /* sampling rate the mel scale is built for (22050) */
+  int32_t n_fft;         /* 2048 */
+  int32_t win_length;    /* 0 -> n_fft */
+  int32_t hop_length;    /* 512 */
+  int32_t window;        /* asr_window */
+  int32_t center;        /* 1 */
+  int32_t pad_mode;      /* asr_pad_mode; librosa 0.9: reflect */
+  int32_t fftfreq_mode;  /* asr_fftfreq_mode; librosa 0.9: linspace */
+  int32_t n_mels;        /* 128 */
+  int32_t n_mfcc;        /* 20 */
+  float fmin;            /* 0 */
+  float fmax;            /* 0 -> sr/2 */
+  float top_db;          /* 80; < 0 -> no clamp */
+  float amin;            /* 1e-10 */
+  float lifter;          /* 0 -> none */
+  float preemph;         /* 0 -> none (librosa.effects.preemphasis coef otherwise) */
+  int32_t delta_orders;  /* 0, 1 (append delta) or 2 (append delta and delta-delta) */
+  int32_t delta_width;   /* 9 */
+} asr_mfcc_params;
+
+/*
+ * Additive noise fused in front of the MFCC, applied to the decoded audio exactly as
+ * the reference does before calling librosa.feature.mfcc:
+ *   WHITE    x + sigma[b]*z          VDR/attacks.py:73-86 (add_white_noise) and :222-245
+ *                                    (add_white_noise_with_snr, sigma[b] from the SNR chain)
+ *   MIXTURE  x + (|q|<p ? s1:s0)*g   VDR/attacks.py:145-183 (mixtgauss / add_noise)
+ * z / q / g are float64 standard-normal streams laid out like the audio (same offsets).
+ * The mix is done in float64 with two separately rounded operations (no FMA), then
+ * rounded once to float32 for the MFCC arithmetic.
+ */
+typedef enum asr_noise_mode { ASR_NOISE_NONE = 0, ASR_NOISE_WHITE = 1, ASR_NOISE_MIXTURE = 2 } asr_noise_mode;
+
+typedef struct asr_noise {
+  int32_t mode;              /* asr_noise_mode */
+  int32_t reserved;
+  const double* z_dev;       /* WHITE: z ; MIXTURE: selector stream q */
+  const double* z2_dev;      /* MIXTURE: carrier stream g */
+  const double* sigma_dev;   /* WHITE: per-clip sigma [n_clips] */
+  double p;                  /* MIXTURE: probability threshold  */
+  double sigma0;             /* MIXTURE: background sigma (alpha) */
+  double sigma1;             /* MIXTURE: impulse sigma (10*alpha) */
+} asr_noise;
+
+typedef struct asr_plan asr_plan;
+
+int asr_version(void);
+const char* asr_last_error(void);
+int asr_device_count(void);
+
+/* ---- plan: immutable tables (window, FFT twiddles, sparse mel bank, DCT*lifter, delta taps)
+ *      built on the host in float64, stored in float32 on the current device. ------------- */
+int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_out);
+void asr_plan_destroy(asr_plan* plan);
+/* T = 1 + (len + 2*(n_fft/2) - n_fft)/hop for center=1 (0 when the clip cannot be framed) */
+int32_t asr_plan_num_frames(const asr_plan* plan, int64_t length);
+/* n_mfcc * (1 + delta_orders) */
+int32_t asr_plan_feature_rows(const asr_plan* plan);
+/* 1 = radix-2 register FFT (n_fft in {512,1024,2048}); 0 = direct DFT (any n_fft, e.g. 441) */
+int32_t asr_plan_uses_fft(const asr_plan* plan);
+/* copies of the float32 tables, for table-level parity tests (host pointers; NULL to skip) */
+int asr_plan_get_tables(const asr_plan* plan, float* window /*n_fft*/, float* mel_dense /*n_mels*(1+n_fft/2)*/,
+                        float* dct /*n_mfcc*n_mels, lifter folded in*/, float* delta_taps /*orders*width*/);
+
+/*
+ * Batched fused MFCC.  Replaces the per-file loop + librosa.feature.mfcc call of
+ *   extract_features / compute_mfcc_all_files   VDR/extract_features_construct_dataset.py:24-39,144-150
+ *   load_audio_dataset_and_labels               SR/extract_features_construct_dataset.py:224-232
+ *   black_box_attack_on_audio[_snr]             VDR/attacks.py:89-121,248-274 ; SR/attacks.py:97-146,254-295
+ * One launch: [noise mix] -> [pre-emphasis] -> reflect-pad framing -> window -> real FFT ->
+ * power -> sparse mel -> 10*log10 -> clip-wide top_db clamp -> DCT-II(ortho) -> lifter ->
+ * [delta, delta-delta] -> truncate / zero-pad to out_frames.
+ *
+ *   audio_dev    packed samples of dtype `dtype`; clip b = audio[offsets[b] .. offsets[b]+lengths[b])
+ *   offsets_dev  int64 [n_clips] element offsets, lengths_dev int32 [n_clips]
+ *   max_length   max over lengths (host knows it; sizes shared memory)
+ *   noise        NULL or a descriptor (device pointers)
+ *   out_dev      [n_clips][rows][out_frames] of out_dtype (ASR_F32 or ASR_F64), rows = feature_rows;
+ *                flattening a clip's block row-major gives the reference's (n_mfcc*T,) row
+ *                (VDR/extract...py:149).  Frames >= T are zero (VDR/extract...py:36-37).
+ *   status_dev   int32 [n_clips] or NULL
+ */
+int asr_mfcc_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
+                   const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
+                   void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev, void* stream);
+
+/* Stage-level probe for parity tests: the clamped log-mel matrix [n_clips][n_mels][out_frames] (float32). */
+int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
+                     const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
+                     float* out_dev, int32_t out_frames, int32_t* status_dev, void* stream);
+
+/* ---- noise path (VDR/attacks.py:73-86,145-183,222-245 ; SR/attacks.py:81-94,149-189,228-251) ---- */
+
+/* P[b] = np.mean(sample**2) in float32, in numpy's pairwise summation order - bit-exact
+ * (VDR/attacks.py:234).  audio dtype ASR_I16 (value/32768) or ASR_F32. */
+int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
+                   int32_t n_clips, float* power_dev, void* stream);
+
+/* sigma[b] = sqrt(10**((10*log10(P[b]) - snr_db)/10)) with every step rounded to float32
+ * (VDR/attacks.py:235-241 under numpy >= 2 scalar rules), evaluated on the device in float64
+ * and rounded; the host-exact alternative is to run those four numpy lines on P. */
+int asr_snr_sigma(const float* power_dev, float target_snr_db, double* sigma_dev, int32_t n_clips, void* stream);
+
+/* out = float64(x) + sigma[b]*z   (two roundings, no FMA) - VDR/attacks.py:84-85, :241-244 */
+int asr_mix_white(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
+                  int32_t n_clips, const double* z_dev, const double* sigma_dev, double* out_dev, void* stream);
+
+/* out = float64(x) + (|q|<p ? sigma1 : sigma0)*g - VDR/attacks.py:159-181 */
+int asr_mix_mixture(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
+                    int32_t n_clips, const double* q_dev, const double* g_dev, double p, double sigma0,
+                    double sigma1, double* out_dev, void* stream);
+
+/* Feature-domain variants on an (n_rows, n_cols) float64 matrix, one sigma for all rows
+ * (add_white_noise_on_dataset / add_noise_mixture_on_dataset, VDR/attacks.py:186-219). */
+int asr_mix_rows_white(const double* x_dev, int64_t n, const double* z_dev, double sigma, double* out_dev, void* stream);
+int asr_mix_rows_mixture(const double* x_dev, int64_t n, const double* q_dev, const double* g_dev, double p,
+                         double sigma0, double sigma1, double* out_dev, void* stream);
+
+/* Seeded standard-normal stream generated on the device (Philox4x32-10 + Box-Muller),
+ * element i depends only on (seed, first_index + i): shard- and batch-size independent. */
+int asr_randn_f64(uint64_t seed, uint64_t first_index, int64_t n, double* out_dev, void* stream);
+
+/* ---- standardisation ("CMVN"): standardize_dataset, VDR/attacks.py:48-69 (StandardScaler) ----
+ * Two passes like sklearn's _incremental_mean_and_var:
+ *   pass 1  acc1[c]   += sum_r x[r][c]
+ *   pass 2  acc2[c]   += sum_r (x[r][c]-mean[c]) ; acc2[n_cols+c] += sum_r (x[r][c]-mean[c])^2
+ * The accumulators are float64 device vectors the caller zeroes and - when rows are sharded
+ * over GPUs - all-reduces (sum) between the passes.  x is row-major with leading dimension ld. */
+int asr_cmvn_colsum(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld,
+                    double* acc1_dev, void* stream);
+int asr_cmvn_mean(const double* acc1_dev, int64_t n_total, int32_t n_cols, double* mean_dev, void* stream);
+int asr_cmvn_colsum_centered(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld,
+                             const double* mean_dev, double* acc2_dev, void* stream);
+/* var = acc2sq/n - (acc2/n)^2 ; scale = sqrt(var), 1 where sklearn's _is_constant_feature holds */
+int asr_cmvn_finalize(const double* acc2_dev, const double* mean_dev, int64_t n_total, int32_t n_cols,
+                      double* var_dev, double* scale_dev, void* stream);
+/* out[r][c] = (x[r][c]-mean[c])/scale[c] ; out dtype ASR_F32 or ASR_F64, leading dimension n_cols */
+int asr_cmvn_apply(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld,
+                   const double* mean_dev, const double* scale_dev, void* out_dev, int32_t out_dtype, void* stream);
+
+/* ---- host-buffer entry points (what a ctypes binding on the reference side calls) ----------
+ * Synchronous; host<->device copies are pipelined in chunks over two streams inside. */
+
+/* compute_mfcc_all_files (VDR/extract...py:144-150) on decoded waveforms: out_host is
+ * [n_clips][rows*out_frames] of out_dtype (ASR_F64 = the reference's np.zeros float64 rows).
+ * snr_mode: 0 none; 1 = add_white_noise_with_snr with target_snr_db and the seeded device
+ * normal stream (seed, clip b uses indices offsets[b]..); sigma chain evaluated on the device. */
+int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host, int32_t dtype, const int64_t* offsets_host,
+                        const int32_t* lengths_host, int32_t n_clips, int32_t snr_mode, float target_snr_db,
+                        uint64_t seed, void* out_host, int32_t out_dtype, int32_t out_frames,
+                        int32_t* status_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASR_B200_H_ */
