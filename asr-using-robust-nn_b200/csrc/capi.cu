@@ -167,8 +167,8 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
   pl->fft_path = fft_shape(p.n_fft, &fs) ? 1 : 0;
   pl->fb = pl->fft_path ? kWarps * (32 / fs.G) : kWarps;
   const int s_off = pl->fft_path ? 0 : round4(p.n_fft);
-  pl->frame_stride = pl->fft_path ? pitch_odd4(2 * (fs.M + fs.G)) : pitch_odd4(s_off + round4(pl->n_bins));
-  pl->chunk_cap = round4((pl->fb - 1) * p.hop_length + p.n_fft);
+  pl->frame_stride = pl->fft_path ? pitch_odd4(2 * (fs.M + fs.G)) : pitch_odd4(s_off + round4(pl->n_bins + 16));
+  pl->chunk_cap = ((pl->fb - 1) * p.hop_length + p.n_fft + 8 + 7) & ~7;   // + up to 7 samples of alignment shift
   pl->lm_pitch = pitch_odd4(p.n_mels);
   pl->dct_pitch = round4(p.n_mels);
   pl->n_streams = kWarps * (32 / pl->fb);
@@ -201,7 +201,8 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
         t.k_start = a + 4 * q0;
         t.n_quads = std::min(kMelChunkQuads, quads - q0);
         t.w_off = static_cast<int>(melw.size() / 4);
-        for (int k = t.k_start; k < t.k_start + 4 * t.n_quads; ++k) melw.push_back(k < pl->n_bins ? row[k] : 0.0f);
+        for (int k = t.k_start; k < t.k_start + 4 * kMelChunkQuads; ++k)   // always 4 quads, zero beyond the support
+          melw.push_back((k < pl->n_bins && k < t.k_start + 4 * t.n_quads) ? row[k] : 0.0f);
         tasks.push_back(t);
       }
     }
@@ -378,6 +379,10 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     kp.noise_mode = noise->mode;
     kp.z = noise->z_dev; kp.z2 = noise->z2_dev; kp.sigma = noise->sigma_dev;
     kp.mix_p = noise->p; kp.mix_s0 = noise->sigma0; kp.mix_s1 = noise->sigma1;
+  }
+  {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    kp.vec_ok = al16(audio_dev) && (kp.noise_mode == ASR_NOISE_NONE || (al16(kp.z) && (kp.noise_mode != ASR_NOISE_MIXTURE || al16(kp.z2))));
   }
   kp.out = out_dev;
   kp.out_f64 = out_dtype == ASR_F64;

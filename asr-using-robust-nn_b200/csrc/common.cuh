@@ -69,6 +69,7 @@ struct KParams {
   int sm_audio, sm_frames, sm_part, sm_lm, sm_cbuf, sm_red;
   int t_cap;          // frame capacity of one CTA's log-mel buffer
   int cluster_size;   // CTAs per clip (thread-block cluster), 1..16
+  int vec_ok;         // audio (and noise) pointers are 16-byte aligned: vector staging allowed
   int cbuf_pitch;
 };
 

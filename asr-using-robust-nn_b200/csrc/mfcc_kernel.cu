@@ -206,7 +206,7 @@ __device__ __forceinline__ void frame_power_fft(const float* __restrict__ xs, co
       fbuf[M - k] = fmaf(yr, yr, yi * yi);
     }
   if (l == 0) fbuf[M / 2] = fmaf(ur[0][G / 2], ur[0][G / 2], ui[0][G / 2] * ui[0][G / 2]);
-  if (l >= 1 && l <= 3) fbuf[M + l] = 0.0f;   // float4 tail read by the mel stage
+  if (l < 16) fbuf[M + 1 + l] = 0.0f;         // tail read by the (fixed 4-quad) mel tasks
 }
 
 // Direct DFT for any n_fft (the reference's speaker preset uses n_fft = 441 = 3^2 * 7^2).
@@ -244,8 +244,7 @@ __device__ __forceinline__ void frame_power_dft(const float* __restrict__ xs, co
       if (kk < n_bins) fbuf[s_off + kk] = fmaf(ar[j], ar[j], ai[j] * ai[j]);
     }
   }
-  const int nb4 = (n_bins + 3) & ~3;
-  if (lane < nb4 - n_bins) fbuf[s_off + n_bins + lane] = 0.0f;
+  if (lane < 16) fbuf[s_off + n_bins + lane] = 0.0f;   // tail read by the (fixed 4-quad) mel tasks
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -280,6 +279,160 @@ __device__ __forceinline__ float signal_at(const KParams& kp, const long long ba
   // librosa.effects.preemphasis: lfilter state zi = 2*y[0]-y[1]  ->  out[0] = y[0] + zi
   const float y1 = sample_at(kp, base + 1, sig);
   return __fadd_rn(x, __fadd_rn(2.0f * x, -y1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staging of one batch's padded signal span into shared memory.
+//
+// The span is cut into groups of 8 samples aligned in the GLOBAL sample index, so every group that
+// lies inside the clip is fetched with 16-byte loads (1 for int16, 2 for float32, 4 for float64) and
+// written with two 16-byte shared stores; s_audio[k] holds global sample g_al + k, the first padded
+// position of the batch sits at s_audio[shift].  Groups that touch a clip edge (reflect / zero
+// padding) or need pre-emphasis take the element-wise path.  For int16 / float32 audio the loads of
+// the NEXT batch are issued before the current batch's FFTs (register prefetch), the noise streams of
+// the next batch are pulled into L2 with prefetch hints.
+struct Stage {
+  long long g_al;   // global element index of s_audio[0] (multiple of 8)
+  int shift;        // s_audio[shift] = padded position t0*hop
+  int n;            // padded samples the batch needs
+  int n_groups;
+};
+
+__device__ __forceinline__ Stage stage_setup(const KParams& kp, const long long base, const int t0, const int nb) {
+  Stage s;
+  const long long g0 = base + static_cast<long long>(t0) * kp.hop - kp.pad;
+  s.g_al = (g0 >= 0 ? g0 : g0 - 7) / 8 * 8;
+  s.shift = static_cast<int>(g0 - s.g_al);
+  s.n = (nb - 1) * kp.hop + kp.n_fft;
+  s.n_groups = (s.shift + s.n + 7) / 8;
+  return s;
+}
+
+__device__ __forceinline__ bool group_inside(const Stage& s, const int gi, const long long base, const int L) {
+  const long long e0 = s.g_al + 8LL * gi;
+  return e0 >= base && e0 + 8 <= base + L;
+}
+
+__device__ __forceinline__ void stage_prefetch(const KParams& kp, const Stage& s, const long long base, const int L,
+                                               const int tid, int4 (&pre)[2][2]) {
+  if (!kp.vec_ok || kp.dtype == ASR_F64 || kp.preemph != 0.0f) return;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int gi = tid + r * kThreads;
+    if (gi < s.n_groups && group_inside(s, gi, base, L)) {
+      const long long e0 = s.g_al + 8LL * gi;
+      if (kp.dtype == ASR_I16) {
+        pre[r][0] = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const short*>(kp.audio) + e0));
+      } else {
+        const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const float*>(kp.audio) + e0);
+        pre[r][0] = __ldg(p);
+        pre[r][1] = __ldg(p + 1);
+      }
+    }
+  }
+  if (kp.noise_mode != ASR_NOISE_NONE) {
+    // one 128-byte line of each noise stream per thread -> L2
+    const long long lines = (static_cast<long long>(s.n_groups) * 64 + 127) / 128;
+    for (long long ln = tid; ln < lines; ln += kThreads) {
+      const long long e = s.g_al + ln * 16;
+      if (e >= base && e < base + L) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.z + e));
+        if (kp.noise_mode == ASR_NOISE_MIXTURE) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.z2 + e));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void unpack_i16(const int4 raw, float (&v)[8]) {
+  const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = static_cast<float>(static_cast<short>(w[j] & 0xffff)) * (1.0f / 32768.0f);
+    v[2 * j + 1] = static_cast<float>(w[j] >> 16) * (1.0f / 32768.0f);
+  }
+}
+
+// one group of 8 samples -> s_audio[8*gi .. 8*gi+8)
+__device__ __forceinline__ void stage_group(const KParams& kp, const Stage& s, const long long base, const int L,
+                                            const double sig, const int gi, const bool have_pre, const int4 pre0,
+                                            const int4 pre1, float* __restrict__ s_audio) {
+  const long long e0 = s.g_al + 8LL * gi;
+  float v[8];
+  if (kp.vec_ok && kp.preemph == 0.0f && group_inside(s, gi, base, L)) {
+    double xd[8];
+    if (kp.dtype == ASR_I16) {
+      const int4 raw = have_pre ? pre0 : __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const short*>(kp.audio) + e0));
+      unpack_i16(raw, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xd[j] = static_cast<double>(v[j]);
+    } else if (kp.dtype == ASR_F32) {
+      const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const float*>(kp.audio) + e0);
+      const int4 a = have_pre ? pre0 : __ldg(p);
+      const int4 b = have_pre ? pre1 : __ldg(p + 1);
+      v[0] = __int_as_float(a.x); v[1] = __int_as_float(a.y); v[2] = __int_as_float(a.z); v[3] = __int_as_float(a.w);
+      v[4] = __int_as_float(b.x); v[5] = __int_as_float(b.y); v[6] = __int_as_float(b.z); v[7] = __int_as_float(b.w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xd[j] = static_cast<double>(v[j]);
+    } else {
+      const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(kp.audio) + e0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 d = __ldg(p + j);
+        xd[2 * j] = d.x; xd[2 * j + 1] = d.y;
+        v[2 * j] = static_cast<float>(d.x); v[2 * j + 1] = static_cast<float>(d.y);
+      }
+    }
+    if (kp.noise_mode != ASR_NOISE_NONE) {
+      double zz[8];
+      const double2* zp = reinterpret_cast<const double2*>(kp.z + e0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const double2 d = __ldg(zp + j); zz[2 * j] = d.x; zz[2 * j + 1] = d.y; }
+      if (kp.noise_mode == ASR_NOISE_WHITE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = static_cast<float>(__dadd_rn(xd[j], __dmul_rn(sig, zz[j])));
+      } else {
+        const double2* gp = reinterpret_cast<const double2*>(kp.z2 + e0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 g = __ldg(gp + j);
+          const double s0 = (fabs(zz[2 * j]) < kp.mix_p) ? kp.mix_s1 : kp.mix_s0;
+          const double s1 = (fabs(zz[2 * j + 1]) < kp.mix_p) ? kp.mix_s1 : kp.mix_s0;
+          v[2 * j] = static_cast<float>(__dadd_rn(xd[2 * j], __dmul_rn(s0, g.x)));
+          v[2 * j + 1] = static_cast<float>(__dadd_rn(xd[2 * j + 1], __dmul_rn(s1, g.y)));
+        }
+      }
+    }
+  } else {
+    // clip edge (reflect / zero padding), unaligned buffers or pre-emphasis: element-wise
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      const int i = 8 * gi + j - s.shift;            // padded position relative to the batch start
+      long long o = e0 + j - base;                   // original sample index
+      float x = 0.0f;
+      if (i >= 0 && i < s.n) {
+        bool ok = true;
+        if (o < 0) { if (kp.pad_mode == ASR_PAD_REFLECT) o = -o; else ok = false; }
+        else if (o >= L) { if (kp.pad_mode == ASR_PAD_REFLECT) o = 2LL * (L - 1) - o; else ok = false; }
+        if (ok) x = signal_at(kp, base, static_cast<int>(o), sig);
+      }
+      s_audio[8 * gi + j] = x;
+    }
+    return;
+  }
+  float4* dst = reinterpret_cast<float4*>(s_audio + 8 * gi);
+  dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+  dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+__device__ __forceinline__ void stage_commit(const KParams& kp, const Stage& s, const long long base, const int L,
+                                             const double sig, const int tid, const int4 (&pre)[2][2],
+                                             float* __restrict__ s_audio) {
+  const bool have_pre = kp.vec_ok && kp.dtype != ASR_F64 && kp.preemph == 0.0f;
+  if (tid < s.n_groups) stage_group(kp, s, base, L, sig, tid, have_pre, pre[0][0], pre[0][1], s_audio);
+  if (tid + kThreads < s.n_groups)
+    stage_group(kp, s, base, L, sig, tid + kThreads, have_pre, pre[1][0], pre[1][1], s_audio);
+  for (int gi = tid + 2 * kThreads; gi < s.n_groups; gi += kThreads)
+    stage_group(kp, s, base, L, sig, gi, false, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), s_audio);
 }
 
 __device__ __forceinline__ int num_frames_dev(const KParams& kp, const int L) {
@@ -353,27 +506,26 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 2 : 1)) mfcc_kernel(c
   for (int i = tid; i < nF * kp.lm_pitch; i += kThreads) s_lm[i] = 0.0f;
 
   const double sig = (kp.noise_mode == ASR_NOISE_WHITE) ? kp.sigma[b] : 0.0;
-  const int FB = kp.fb;
+  const int FB = kp.fb;                             // 8 or 16
+  const int fb_sh = (FB == 16) ? 4 : 3;
   const int s_off = (NFFT == 0) ? ((kp.n_fft + 3) & ~3) : 0;
   float run_max = -3.0e38f;
 
+  int4 pre[2][2];
+  pre[0][0] = pre[0][1] = pre[1][0] = pre[1][1] = make_int4(0, 0, 0, 0);
+  Stage sg = stage_setup(kp, base, f0, min(FB, max(nF, 1)));
+  if (nF > 0) stage_prefetch(kp, sg, base, L, tid, pre);
+
   for (int t0 = f0; t0 < f1; t0 += FB) {
     const int nb = min(FB, f1 - t0);
-    // ---- stage the padded signal span of this batch ----
-    {
-      const int p0 = t0 * kp.hop;
-      const int n = (nb - 1) * kp.hop + kp.n_fft;
-      for (int i = tid; i < n; i += kThreads) {
-        int o = p0 + i - kp.pad;
-        float v = 0.0f;
-        bool ok = true;
-        if (o < 0) { if (kp.pad_mode == ASR_PAD_REFLECT) o = -o; else ok = false; }
-        else if (o >= L) { if (kp.pad_mode == ASR_PAD_REFLECT) o = 2 * (L - 1) - o; else ok = false; }
-        if (ok) v = signal_at(kp, base, o, sig);
-        s_audio[i] = v;
-      }
-    }
+    // ---- stage the padded signal span of this batch (s_audio[shift] = padded position t0*hop) ----
+    stage_commit(kp, sg, base, L, sig, tid, pre, s_audio);
+    const int shift = sg.shift;
     __syncthreads();
+    if (t0 + FB < f1) {                              // next batch's loads fly during this batch's FFTs
+      sg = stage_setup(kp, base, t0 + FB, min(FB, f1 - t0 - FB));
+      stage_prefetch(kp, sg, base, L, tid, pre);
+    }
     // ---- frames -> power spectra ----
     if constexpr (NFFT != 0) {
       constexpr int G = FftCfg<NFFT>::G;
@@ -381,30 +533,31 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 2 : 1)) mfcc_kernel(c
       const int fs = warp * GPW + lane / G;
       if (warp * GPW < nb) {
         const int fr = min(fs, nb - 1);            // idle groups recompute the last frame into their own buffer
-        const float* xs = s_audio + fr * kp.hop;
-        const bool aligned2 = ((fr * kp.hop) & 1) == 0;
+        const float* xs = s_audio + shift + fr * kp.hop;
+        const bool aligned2 = ((shift + fr * kp.hop) & 1) == 0;
         frame_power_fft<NFFT>(xs, aligned2, reinterpret_cast<const float2*>(s_window), s_twp, s_twu,
                               s_frames + fs * kp.frame_stride, lane % G);
       }
     } else {
       if (warp < nb)
-        frame_power_dft(s_audio + warp * kp.hop, s_window, s_twu, kp.n_fft, kp.n_bins,
+        frame_power_dft(s_audio + shift + warp * kp.hop, s_window, s_twu, kp.n_fft, kp.n_bins,
                         s_frames + warp * kp.frame_stride, s_off, lane);
     }
     __syncthreads();
     // ---- sparse mel bank: lanes <-> frames of the batch, task streams <-> sub-warps ----
     {
-      const int f = lane % FB;
-      const int stream = warp * (32 / FB) + lane / FB;
+      const int f = lane & (FB - 1);
+      const int stream = (warp << (5 - fb_sh)) + (lane >> fb_sh);
       const float* S = s_frames + f * kp.frame_stride + s_off;
       const int tb = s_sbeg[stream], te = s_sbeg[stream + 1];
       for (int ti = tb; ti < te; ++ti) {
         const int task = s_stasks[ti];
-        const int4 tk = s_tasks[task];             // (filter, k_start, n_quads, w_off)
+        const int4 tk = s_tasks[task];             // (filter, k_start, n_quads, w_off); weights padded to 4 quads
         const float4* s4 = reinterpret_cast<const float4*>(S + tk.y);
         const float4* w4 = s_melw + tk.w;
         float acc = 0.0f;
-        for (int q = 0; q < tk.z; ++q) {
+#pragma unroll
+        for (int q = 0; q < kMelChunkQuads; ++q) {
           const float4 s = s4[q];
           const float4 w = w4[q];
           acc = fmaf(s.x, w.x, acc);
@@ -417,14 +570,18 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 2 : 1)) mfcc_kernel(c
     }
     __syncthreads();
     // ---- combine partials, 10*log10, running clip max ----
-    for (int e = tid; e < nb * kp.n_mels; e += kThreads) {
-      const int f = e % nb, i = e / nb;
-      const int2 ft = s_ftasks[i];
-      float m = 0.0f;
-      for (int j = 0; j < ft.y; ++j) m += s_part[(ft.x + j) * FB + f];
-      const float db = 3.01029995663981195f * __log2f(fmaxf(kp.amin, m));
-      s_lm[(t0 - f0 + f) * kp.lm_pitch + i] = db;
-      run_max = fmaxf(run_max, db);
+    {
+      const int f = tid & (FB - 1);
+      if (f < nb) {
+        for (int i = tid >> fb_sh; i < kp.n_mels; i += kThreads >> fb_sh) {
+          const int2 ft = s_ftasks[i];
+          float m = 0.0f;
+          for (int j = 0; j < ft.y; ++j) m += s_part[(ft.x + j) * FB + f];
+          const float db = 3.01029995663981195f * __log2f(fmaxf(kp.amin, m));
+          s_lm[(t0 - f0 + f) * kp.lm_pitch + i] = db;
+          run_max = fmaxf(run_max, db);
+        }
+      }
     }
     // next batch's staging / FFT do not touch s_part or s_lm; its barriers order the reuse of s_part
   }
