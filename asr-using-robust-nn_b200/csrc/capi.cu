@@ -171,7 +171,6 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
   pl->chunk_cap = ((pl->fb - 1) * p.hop_length + p.n_fft + 8 + 7) & ~7;   // + up to 7 samples of alignment shift
   pl->lm_pitch = pitch_odd4(p.n_mels);
   pl->dct_pitch = round4(p.n_mels);
-  pl->n_streams = kWarps * (32 / pl->fb);
 
   // ---- window: scipy.signal.get_window(name, win_length, fftbins=True), centre-padded to n_fft ----
   pl->h_window.assign(p.n_fft, 0.0f);
@@ -209,24 +208,33 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
     ftasks[2 * i + 1] = static_cast<int>(tasks.size()) - ftasks[2 * i];
   }
   pl->n_tasks = static_cast<int>(tasks.size());
-  // longest-processing-time assignment of tasks to the sub-warp streams
-  std::vector<int> order(pl->n_tasks);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tasks[a].n_quads > tasks[b].n_quads; });
-  std::vector<std::vector<int>> per_stream(pl->n_streams);
-  std::vector<int> load(pl->n_streams, 0);
-  for (int t : order) {
-    const int s = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
-    per_stream[s].push_back(t);
-    load[s] += tasks[t].n_quads + 1;
+  // Task order for the per-warp mel stage: lanes of a quarter-warp read S with 16-byte loads, so tasks that
+  // sit next to each other should start in different 16-byte bank groups ((k_start/4) mod 8); deal them out
+  // round-robin over the 8 residues.  Padded with empty tasks to a multiple of the streams per frame.
+  const int spf = 32 / (pl->fb / kWarps);
+  std::vector<std::vector<int>> bucket(8);
+  for (int t = 0; t < pl->n_tasks; ++t) bucket[(tasks[t].k_start / 4) & 7].push_back(t);
+  std::vector<int> order;
+  for (size_t round = 0; order.size() < tasks.size(); ++round)
+    for (int r = 0; r < 8; ++r)
+      if (round < bucket[r].size()) order.push_back(bucket[r][round]);
+  pl->n_tasks_padded = std::max(spf, (pl->n_tasks + spf - 1) / spf * spf);
+  pl->part_pitch = round4(pl->n_tasks + 1);                    // slot n_tasks swallows the padding tasks
+  std::vector<int> task_tab(2 * static_cast<size_t>(pl->n_tasks_padded), 0);
+  std::vector<float> melw_q(static_cast<size_t>(kMelChunkQuads) * pl->n_tasks_padded * 4, 0.0f);
+  for (int tp = 0; tp < pl->n_tasks_padded; ++tp) {
+    if (tp < pl->n_tasks) {
+      const int t = order[tp];
+      task_tab[2 * tp] = tasks[t].k_start;
+      task_tab[2 * tp + 1] = t;
+      for (int q = 0; q < kMelChunkQuads; ++q)
+        for (int e = 0; e < 4; ++e)
+          melw_q[(static_cast<size_t>(q) * pl->n_tasks_padded + tp) * 4 + e] = melw[(static_cast<size_t>(tasks[t].w_off) + q) * 4 + e];
+    } else {
+      task_tab[2 * tp] = 0;
+      task_tab[2 * tp + 1] = pl->n_tasks;
+    }
   }
-  std::vector<int> sbeg(pl->n_streams + 1, 0), stasks;
-  for (int s = 0; s < pl->n_streams; ++s) {
-    std::sort(per_stream[s].begin(), per_stream[s].end());
-    sbeg[s] = static_cast<int>(stasks.size());
-    stasks.insert(stasks.end(), per_stream[s].begin(), per_stream[s].end());
-  }
-  sbeg[pl->n_streams] = static_cast<int>(stasks.size());
   // ---- DCT-II ortho rows [0, n_mfcc) with the lifter folded in ----
   pl->h_dct.assign(static_cast<size_t>(p.n_mfcc) * p.n_mels, 0.0f);
   std::vector<float> dct_p(static_cast<size_t>(p.n_mfcc) * pl->dct_pitch, 0.0f);
@@ -291,12 +299,15 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
     return off;
   };
   pl->off_window = put_f(pl->h_window.data(), pl->h_window.size());
+  {
+    std::vector<float> wi(pl->h_window);
+    for (float& v : wi) v *= (1.0f / 32768.0f);      // exact: int16 samples are scaled through the window
+    pl->off_window_i16 = put_f(wi.data(), wi.size());
+  }
   pl->off_twp = put_f(twp.data(), twp.size());
   pl->off_twu = put_f(twu.data(), twu.size());
-  pl->off_tasks = put_i(reinterpret_cast<const int*>(tasks.data()), tasks.size() * 4);
-  pl->off_melw = put_f(melw.data(), melw.size());
-  pl->off_sbeg = put_i(sbeg.data(), sbeg.size());
-  pl->off_stasks = put_i(stasks.data(), stasks.size());
+  pl->off_tasks = put_i(task_tab.data(), task_tab.size());
+  pl->off_melw = put_f(melw_q.data(), melw_q.size());
   pl->off_ftasks = put_i(ftasks.data(), ftasks.size());
   pl->off_dct = put_f(dct_p.data(), dct_p.size());
   pl->off_taps = put_f(pl->h_taps.data(), pl->h_taps.size());
@@ -396,12 +407,12 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
   kp.top_db = p.top_db; kp.amin = p.amin; kp.preemph = p.preemph;
   kp.lm_pitch = plan->lm_pitch; kp.dct_pitch = plan->dct_pitch;
   kp.fft_path = plan->fft_path; kp.fb = plan->fb; kp.frame_stride = plan->frame_stride; kp.chunk_cap = plan->chunk_cap;
-  kp.n_tasks = plan->n_tasks; kp.n_streams = plan->n_streams;
+  kp.n_tasks = plan->n_tasks; kp.n_tasks_padded = plan->n_tasks_padded; kp.part_pitch = plan->part_pitch;
   kp.blob = reinterpret_cast<const float4*>(plan->blob_dev);
   kp.blob_f4 = plan->blob_floats / 4;
-  kp.off_window = plan->off_window; kp.off_twp = plan->off_twp; kp.off_twu = plan->off_twu;
-  kp.off_tasks = plan->off_tasks; kp.off_melw = plan->off_melw; kp.off_sbeg = plan->off_sbeg;
-  kp.off_stasks = plan->off_stasks; kp.off_ftasks = plan->off_ftasks; kp.off_dct = plan->off_dct;
+  kp.off_window = plan->off_window; kp.off_window_i16 = plan->off_window_i16; kp.off_twp = plan->off_twp; kp.off_twu = plan->off_twu;
+  kp.off_tasks = plan->off_tasks; kp.off_melw = plan->off_melw;
+  kp.off_ftasks = plan->off_ftasks; kp.off_dct = plan->off_dct;
   kp.off_taps = plan->off_taps;
   // ---- cluster size + dynamic shared memory layout ----
   // One CTA holds the log-mel rows of ceil(T/cs) frames; grow the cluster until that fits, then keep
@@ -412,9 +423,8 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
   auto layout = [&](int cs, KParams& k) -> long long {
     const int t_cap = (t_all + cs - 1) / cs;
     int off = plan->blob_floats;
-    k.sm_audio = off; off += plan->chunk_cap;
     k.sm_frames = off; off += plan->fb * plan->frame_stride;
-    k.sm_part = off; off += round4(std::max(1, plan->n_tasks) * plan->fb);
+    k.sm_part = off; off += plan->fb * plan->part_pitch;
     k.sm_lm = off; off += t_cap * plan->lm_pitch;
     k.cbuf_pitch = round4(t_cap + 2 * half + 1);
     k.sm_cbuf = off; off += want_cbuf ? p.n_mfcc * k.cbuf_pitch : 0;

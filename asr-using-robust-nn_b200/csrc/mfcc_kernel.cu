@@ -1,7 +1,8 @@
 // Fused MFCC kernel for sm_100a: one CTA per clip, frames processed in batches of `fb`.
 //
-//   stage audio chunk (dtype decode, [noise mix], [pre-emphasis], reflect/zero padding) -> smem
-//   per frame: window -> real FFT (register radix-2 DIT passes, one smem exchange) -> |X|^2  (smem)
+//   per frame: samples straight from global/L1 (dtype decode, [noise mix], [pre-emphasis], reflect/zero
+//              padding) -> window -> real FFT (register radix-2 DIT passes, one smem exchange,
+//              shuffle unpack) -> |X|^2  (smem)
 //   per batch: sparse mel bank (lanes <-> frames, float4 smem reads) -> 10*log10 -> log-mel (smem)
 //   per clip : clip-wide max -> top_db clamp -> DCT-II*lifter -> [delta, delta-delta] -> global
 //
@@ -108,145 +109,6 @@ template <> struct FftCfg<512>  { static constexpr int M = 256,  G = 16, P = 16;
 template <> struct FftCfg<1024> { static constexpr int M = 512,  G = 16, P = 32; };
 template <> struct FftCfg<2048> { static constexpr int M = 1024, G = 32, P = 32; };
 
-// Power spectrum of one real frame of NFFT samples via a complex FFT of M = NFFT/2 points held by
-// a group of G lanes (P = M/G points per lane):   n = n1 + G*n2 ,  k = k2 + P*k1
-//   pass 1 (lane n1): DFT_P over n2, times W_M^(n1*k2)            -> smem exchange
-//   pass 2 (lane l ): DFT_G over n1 for k2 = l + G*q              -> Z[k]
-//   unpack          : X[k], X[M-k] from Z[k], conj Z[M-k]         -> |X|^2 into fbuf[0..M]
-// fbuf is reused as exchange buffer, Z buffer and finally the power spectrum.
-template <int NFFT>
-__device__ __forceinline__ void frame_power_fft(const float* __restrict__ xs, const bool aligned2,
-                                                const float2* __restrict__ win2, const float* __restrict__ twp,
-                                                const float2* __restrict__ twu, float* __restrict__ fbuf,
-                                                const int l) {
-  constexpr int M = FftCfg<NFFT>::M, G = FftCfg<NFFT>::G, P = FftCfg<NFFT>::P;
-  constexpr int Q = P / G;
-  float2* xb = reinterpret_cast<float2*>(fbuf);
-  {
-    float re[P], im[P];
-    if (aligned2) {
-      const float2* xs2 = reinterpret_cast<const float2*>(xs);
-#pragma unroll
-      for (int n2 = 0; n2 < P; ++n2) {
-        const int n = l + G * n2;
-        const float2 x = xs2[n];
-        const float2 w = win2[n];
-        re[brev<P>(n2)] = x.x * w.x;
-        im[brev<P>(n2)] = x.y * w.y;
-      }
-    } else {
-#pragma unroll
-      for (int n2 = 0; n2 < P; ++n2) {
-        const int n = l + G * n2;
-        const float2 w = win2[n];
-        re[brev<P>(n2)] = xs[2 * n] * w.x;
-        im[brev<P>(n2)] = xs[2 * n + 1] * w.y;
-      }
-    }
-    dft_dit<P>(re, im);
-    const float4* tw4 = reinterpret_cast<const float4*>(twp + l * (2 * P + 4));
-#pragma unroll
-    for (int k2 = 0; k2 < P; k2 += 2) {
-      const float4 t = tw4[k2 / 2];
-      if (k2 != 0) {
-        const float r = re[k2], i = im[k2];
-        re[k2] = fmaf(r, t.x, -i * t.y);
-        im[k2] = fmaf(r, t.y, i * t.x);
-      }
-      const float r = re[k2 + 1], i = im[k2 + 1];
-      re[k2 + 1] = fmaf(r, t.z, -i * t.w);
-      im[k2 + 1] = fmaf(r, t.w, i * t.z);
-    }
-#pragma unroll
-    for (int k2 = 0; k2 < P; ++k2) xb[l * (P + 1) + k2] = make_float2(re[k2], im[k2]);
-  }
-  __syncwarp();
-  float ur[Q][G], ui[Q][G];
-#pragma unroll
-  for (int q = 0; q < Q; ++q) {
-#pragma unroll
-    for (int n1 = 0; n1 < G; ++n1) {
-      const float2 a = xb[n1 * (P + 1) + l + G * q];
-      ur[q][brev<G>(n1)] = a.x;
-      ui[q][brev<G>(n1)] = a.y;
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < Q; ++q) dft_dit<G>(ur[q], ui[q]);
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < Q; ++q)
-#pragma unroll
-    for (int k1 = 0; k1 < G; ++k1) xb[l + G * q + P * k1] = make_float2(ur[q][k1], ui[q][k1]);
-  __syncwarp();
-  float2 zp[Q][G / 2];
-#pragma unroll
-  for (int q = 0; q < Q; ++q)
-#pragma unroll
-    for (int k1 = 0; k1 < G / 2; ++k1) {
-      const int k = l + G * q + P * k1;
-      zp[q][k1] = xb[(M - k) & (M - 1)];
-    }
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < Q; ++q)
-#pragma unroll
-    for (int k1 = 0; k1 < G / 2; ++k1) {
-      const int k = l + G * q + P * k1;
-      const float2 w = twu[k];                 // (-sin(2 pi k/N)/2, -cos(2 pi k/N)/2)
-      const float ar = ur[q][k1], ai = ui[q][k1];
-      const float br = zp[q][k1].x, bi = zp[q][k1].y;
-      const float sr = ar + br, si = ai - bi;  // A + conj(B)
-      const float dr = ar - br, di = ai + bi;  // A - conj(B)
-      const float tr = fmaf(w.x, dr, -w.y * di);
-      const float ti = fmaf(w.x, di, w.y * dr);
-      const float xr = fmaf(0.5f, sr, tr), xi = fmaf(0.5f, si, ti);
-      const float yr = fmaf(0.5f, sr, -tr), yi = fmaf(0.5f, si, -ti);
-      fbuf[k] = fmaf(xr, xr, xi * xi);
-      fbuf[M - k] = fmaf(yr, yr, yi * yi);
-    }
-  if (l == 0) fbuf[M / 2] = fmaf(ur[0][G / 2], ur[0][G / 2], ui[0][G / 2] * ui[0][G / 2]);
-  if (l < 16) fbuf[M + 1 + l] = 0.0f;         // tail read by the (fixed 4-quad) mel tasks
-}
-
-// Direct DFT for any n_fft (the reference's speaker preset uses n_fft = 441 = 3^2 * 7^2).
-// One warp per frame; lane handles bins k = lane + 32*j.  fbuf[0..n_fft) holds the windowed frame,
-// the power spectrum goes to fbuf[s_off..].
-__device__ __forceinline__ void frame_power_dft(const float* __restrict__ xs, const float* __restrict__ win,
-                                                const float2* __restrict__ cs, const int n_fft, const int n_bins,
-                                                float* __restrict__ fbuf, const int s_off, const int lane) {
-  for (int n = lane; n < n_fft; n += 32) fbuf[n] = xs[n] * win[n];
-  __syncwarp();
-  constexpr int KJ = 8;
-  for (int kb0 = 0; kb0 < n_bins; kb0 += 32 * KJ) {
-    int k[KJ], idx[KJ];
-    float ar[KJ], ai[KJ];
-#pragma unroll
-    for (int j = 0; j < KJ; ++j) {
-      k[j] = kb0 + lane + 32 * j;
-      if (k[j] >= n_bins) k[j] = 0;
-      idx[j] = 0; ar[j] = 0.0f; ai[j] = 0.0f;
-    }
-    for (int n = 0; n < n_fft; ++n) {
-      const float x = fbuf[n];
-#pragma unroll
-      for (int j = 0; j < KJ; ++j) {
-        const float2 c = cs[idx[j]];
-        ar[j] = fmaf(x, c.x, ar[j]);
-        ai[j] = fmaf(x, c.y, ai[j]);
-        idx[j] += k[j];
-        if (idx[j] >= n_fft) idx[j] -= n_fft;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < KJ; ++j) {
-      const int kk = kb0 + lane + 32 * j;
-      if (kk < n_bins) fbuf[s_off + kk] = fmaf(ar[j], ar[j], ai[j] * ai[j]);
-    }
-  }
-  if (lane < 16) fbuf[s_off + n_bins + lane] = 0.0f;   // tail read by the (fixed 4-quad) mel tasks
-}
-
 // ------------------------------------------------------------------------------------------------
 // audio decode (+ fused additive noise).  The mix is float64(x) + s*z with two roundings.
 __device__ __forceinline__ float clean_f32(const void* __restrict__ audio, const int dtype, const long long i) {
@@ -281,158 +143,243 @@ __device__ __forceinline__ float signal_at(const KParams& kp, const long long ba
   return __fadd_rn(x, __fadd_rn(2.0f * x, -y1));
 }
 
-// ------------------------------------------------------------------------------------------------
-// Staging of one batch's padded signal span into shared memory.
+// signal value at padded position `p` of a clip of L samples (reflect / zero padding), 0 outside
+__device__ __forceinline__ float padded_at(const KParams& kp, const long long base, const int L, const int p,
+                                           const double sig) {
+  int o = p - kp.pad;
+  if (o < 0) { if (kp.pad_mode != ASR_PAD_REFLECT) return 0.0f; o = -o; }
+  else if (o >= L) { if (kp.pad_mode != ASR_PAD_REFLECT) return 0.0f; o = 2 * (L - 1) - o; }
+  return signal_at(kp, base, o, sig);
+}
+
+// Pass-1 operands of lane `l`: complex points z[n] = (x[2n], x[2n+1]) * window, n = l + G*n2, stored in
+// bit-reversed order for the DIT DFT.
 //
-// The span is cut into groups of 8 samples aligned in the GLOBAL sample index, so every group that
-// lies inside the clip is fetched with 16-byte loads (1 for int16, 2 for float32, 4 for float64) and
-// written with two 16-byte shared stores; s_audio[k] holds global sample g_al + k, the first padded
-// position of the batch sits at s_audio[shift].  Groups that touch a clip edge (reflect / zero
-// padding) or need pre-emphasis take the element-wise path.  For int16 / float32 audio the loads of
-// the NEXT batch are issued before the current batch's FFTs (register prefetch), the noise streams of
-// the next batch are pulled into L2 with prefetch hints.
-struct Stage {
-  long long g_al;   // global element index of s_audio[0] (multiple of 8)
-  int shift;        // s_audio[shift] = padded position t0*hop
-  int n;            // padded samples the batch needs
-  int n_groups;
-};
-
-__device__ __forceinline__ Stage stage_setup(const KParams& kp, const long long base, const int t0, const int nb) {
-  Stage s;
-  const long long g0 = base + static_cast<long long>(t0) * kp.hop - kp.pad;
-  s.g_al = (g0 >= 0 ? g0 : g0 - 7) / 8 * 8;
-  s.shift = static_cast<int>(g0 - s.g_al);
-  s.n = (nb - 1) * kp.hop + kp.n_fft;
-  s.n_groups = (s.shift + s.n + 7) / 8;
-  return s;
-}
-
-__device__ __forceinline__ bool group_inside(const Stage& s, const int gi, const long long base, const int L) {
-  const long long e0 = s.g_al + 8LL * gi;
-  return e0 >= base && e0 + 8 <= base + L;
-}
-
-__device__ __forceinline__ void stage_prefetch(const KParams& kp, const Stage& s, const long long base, const int L,
-                                               const int tid, int4 (&pre)[2][2]) {
-  if (!kp.vec_ok || kp.dtype == ASR_F64 || kp.preemph != 0.0f) return;
+// load_frame_global: the frame lies inside the clip and needs no noise / pre-emphasis - one 4/8/16-byte
+// load per sample pair straight from global memory (through L1: consecutive frames overlap by n_fft-hop).
+template <int NFFT, int DT>
+__device__ __forceinline__ void load_frame_global(const KParams& kp, const long long e_start,
+                                                  const float2* __restrict__ win2,
+                                                  const float2* __restrict__ win2_i16, const int l,
+                                                  float (&re)[FftCfg<NFFT>::P], float (&im)[FftCfg<NFFT>::P]) {
+  constexpr int G = FftCfg<NFFT>::G, P = FftCfg<NFFT>::P;
+  if (DT == ASR_I16) {
+    const int* p = reinterpret_cast<const int*>(reinterpret_cast<const short*>(kp.audio) + e_start);
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int gi = tid + r * kThreads;
-    if (gi < s.n_groups && group_inside(s, gi, base, L)) {
-      const long long e0 = s.g_al + 8LL * gi;
-      if (kp.dtype == ASR_I16) {
-        pre[r][0] = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const short*>(kp.audio) + e0));
-      } else {
-        const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const float*>(kp.audio) + e0);
-        pre[r][0] = __ldg(p);
-        pre[r][1] = __ldg(p + 1);
-      }
+    for (int n2 = 0; n2 < P; ++n2) {
+      const int n = l + G * n2;
+      const int v = __ldg(p + n);
+      const float2 w = win2_i16[n];                        // window / 32768 (exact power-of-two scaling)
+      re[brev<P>(n2)] = static_cast<float>(static_cast<short>(v)) * w.x;
+      im[brev<P>(n2)] = static_cast<float>(v >> 16) * w.y;
     }
-  }
-  if (kp.noise_mode != ASR_NOISE_NONE) {
-    // one 128-byte line of each noise stream per thread -> L2
-    const long long lines = (static_cast<long long>(s.n_groups) * 64 + 127) / 128;
-    for (long long ln = tid; ln < lines; ln += kThreads) {
-      const long long e = s.g_al + ln * 16;
-      if (e >= base && e < base + L) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.z + e));
-        if (kp.noise_mode == ASR_NOISE_MIXTURE) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp.z2 + e));
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void unpack_i16(const int4 raw, float (&v)[8]) {
-  const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+  } else if (DT == ASR_F32) {
+    const float2* p = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(kp.audio) + e_start);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    v[2 * j] = static_cast<float>(static_cast<short>(w[j] & 0xffff)) * (1.0f / 32768.0f);
-    v[2 * j + 1] = static_cast<float>(w[j] >> 16) * (1.0f / 32768.0f);
-  }
-}
-
-// one group of 8 samples -> s_audio[8*gi .. 8*gi+8)
-__device__ __forceinline__ void stage_group(const KParams& kp, const Stage& s, const long long base, const int L,
-                                            const double sig, const int gi, const bool have_pre, const int4 pre0,
-                                            const int4 pre1, float* __restrict__ s_audio) {
-  const long long e0 = s.g_al + 8LL * gi;
-  float v[8];
-  if (kp.vec_ok && kp.preemph == 0.0f && group_inside(s, gi, base, L)) {
-    double xd[8];
-    if (kp.dtype == ASR_I16) {
-      const int4 raw = have_pre ? pre0 : __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const short*>(kp.audio) + e0));
-      unpack_i16(raw, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xd[j] = static_cast<double>(v[j]);
-    } else if (kp.dtype == ASR_F32) {
-      const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const float*>(kp.audio) + e0);
-      const int4 a = have_pre ? pre0 : __ldg(p);
-      const int4 b = have_pre ? pre1 : __ldg(p + 1);
-      v[0] = __int_as_float(a.x); v[1] = __int_as_float(a.y); v[2] = __int_as_float(a.z); v[3] = __int_as_float(a.w);
-      v[4] = __int_as_float(b.x); v[5] = __int_as_float(b.y); v[6] = __int_as_float(b.z); v[7] = __int_as_float(b.w);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xd[j] = static_cast<double>(v[j]);
-    } else {
-      const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(kp.audio) + e0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double2 d = __ldg(p + j);
-        xd[2 * j] = d.x; xd[2 * j + 1] = d.y;
-        v[2 * j] = static_cast<float>(d.x); v[2 * j + 1] = static_cast<float>(d.y);
-      }
-    }
-    if (kp.noise_mode != ASR_NOISE_NONE) {
-      double zz[8];
-      const double2* zp = reinterpret_cast<const double2*>(kp.z + e0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const double2 d = __ldg(zp + j); zz[2 * j] = d.x; zz[2 * j + 1] = d.y; }
-      if (kp.noise_mode == ASR_NOISE_WHITE) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = static_cast<float>(__dadd_rn(xd[j], __dmul_rn(sig, zz[j])));
-      } else {
-        const double2* gp = reinterpret_cast<const double2*>(kp.z2 + e0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double2 g = __ldg(gp + j);
-          const double s0 = (fabs(zz[2 * j]) < kp.mix_p) ? kp.mix_s1 : kp.mix_s0;
-          const double s1 = (fabs(zz[2 * j + 1]) < kp.mix_p) ? kp.mix_s1 : kp.mix_s0;
-          v[2 * j] = static_cast<float>(__dadd_rn(xd[2 * j], __dmul_rn(s0, g.x)));
-          v[2 * j + 1] = static_cast<float>(__dadd_rn(xd[2 * j + 1], __dmul_rn(s1, g.y)));
-        }
-      }
+    for (int n2 = 0; n2 < P; ++n2) {
+      const int n = l + G * n2;
+      const float2 x = __ldg(p + n);
+      const float2 w = win2[n];
+      re[brev<P>(n2)] = x.x * w.x;
+      im[brev<P>(n2)] = x.y * w.y;
     }
   } else {
-    // clip edge (reflect / zero padding), unaligned buffers or pre-emphasis: element-wise
-#pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-      const int i = 8 * gi + j - s.shift;            // padded position relative to the batch start
-      long long o = e0 + j - base;                   // original sample index
-      float x = 0.0f;
-      if (i >= 0 && i < s.n) {
-        bool ok = true;
-        if (o < 0) { if (kp.pad_mode == ASR_PAD_REFLECT) o = -o; else ok = false; }
-        else if (o >= L) { if (kp.pad_mode == ASR_PAD_REFLECT) o = 2LL * (L - 1) - o; else ok = false; }
-        if (ok) x = signal_at(kp, base, static_cast<int>(o), sig);
-      }
-      s_audio[8 * gi + j] = x;
+    const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(kp.audio) + e_start);
+#pragma unroll
+    for (int n2 = 0; n2 < P; ++n2) {
+      const int n = l + G * n2;
+      const double2 x = __ldg(p + n);
+      const float2 w = win2[n];
+      re[brev<P>(n2)] = static_cast<float>(x.x) * w.x;
+      im[brev<P>(n2)] = static_cast<float>(x.y) * w.y;
     }
-    return;
   }
-  float4* dst = reinterpret_cast<float4*>(s_audio + 8 * gi);
-  dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-  dst[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-__device__ __forceinline__ void stage_commit(const KParams& kp, const Stage& s, const long long base, const int L,
-                                             const double sig, const int tid, const int4 (&pre)[2][2],
-                                             float* __restrict__ s_audio) {
-  const bool have_pre = kp.vec_ok && kp.dtype != ASR_F64 && kp.preemph == 0.0f;
-  if (tid < s.n_groups) stage_group(kp, s, base, L, sig, tid, have_pre, pre[0][0], pre[0][1], s_audio);
-  if (tid + kThreads < s.n_groups)
-    stage_group(kp, s, base, L, sig, tid + kThreads, have_pre, pre[1][0], pre[1][1], s_audio);
-  for (int gi = tid + 2 * kThreads; gi < s.n_groups; gi += kThreads)
-    stage_group(kp, s, base, L, sig, gi, false, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), s_audio);
+// load_frame_smem: the frame's samples were staged (float32, after noise / pre-emphasis / padding) at xs.
+template <int NFFT>
+__device__ __forceinline__ void load_frame_smem(const float* __restrict__ xs, const bool aligned2,
+                                                const float2* __restrict__ win2, const int l,
+                                                float (&re)[FftCfg<NFFT>::P], float (&im)[FftCfg<NFFT>::P]) {
+  constexpr int G = FftCfg<NFFT>::G, P = FftCfg<NFFT>::P;
+  if (aligned2) {
+    const float2* xs2 = reinterpret_cast<const float2*>(xs);
+#pragma unroll
+    for (int n2 = 0; n2 < P; ++n2) {
+      const int n = l + G * n2;
+      const float2 x = xs2[n];
+      const float2 w = win2[n];
+      re[brev<P>(n2)] = x.x * w.x;
+      im[brev<P>(n2)] = x.y * w.y;
+    }
+  } else {
+#pragma unroll
+    for (int n2 = 0; n2 < P; ++n2) {
+      const int n = l + G * n2;
+      const float2 w = win2[n];
+      re[brev<P>(n2)] = xs[2 * n] * w.x;
+      im[brev<P>(n2)] = xs[2 * n + 1] * w.y;
+    }
+  }
+}
+
+// Warp-cooperative staging of `count` samples starting at padded position p_begin of the clip into dst
+// (float32): dtype decode, [float64 noise mix], [pre-emphasis], reflect / zero padding.  Spans inside the
+// clip with an even global start are processed two samples per lane with vector loads.
+template <int DT>
+__device__ __forceinline__ void fill_span(const KParams& kp, const long long base, const int L, const int p_begin,
+                                          const int count, const double sig, float* __restrict__ dst, const int lane) {
+  const int o_begin = p_begin - kp.pad;
+  const long long e_begin = base + o_begin;
+  const bool vec = kp.vec_ok && kp.preemph == 0.0f && o_begin >= 0 && o_begin + count <= L && (e_begin & 1) == 0 &&
+                   (count & 1) == 0;
+  if (!vec) {
+    for (int i = lane; i < count; i += 32) dst[i] = padded_at(kp, base, L, p_begin + i, sig);
+    return;
+  }
+  float2* dst2 = reinterpret_cast<float2*>(dst);
+  const bool white = kp.noise_mode == ASR_NOISE_WHITE;
+  for (int n = lane; 2 * n < count; n += 32) {
+    double x0, x1;
+    if (DT == ASR_I16) {
+      const int v = __ldg(reinterpret_cast<const int*>(reinterpret_cast<const short*>(kp.audio) + e_begin) + n);
+      x0 = static_cast<double>(static_cast<float>(static_cast<short>(v)) * (1.0f / 32768.0f));
+      x1 = static_cast<double>(static_cast<float>(v >> 16) * (1.0f / 32768.0f));
+    } else if (DT == ASR_F32) {
+      const float2 x = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(kp.audio) + e_begin) + n);
+      x0 = static_cast<double>(x.x); x1 = static_cast<double>(x.y);
+    } else {
+      const double2 x = __ldg(reinterpret_cast<const double2*>(reinterpret_cast<const double*>(kp.audio) + e_begin) + n);
+      x0 = x.x; x1 = x.y;
+    }
+    if (kp.noise_mode != ASR_NOISE_NONE) {
+      const double2 z = __ldg(reinterpret_cast<const double2*>(kp.z + e_begin) + n);
+      double s0 = sig, s1 = sig, g0 = z.x, g1 = z.y;
+      if (!white) {
+        const double2 g = __ldg(reinterpret_cast<const double2*>(kp.z2 + e_begin) + n);
+        s0 = (fabs(z.x) < kp.mix_p) ? kp.mix_s1 : kp.mix_s0;
+        s1 = (fabs(z.y) < kp.mix_p) ? kp.mix_s1 : kp.mix_s0;
+        g0 = g.x; g1 = g.y;
+      }
+      x0 = __dadd_rn(x0, __dmul_rn(s0, g0));
+      x1 = __dadd_rn(x1, __dmul_rn(s1, g1));
+    }
+    dst2[n] = make_float2(static_cast<float>(x0), static_cast<float>(x1));
+  }
+}
+
+// Power spectrum of one real frame of NFFT samples via a complex FFT of M = NFFT/2 points held by
+// a group of G lanes (P = M/G points per lane):   n = n1 + G*n2 ,  k = k2 + P*k1
+//   pass 1 (lane n1): DFT_P over n2, times W_M^(n1*k2)            -> smem exchange
+//   pass 2 (lane l ): DFT_G over n1 for k2 = l + G*q              -> Z[k]
+//   unpack          : X[k], X[M-k] from Z[k], conj Z[M-k] (fetched from lane G-l by shuffle)
+//                     -> |X|^2 into fbuf[0..M]
+// fbuf is the exchange buffer and finally holds the power spectrum.
+template <int NFFT>
+__device__ __forceinline__ void frame_power_fft(float (&re)[FftCfg<NFFT>::P], float (&im)[FftCfg<NFFT>::P],
+                                                const float* __restrict__ twp, const float2* __restrict__ twu,
+                                                float* __restrict__ fbuf, const int l) {
+  constexpr int M = FftCfg<NFFT>::M, G = FftCfg<NFFT>::G, P = FftCfg<NFFT>::P;
+  constexpr int Q = P / G;
+  float2* xb = reinterpret_cast<float2*>(fbuf);
+  dft_dit<P>(re, im);
+  {
+    const float4* tw4 = reinterpret_cast<const float4*>(twp + l * (2 * P + 4));
+#pragma unroll
+    for (int k2 = 0; k2 < P; k2 += 2) {
+      const float4 t = tw4[k2 / 2];
+      if (k2 != 0) {
+        const float r = re[k2], i = im[k2];
+        re[k2] = fmaf(r, t.x, -i * t.y);
+        im[k2] = fmaf(r, t.y, i * t.x);
+      }
+      const float r = re[k2 + 1], i = im[k2 + 1];
+      re[k2 + 1] = fmaf(r, t.z, -i * t.w);
+      im[k2 + 1] = fmaf(r, t.w, i * t.z);
+    }
+  }
+  __syncwarp();                                    // staged frames read their samples from the frame buffers
+#pragma unroll
+  for (int k2 = 0; k2 < P; ++k2) xb[l * (P + 1) + k2] = make_float2(re[k2], im[k2]);
+  __syncwarp();
+  float ur[Q][G], ui[Q][G];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+#pragma unroll
+    for (int n1 = 0; n1 < G; ++n1) {
+      const float2 a = xb[n1 * (P + 1) + l + G * q];
+      ur[q][brev<G>(n1)] = a.x;
+      ui[q][brev<G>(n1)] = a.y;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) dft_dit<G>(ur[q], ui[q]);
+  __syncwarp();                                    // exchange data consumed; fbuf becomes the spectrum
+  const int partner = (G - l) & (G - 1);
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+#pragma unroll
+    for (int k1 = 0; k1 < G / 2; ++k1) {
+      const int k = l + G * q + P * k1;
+      // Z[M-k] lives in lane G-l at (Q-1-q, G-1-k1); lane 0 pairs with itself at (Q-q, G-1-k1) for q >= 1
+      // and at (0, (G-k1) mod G) for q = 0.  Every lane offers what its requester needs.
+      const int q0 = (q == 0) ? 0 : Q - q, j0 = (q == 0) ? ((G - k1) & (G - 1)) : G - 1 - k1;
+      const float give_r = (l == 0) ? ur[q0][j0] : ur[Q - 1 - q][G - 1 - k1];
+      const float give_i = (l == 0) ? ui[q0][j0] : ui[Q - 1 - q][G - 1 - k1];
+      const float br = __shfl_sync(0xffffffffu, give_r, partner, G);
+      const float bi = __shfl_sync(0xffffffffu, give_i, partner, G);
+      const float2 w = twu[k];                 // (-sin(2 pi k/N)/2, -cos(2 pi k/N)/2)
+      const float ar = ur[q][k1], ai = ui[q][k1];
+      const float sr = ar + br, si = ai - bi;  // A + conj(B)
+      const float dr = ar - br, di = ai + bi;  // A - conj(B)
+      const float tr = fmaf(w.x, dr, -w.y * di);
+      const float ti = fmaf(w.x, di, w.y * dr);
+      const float xr = fmaf(0.5f, sr, tr), xi = fmaf(0.5f, si, ti);
+      const float yr = fmaf(0.5f, sr, -tr), yi = fmaf(0.5f, si, -ti);
+      fbuf[k] = fmaf(xr, xr, xi * xi);
+      fbuf[M - k] = fmaf(yr, yr, yi * yi);
+    }
+  if (l == 0) fbuf[M / 2] = fmaf(ur[0][G / 2], ur[0][G / 2], ui[0][G / 2] * ui[0][G / 2]);
+  if (l < 16) fbuf[M + 1 + l] = 0.0f;         // tail read by the (fixed 4-quad) mel tasks
+}
+
+// Direct DFT for any n_fft (the reference's speaker preset uses n_fft = 441 = 3^2 * 7^2).
+// One warp per frame; lane handles bins k = lane + 32*j.  fbuf[0..n_fft) holds the windowed frame,
+// the power spectrum goes to fbuf[s_off..].
+__device__ __forceinline__ void frame_power_dft(const KParams& kp, const float* __restrict__ win,
+                                                const float2* __restrict__ cs, float* __restrict__ fbuf,
+                                                const int s_off, const int lane) {
+  const int n_fft = kp.n_fft, n_bins = kp.n_bins;
+  for (int n = lane; n < n_fft; n += 32) fbuf[n] *= win[n];     // fbuf[0..n_fft) was staged by fill_span
+  __syncwarp();
+  constexpr int KJ = 8;
+  for (int kb0 = 0; kb0 < n_bins; kb0 += 32 * KJ) {
+    int k[KJ], idx[KJ];
+    float ar[KJ], ai[KJ];
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+      k[j] = kb0 + lane + 32 * j;
+      if (k[j] >= n_bins) k[j] = 0;
+      idx[j] = 0; ar[j] = 0.0f; ai[j] = 0.0f;
+    }
+    for (int n = 0; n < n_fft; ++n) {
+      const float x = fbuf[n];
+#pragma unroll
+      for (int j = 0; j < KJ; ++j) {
+        const float2 c = cs[idx[j]];
+        ar[j] = fmaf(x, c.x, ar[j]);
+        ai[j] = fmaf(x, c.y, ai[j]);
+        idx[j] += k[j];
+        if (idx[j] >= n_fft) idx[j] -= n_fft;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+      const int kk = kb0 + lane + 32 * j;
+      if (kk < n_bins) fbuf[s_off + kk] = fmaf(ar[j], ar[j], ai[j] * ai[j]);
+    }
+  }
+  if (lane < 16) fbuf[s_off + n_bins + lane] = 0.0f;   // tail read by the (fixed 4-quad) mel tasks
 }
 
 __device__ __forceinline__ int num_frames_dev(const KParams& kp, const int L) {
@@ -446,12 +393,13 @@ __device__ __forceinline__ void store_out(const KParams& kp, const long long idx
   else reinterpret_cast<float*>(kp.out)[idx] = v;
 }
 
+
 // ------------------------------------------------------------------------------------------------
 // One CLUSTER of `cs` CTAs per clip (cs = 1 for clips whose log-mel matrix fits one CTA's shared
 // memory).  CTA `rank` owns frames [rank*FC, rank*FC+FC), FC = ceil(T/cs); the clip-wide maximum and
 // the delta halo rows are exchanged through distributed shared memory.
-template <int NFFT>
-__global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 2 : 1)) mfcc_kernel(const __grid_constant__ KParams kp) {
+template <int NFFT, int DT>
+__global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(const __grid_constant__ KParams kp) {
   extern __shared__ __align__(16) float smem[];
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -487,16 +435,14 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 2 : 1)) mfcc_kernel(c
     for (int i = tid; i < kp.blob_f4; i += kThreads) dst[i] = __ldg(kp.blob + i);
   }
   const float* s_window = smem + kp.off_window;
+  const float* s_window_i16 = smem + kp.off_window_i16;
   const float* s_twp = smem + kp.off_twp;
   const float2* s_twu = reinterpret_cast<const float2*>(smem + kp.off_twu);
-  const int4* s_tasks = reinterpret_cast<const int4*>(smem + kp.off_tasks);
+  const int2* s_tasks = reinterpret_cast<const int2*>(smem + kp.off_tasks);
   const float4* s_melw = reinterpret_cast<const float4*>(smem + kp.off_melw);
-  const int* s_sbeg = reinterpret_cast<const int*>(smem + kp.off_sbeg);
-  const int* s_stasks = reinterpret_cast<const int*>(smem + kp.off_stasks);
   const int2* s_ftasks = reinterpret_cast<const int2*>(smem + kp.off_ftasks);
   const float* s_dct = smem + kp.off_dct;
   const float* s_taps = smem + kp.off_taps;
-  float* s_audio = smem + kp.sm_audio;
   float* s_frames = smem + kp.sm_frames;
   float* s_part = smem + kp.sm_part;
   float* s_lm = smem + kp.sm_lm;                    // row r = frame f0 + r
@@ -506,84 +452,91 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 2 : 1)) mfcc_kernel(c
   for (int i = tid; i < nF * kp.lm_pitch; i += kThreads) s_lm[i] = 0.0f;
 
   const double sig = (kp.noise_mode == ASR_NOISE_WHITE) ? kp.sigma[b] : 0.0;
-  const int FB = kp.fb;                             // 8 or 16
-  const int fb_sh = (FB == 16) ? 4 : 3;
   const int s_off = (NFFT == 0) ? ((kp.n_fft + 3) & ~3) : 0;
   float run_max = -3.0e38f;
 
-  int4 pre[2][2];
-  pre[0][0] = pre[0][1] = pre[1][0] = pre[1][1] = make_int4(0, 0, 0, 0);
-  Stage sg = stage_setup(kp, base, f0, min(FB, max(nF, 1)));
-  if (nF > 0) stage_prefetch(kp, sg, base, L, tid, pre);
+  __syncthreads();                                  // tables and the zeroed log-mel rows are visible
 
-  for (int t0 = f0; t0 < f1; t0 += FB) {
-    const int nb = min(FB, f1 - t0);
-    // ---- stage the padded signal span of this batch (s_audio[shift] = padded position t0*hop) ----
-    stage_commit(kp, sg, base, L, sig, tid, pre, s_audio);
-    const int shift = sg.shift;
-    __syncthreads();
-    if (t0 + FB < f1) {                              // next batch's loads fly during this batch's FFTs
-      sg = stage_setup(kp, base, t0 + FB, min(FB, f1 - t0 - FB));
-      stage_prefetch(kp, sg, base, L, tid, pre);
-    }
-    // ---- frames -> power spectra ----
+  // ---- main loop: every warp runs frames -> power spectra -> mel -> log on its own (no CTA barrier) ----
+  constexpr int FPW = (NFFT == 0) ? 1 : 32 / FftCfg<(NFFT == 0 ? 512 : NFFT)>::G;   // frames per warp iteration
+  constexpr int SPF = 32 / FPW;                                                      // mel task streams per frame
+  float* wbuf = s_frames + warp * FPW * kp.frame_stride;          // this warp's FPW frame buffers (contiguous)
+  float* wpart = s_part + warp * FPW * kp.part_pitch;
+  const int ntp = kp.n_tasks_padded;
+  for (int tw = f0 + warp * FPW; tw < f1; tw += kWarps * FPW) {
+    const int nbw = min(FPW, f1 - tw);                             // real frames of this iteration
+    const int jf = lane / SPF;                                     // frame slot of this lane
+    const int fr = min(jf, nbw - 1);                               // idle slots recompute the last frame
     if constexpr (NFFT != 0) {
-      constexpr int G = FftCfg<NFFT>::G;
-      constexpr int GPW = 32 / G;                  // frames per warp
-      const int fs = warp * GPW + lane / G;
-      if (warp * GPW < nb) {
-        const int fr = min(fs, nb - 1);            // idle groups recompute the last frame into their own buffer
-        const float* xs = s_audio + shift + fr * kp.hop;
-        const bool aligned2 = ((shift + fr * kp.hop) & 1) == 0;
-        frame_power_fft<NFFT>(xs, aligned2, reinterpret_cast<const float2*>(s_window), s_twp, s_twu,
-                              s_frames + fs * kp.frame_stride, lane % G);
+      constexpr int G = FftCfg<NFFT>::G, P = FftCfg<NFFT>::P;
+      const int l = lane % G;
+      float re[P], im[P];
+      const int o_first = tw * kp.hop - kp.pad, o_last = (tw + nbw - 1) * kp.hop - kp.pad;
+      const bool direct = kp.noise_mode == ASR_NOISE_NONE && kp.vec_ok && kp.preemph == 0.0f && o_first >= 0 &&
+                          o_last + NFFT <= L && ((base + o_first) & 1) == 0 && (nbw == 1 || (kp.hop & 1) == 0);
+      if (direct) {
+        load_frame_global<NFFT, DT>(kp, base + (tw + fr) * kp.hop - kp.pad, reinterpret_cast<const float2*>(s_window),
+                                    reinterpret_cast<const float2*>(s_window_i16), l, re, im);
+      } else {
+        // stage the span of the iteration's frames in the warp's own buffers (shared by both frames when it fits)
+        const int span = (nbw - 1) * kp.hop + NFFT;
+        if (span <= FPW * kp.frame_stride) {
+          fill_span<DT>(kp, base, L, tw * kp.hop, span, sig, wbuf, lane);
+          __syncwarp();
+          load_frame_smem<NFFT>(wbuf + fr * kp.hop, ((fr * kp.hop) & 1) == 0, reinterpret_cast<const float2*>(s_window), l,
+                                re, im);
+        } else {
+          for (int j = 0; j < nbw; ++j) fill_span<DT>(kp, base, L, (tw + j) * kp.hop, NFFT, sig, wbuf + j * kp.frame_stride, lane);
+          __syncwarp();
+          load_frame_smem<NFFT>(wbuf + fr * kp.frame_stride, true, reinterpret_cast<const float2*>(s_window), l, re, im);
+        }
       }
+      frame_power_fft<NFFT>(re, im, s_twp, s_twu, wbuf + jf * kp.frame_stride, l);
     } else {
-      if (warp < nb)
-        frame_power_dft(s_audio + shift + warp * kp.hop, s_window, s_twu, kp.n_fft, kp.n_bins,
-                        s_frames + warp * kp.frame_stride, s_off, lane);
+      switch (kp.dtype) {
+        case ASR_I16: fill_span<ASR_I16>(kp, base, L, tw * kp.hop, kp.n_fft, sig, wbuf, lane); break;
+        case ASR_F32: fill_span<ASR_F32>(kp, base, L, tw * kp.hop, kp.n_fft, sig, wbuf, lane); break;
+        default: fill_span<ASR_F64>(kp, base, L, tw * kp.hop, kp.n_fft, sig, wbuf, lane); break;
+      }
+      __syncwarp();
+      frame_power_dft(kp, s_window, s_twu, wbuf, s_off, lane);
     }
-    __syncthreads();
-    // ---- sparse mel bank: lanes <-> frames of the batch, task streams <-> sub-warps ----
+    __syncwarp();
+    // ---- sparse mel bank: lane <-> (frame slot, task stream); every task is 4 float4 groups of one filter ----
     {
-      const int f = lane & (FB - 1);
-      const int stream = (warp << (5 - fb_sh)) + (lane >> fb_sh);
-      const float* S = s_frames + f * kp.frame_stride + s_off;
-      const int tb = s_sbeg[stream], te = s_sbeg[stream + 1];
-      for (int ti = tb; ti < te; ++ti) {
-        const int task = s_stasks[ti];
-        const int4 tk = s_tasks[task];             // (filter, k_start, n_quads, w_off); weights padded to 4 quads
-        const float4* s4 = reinterpret_cast<const float4*>(S + tk.y);
-        const float4* w4 = s_melw + tk.w;
+      const float* S = wbuf + jf * kp.frame_stride + s_off;
+      float* prt = wpart + jf * kp.part_pitch;
+      for (int tp = lane % SPF; tp < ntp; tp += SPF) {
+        const int2 tk = s_tasks[tp];                 // (first bin, partial slot)
+        const float4* s4 = reinterpret_cast<const float4*>(S + tk.x);
         float acc = 0.0f;
 #pragma unroll
         for (int q = 0; q < kMelChunkQuads; ++q) {
-          const float4 s = s4[q];
-          const float4 w = w4[q];
-          acc = fmaf(s.x, w.x, acc);
-          acc = fmaf(s.y, w.y, acc);
-          acc = fmaf(s.z, w.z, acc);
-          acc = fmaf(s.w, w.w, acc);
+          const float4 sv = s4[q];
+          const float4 w = s_melw[q * ntp + tp];
+          acc = fmaf(sv.x, w.x, acc);
+          acc = fmaf(sv.y, w.y, acc);
+          acc = fmaf(sv.z, w.z, acc);
+          acc = fmaf(sv.w, w.w, acc);
         }
-        s_part[task * FB + f] = acc;
+        prt[tk.y] = acc;
       }
     }
-    __syncthreads();
-    // ---- combine partials, 10*log10, running clip max ----
-    {
-      const int f = tid & (FB - 1);
-      if (f < nb) {
-        for (int i = tid >> fb_sh; i < kp.n_mels; i += kThreads >> fb_sh) {
-          const int2 ft = s_ftasks[i];
-          float m = 0.0f;
-          for (int j = 0; j < ft.y; ++j) m += s_part[(ft.x + j) * FB + f];
-          const float db = 3.01029995663981195f * __log2f(fmaxf(kp.amin, m));
-          s_lm[(t0 - f0 + f) * kp.lm_pitch + i] = db;
-          run_max = fmaxf(run_max, db);
-        }
+    __syncwarp();
+    // ---- combine partials in filter order, 10*log10, running clip max ----
+    for (int j = 0; j < nbw; ++j) {
+      const float* prt = wpart + j * kp.part_pitch;
+      float* lrow = s_lm + (tw + j - f0) * kp.lm_pitch;
+      for (int i = lane; i < kp.n_mels; i += 32) {
+        const int2 ft = s_ftasks[i];
+        float m = 0.0f;
+        for (int u = 0; u < ft.y; ++u) m += prt[ft.x + u];
+        const float db = 3.01029995663981195f * __log2f(fmaxf(kp.amin, m));
+        lrow[i] = db;
+        run_max = fmaxf(run_max, db);
       }
     }
-    // next batch's staging / FFT do not touch s_part or s_lm; its barriers order the reuse of s_part
+    __syncwarp();                                     // partials / frame buffers are reused next iteration
   }
 
   // ---- clip-wide max (power_to_db top_db spans every frame of the call) ----
@@ -719,22 +672,30 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 2 : 1)) mfcc_kernel(c
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NFFT>
+template <int NFFT, int DT>
 static cudaError_t init_one() {
-  cudaError_t e = cudaFuncSetAttribute(mfcc_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(mfcc_kernel<NFFT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(mfcc_kernel<NFFT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return cudaFuncSetAttribute(mfcc_kernel<NFFT, DT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 }
 
-cudaError_t mfcc_kernel_init() {
-  cudaError_t e = init_one<512>();
-  if (e == cudaSuccess) e = init_one<1024>();
-  if (e == cudaSuccess) e = init_one<2048>();
-  if (e == cudaSuccess) e = init_one<0>();
+template <int NFFT>
+static cudaError_t init_fft() {
+  cudaError_t e = init_one<NFFT, ASR_I16>();
+  if (e == cudaSuccess) e = init_one<NFFT, ASR_F32>();
+  if (e == cudaSuccess) e = init_one<NFFT, ASR_F64>();
   return e;
 }
 
-template <int NFFT>
+cudaError_t mfcc_kernel_init() {
+  cudaError_t e = init_fft<512>();
+  if (e == cudaSuccess) e = init_fft<1024>();
+  if (e == cudaSuccess) e = init_fft<2048>();
+  if (e == cudaSuccess) e = init_one<0, ASR_F32>();   // the direct-DFT kernel decodes the dtype at run time
+  return e;
+}
+
+template <int NFFT, int DT>
 static cudaError_t launch_one(const KParams& kp, int smem_bytes, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -749,15 +710,24 @@ static cudaError_t launch_one(const KParams& kp, int smem_bytes, cudaStream_t st
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = kp.cluster_size > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, mfcc_kernel<NFFT>, kp);
+  return cudaLaunchKernelEx(&cfg, mfcc_kernel<NFFT, DT>, kp);
+}
+
+template <int NFFT>
+static cudaError_t launch_fft(const KParams& kp, int smem_bytes, cudaStream_t stream) {
+  switch (kp.dtype) {
+    case ASR_I16: return launch_one<NFFT, ASR_I16>(kp, smem_bytes, stream);
+    case ASR_F32: return launch_one<NFFT, ASR_F32>(kp, smem_bytes, stream);
+    default: return launch_one<NFFT, ASR_F64>(kp, smem_bytes, stream);
+  }
 }
 
 cudaError_t launch_mfcc(const KParams& kp, int smem_bytes, cudaStream_t stream) {
   switch (kp.fft_path ? kp.n_fft : 0) {
-    case 512: return launch_one<512>(kp, smem_bytes, stream);
-    case 1024: return launch_one<1024>(kp, smem_bytes, stream);
-    case 2048: return launch_one<2048>(kp, smem_bytes, stream);
-    default: return launch_one<0>(kp, smem_bytes, stream);
+    case 512: return launch_fft<512>(kp, smem_bytes, stream);
+    case 1024: return launch_fft<1024>(kp, smem_bytes, stream);
+    case 2048: return launch_fft<2048>(kp, smem_bytes, stream);
+    default: return launch_one<0, ASR_F32>(kp, smem_bytes, stream);
   }
 }
 

@@ -62,54 +62,105 @@ __device__ void heap_combine(Heap& h, const int limit) {
   }
 }
 
-__device__ __forceinline__ float leaf_sum(const float* __restrict__ a, const int n) {
+// One leaf (n <= 128) summed by a group of 8 lanes, lane j owning numpy's accumulator r[j]; the xor-shuffle
+// tree reproduces ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) (float addition is commutative), lane 0 adds the tail.
+__device__ __forceinline__ float leaf_sum8(const float* __restrict__ a, const int n, const int j, const unsigned gmask) {
   if (n < 8) {
     float res = 0.0f;
-    for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+    if (j == 0)
+      for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
     return res;
   }
-  float r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = a[j];
-  int i = 8;
-  for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
-  }
-  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __fadd_rn(res, a[i]);
-  return res;
+  const int n8 = n - (n % 8);
+  float r = a[j];
+  for (int i = 8; i < n8; i += 8) r = __fadd_rn(r, a[i + j]);
+  r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+  r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+  r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+  if (j == 0)
+    for (int i = n8; i < n; ++i) r = __fadd_rn(r, a[i]);
+  return r;
 }
 
 __global__ void __launch_bounds__(256) clip_power_kernel(const void* __restrict__ audio, const int dtype,
                                                          const long long* __restrict__ offsets,
-                                                         const int* __restrict__ lengths, float* __restrict__ power) {
+                                                         const int* __restrict__ lengths, float* __restrict__ power,
+                                                         const int vec_ok) {
   extern __shared__ __align__(16) float sq[];   // kSubMax squares
   __shared__ Heap top, sub;
+  __shared__ int leaf_list[kHeap];
+  __shared__ int n_leaves;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int L = lengths[b];
   const long long base = offsets[b];
-  if (L <= 0) {
-    if (tid == 0) power[b] = __int_as_float(0x7fc00000);   // np.mean of an empty array is nan
+  if (L <= 0 || L > 4000000) {                  // np.mean of an empty array is nan; > 4M samples exceeds the heap depth
+    if (tid == 0) power[b] = __int_as_float(0x7fc00000);
     return;
   }
   heap_expand(top, 0, L, kSubMax);
   for (int node = 1; node < kHeap; ++node) {
     const int n = top.len[node];
-    if (n <= 0 || n > kSubMax) continue;          // absent or internal
+    if (n <= 0 || n > kSubMax) continue;          // absent or internal (uniform over the block)
     const int off = top.off[node];
-    // stage sample**2 (exact float32 products) for this sub-tree
-    for (int i = tid; i < n; i += blockDim.x) {
-      float x;
-      if (dtype == ASR_I16) x = static_cast<float>(__ldg(reinterpret_cast<const short*>(audio) + base + off + i)) * (1.0f / 32768.0f);
-      else x = __ldg(reinterpret_cast<const float*>(audio) + base + off + i);
-      sq[i] = __fmul_rn(x, x);
+    // ---- stage sample**2 (exact float32 products) for this sub-tree ----
+    const long long e0 = base + off;
+    if (vec_ok && (e0 & 7) == 0) {
+      const int n8 = n & ~7;
+      if (dtype == ASR_I16) {
+        const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const short*>(audio) + e0);
+        for (int g = tid; g < n8 / 8; g += blockDim.x) {
+          const int4 raw = __ldg(p + g);
+          const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x0 = static_cast<float>(static_cast<short>(w[j])) * (1.0f / 32768.0f);
+            const float x1 = static_cast<float>(w[j] >> 16) * (1.0f / 32768.0f);
+            v[2 * j] = __fmul_rn(x0, x0);
+            v[2 * j + 1] = __fmul_rn(x1, x1);
+          }
+          float4* d = reinterpret_cast<float4*>(sq + 8 * g);
+          d[0] = make_float4(v[0], v[1], v[2], v[3]);
+          d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      } else {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(audio) + e0);
+        for (int g = tid; g < n8 / 4; g += blockDim.x) {
+          const float4 x = __ldg(p + g);
+          reinterpret_cast<float4*>(sq)[g] = make_float4(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y), __fmul_rn(x.z, x.z),
+                                                        __fmul_rn(x.w, x.w));
+        }
+      }
+      for (int i = n8 + tid; i < n; i += blockDim.x) {
+        float x;
+        if (dtype == ASR_I16) x = static_cast<float>(__ldg(reinterpret_cast<const short*>(audio) + e0 + i)) * (1.0f / 32768.0f);
+        else x = __ldg(reinterpret_cast<const float*>(audio) + e0 + i);
+        sq[i] = __fmul_rn(x, x);
+      }
+    } else {
+      for (int i = tid; i < n; i += blockDim.x) {
+        float x;
+        if (dtype == ASR_I16) x = static_cast<float>(__ldg(reinterpret_cast<const short*>(audio) + e0 + i)) * (1.0f / 32768.0f);
+        else x = __ldg(reinterpret_cast<const float*>(audio) + e0 + i);
+        sq[i] = __fmul_rn(x, x);
+      }
     }
-    heap_expand(sub, 0, n, 128);                   // barriers inside also publish sq[]
+    if (tid == 0) n_leaves = 0;
+    heap_expand(sub, 0, n, 128);                   // barriers inside also publish sq[] and n_leaves
     for (int i = 1 + tid; i < kHeap; i += blockDim.x) {
       const int ln = sub.len[i];
-      if (ln > 0 && ln <= 128) sub.val[i] = leaf_sum(sq + sub.off[i], ln);
+      if (ln > 0 && ln <= 128) leaf_list[atomicAdd(&n_leaves, 1)] = i;
+    }
+    __syncthreads();
+    {
+      const int j = tid & 7;
+      const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+      const int nl = n_leaves;
+      for (int li = tid >> 3; li < nl; li += blockDim.x >> 3) {
+        const int nd = leaf_list[li];
+        const float r = leaf_sum8(sq + sub.off[nd], sub.len[nd], j, gmask);
+        if (j == 0) sub.val[nd] = r;
+      }
     }
     __syncthreads();
     heap_combine(sub, 128);
@@ -246,7 +297,8 @@ extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_
     attr_done = true;
   }
   clip_power_kernel<<<n_clips, 256, kSubMax * 4, as_stream(stream)>>>(
-      audio_dev, dtype, reinterpret_cast<const long long*>(offsets_dev), lengths_dev, power_dev);
+      audio_dev, dtype, reinterpret_cast<const long long*>(offsets_dev), lengths_dev, power_dev,
+      (reinterpret_cast<uintptr_t>(audio_dev) & 15) == 0 ? 1 : 0);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }
