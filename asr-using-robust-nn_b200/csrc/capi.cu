@@ -167,7 +167,10 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
   pl->fft_path = fft_shape(p.n_fft, &fs) ? 1 : 0;
   pl->fb = pl->fft_path ? kWarps * (32 / fs.G) : kWarps;
   const int s_off = pl->fft_path ? 0 : round4(p.n_fft);
-  pl->frame_stride = pl->fft_path ? pitch_odd4(2 * (fs.M + fs.G)) : pitch_odd4(s_off + round4(pl->n_bins + 16));
+  // FFT paths: two half-warps work on adjacent frame buffers; a stride of 16 (mod 32) words puts their
+  // 64-byte rows in complementary bank halves
+  auto stride16 = [](int x) { int v = (x + 31) / 32 * 32 + 16; return v - 32 >= x ? v - 32 : v; };
+  pl->frame_stride = pl->fft_path ? stride16(2 * (fs.M + fs.G)) : pitch_odd4(s_off + round4(pl->n_bins + 16));
   pl->chunk_cap = ((pl->fb - 1) * p.hop_length + p.n_fft + 8 + 7) & ~7;   // + up to 7 samples of alignment shift
   pl->lm_pitch = pitch_odd4(p.n_mels);
   pl->dct_pitch = round4(p.n_mels);
@@ -219,7 +222,14 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
     for (int r = 0; r < 8; ++r)
       if (round < bucket[r].size()) order.push_back(bucket[r][round]);
   pl->n_tasks_padded = std::max(spf, (pl->n_tasks + spf - 1) / spf * spf);
-  pl->part_pitch = round4(pl->n_tasks + 1);                    // slot n_tasks swallows the padding tasks
+  pl->part_pitch = round4(pl->n_tasks + 2);                    // slot n_tasks swallows the padding tasks, slot n_tasks+1 stays 0
+  // per filter: up to 8 partial slots in summation order, padded with the always-zero slot
+  int max_tasks = 0;
+  for (int i = 0; i < p.n_mels; ++i) max_tasks = std::max(max_tasks, ftasks[2 * i + 1]);
+  pl->fixed_slots = max_tasks <= 8 ? 1 : 0;
+  std::vector<int> fslots(8 * static_cast<size_t>(p.n_mels), pl->n_tasks + 1);
+  for (int i = 0; i < p.n_mels; ++i)
+    for (int u = 0; u < std::min(8, ftasks[2 * i + 1]); ++u) fslots[8 * i + u] = ftasks[2 * i] + u;
   std::vector<int> task_tab(2 * static_cast<size_t>(pl->n_tasks_padded), 0);
   std::vector<float> melw_q(static_cast<size_t>(kMelChunkQuads) * pl->n_tasks_padded * 4, 0.0f);
   for (int tp = 0; tp < pl->n_tasks_padded; ++tp) {
@@ -237,7 +247,7 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
   }
   // ---- DCT-II ortho rows [0, n_mfcc) with the lifter folded in ----
   pl->h_dct.assign(static_cast<size_t>(p.n_mfcc) * p.n_mels, 0.0f);
-  std::vector<float> dct_p(static_cast<size_t>(p.n_mfcc) * pl->dct_pitch, 0.0f);
+  std::vector<float> dct_p(static_cast<size_t>(round4(p.n_mfcc)) * pl->dct_pitch, 0.0f);   // zero rows pad the last group of 4
   for (int c = 0; c < p.n_mfcc; ++c) {
     const double sc = c == 0 ? std::sqrt(1.0 / p.n_mels) : std::sqrt(2.0 / p.n_mels);
     const double lift = p.lifter > 0 ? 1.0 + (p.lifter / 2.0) * std::sin(kPi * (c + 1) / p.lifter) : 1.0;
@@ -309,6 +319,7 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
   pl->off_tasks = put_i(task_tab.data(), task_tab.size());
   pl->off_melw = put_f(melw_q.data(), melw_q.size());
   pl->off_ftasks = put_i(ftasks.data(), ftasks.size());
+  pl->off_fslots = put_i(fslots.data(), fslots.size());
   pl->off_dct = put_f(dct_p.data(), dct_p.size());
   pl->off_taps = put_f(pl->h_taps.data(), pl->h_taps.size());
   pl->blob_floats = static_cast<int>(blob.size());
@@ -412,7 +423,8 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
   kp.blob_f4 = plan->blob_floats / 4;
   kp.off_window = plan->off_window; kp.off_window_i16 = plan->off_window_i16; kp.off_twp = plan->off_twp; kp.off_twu = plan->off_twu;
   kp.off_tasks = plan->off_tasks; kp.off_melw = plan->off_melw;
-  kp.off_ftasks = plan->off_ftasks; kp.off_dct = plan->off_dct;
+  kp.off_ftasks = plan->off_ftasks; kp.off_fslots = plan->off_fslots; kp.fixed_slots = plan->fixed_slots;
+  kp.off_dct = plan->off_dct;
   kp.off_taps = plan->off_taps;
   // ---- cluster size + dynamic shared memory layout ----
   // One CTA holds the log-mel rows of ceil(T/cs) frames; grow the cluster until that fits, then keep

@@ -60,11 +60,11 @@ struct KParams {
   int fb;             // frames per batch (frame buffers per CTA)
   int frame_stride;   // floats between frame buffers (frame_stride/4 odd)
   int chunk_cap;      // floats of staged audio per batch
-  int n_tasks, n_tasks_padded, part_pitch;
+  int n_tasks, n_tasks_padded, part_pitch, fixed_slots;
   // ---- table blob (global) and section offsets in floats ----
   const float4* blob;
   int blob_f4;
-  int off_window, off_window_i16, off_twp, off_twu, off_tasks, off_melw, off_ftasks, off_dct, off_taps;
+  int off_window, off_window_i16, off_twp, off_twu, off_tasks, off_melw, off_ftasks, off_fslots, off_dct, off_taps;
   // ---- dynamic shared-memory layout, offsets in floats ----
   int sm_frames, sm_part, sm_lm, sm_cbuf, sm_red;
   int t_cap;          // frame capacity of one CTA's log-mel buffer
@@ -89,8 +89,8 @@ struct asr_plan {
   int frame_stride;
   int chunk_cap;
   int lm_pitch, dct_pitch;
-  int n_tasks, n_tasks_padded, part_pitch;
-  int off_window, off_window_i16, off_twp, off_twu, off_tasks, off_melw, off_ftasks, off_dct, off_taps;
+  int n_tasks, n_tasks_padded, part_pitch, fixed_slots;
+  int off_window, off_window_i16, off_twp, off_twu, off_tasks, off_melw, off_ftasks, off_fslots, off_dct, off_taps;
   int blob_floats;
   float* blob_dev;
   int device;

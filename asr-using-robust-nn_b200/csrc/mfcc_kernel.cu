@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(c
   const int2* s_tasks = reinterpret_cast<const int2*>(smem + kp.off_tasks);
   const float4* s_melw = reinterpret_cast<const float4*>(smem + kp.off_melw);
   const int2* s_ftasks = reinterpret_cast<const int2*>(smem + kp.off_ftasks);
+  const int4* s_fslots = reinterpret_cast<const int4*>(smem + kp.off_fslots);
   const float* s_dct = smem + kp.off_dct;
   const float* s_taps = smem + kp.off_taps;
   float* s_frames = smem + kp.sm_frames;
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(c
   const int s_off = (NFFT == 0) ? ((kp.n_fft + 3) & ~3) : 0;
   float run_max = -3.0e38f;
 
+  for (int i = tid; i < kp.fb * kp.part_pitch; i += kThreads) s_part[i] = 0.0f;   // incl. the always-zero slots
   __syncthreads();                                  // tables and the zeroed log-mel rows are visible
 
   // ---- main loop: every warp runs frames -> power spectra -> mel -> log on its own (no CTA barrier) ----
@@ -524,16 +526,35 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(c
     }
     __syncwarp();
     // ---- combine partials in filter order, 10*log10, running clip max ----
-    for (int j = 0; j < nbw; ++j) {
-      const float* prt = wpart + j * kp.part_pitch;
-      float* lrow = s_lm + (tw + j - f0) * kp.lm_pitch;
+    if (kp.fixed_slots) {
+      // every filter has <= 8 tasks: slot lists padded with the always-zero slot, both frames in one pass
       for (int i = lane; i < kp.n_mels; i += 32) {
-        const int2 ft = s_ftasks[i];
-        float m = 0.0f;
-        for (int u = 0; u < ft.y; ++u) m += prt[ft.x + u];
-        const float db = 3.01029995663981195f * __log2f(fmaxf(kp.amin, m));
-        lrow[i] = db;
-        run_max = fmaxf(run_max, db);
+        const int4 sa = s_fslots[2 * i], sb = s_fslots[2 * i + 1];
+#pragma unroll
+        for (int j = 0; j < FPW; ++j) {
+          if (j < nbw) {
+            const float* prt = wpart + j * kp.part_pitch;
+            float m = prt[sa.x];
+            m += prt[sa.y]; m += prt[sa.z]; m += prt[sa.w];
+            m += prt[sb.x]; m += prt[sb.y]; m += prt[sb.z]; m += prt[sb.w];
+            const float db = 3.01029995663981195f * __log2f(fmaxf(kp.amin, m));
+            s_lm[(tw + j - f0) * kp.lm_pitch + i] = db;
+            run_max = fmaxf(run_max, db);
+          }
+        }
+      }
+    } else {
+      for (int j = 0; j < nbw; ++j) {
+        const float* prt = wpart + j * kp.part_pitch;
+        float* lrow = s_lm + (tw + j - f0) * kp.lm_pitch;
+        for (int i = lane; i < kp.n_mels; i += 32) {
+          const int2 ft = s_ftasks[i];
+          float m = 0.0f;
+          for (int u = 0; u < ft.y; ++u) m += prt[ft.x + u];
+          const float db = 3.01029995663981195f * __log2f(fmaxf(kp.amin, m));
+          lrow[i] = db;
+          run_max = fmaxf(run_max, db);
+        }
       }
     }
     __syncwarp();                                     // partials / frame buffers are reused next iteration
@@ -591,24 +612,31 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(c
   // ---- DCT-II (ortho) with the lifter folded into the matrix: lanes <-> frames ----
   const bool has_delta = kp.delta_orders > 0;
   const int nq = kp.dct_pitch / 4;
+  const int ncg = (kp.n_mfcc + 3) / 4;                // coefficient groups of 4 (table rows padded with zeros)
   if (!has_delta) {
     const int w = max(0, o1 - f0);
     const int n_tblk = (w + 31) / 32;
-    for (int item = warp; item < n_tblk * kp.n_mfcc; item += kWarps) {
-      const int c = item % kp.n_mfcc, r = (item / kp.n_mfcc) * 32 + lane;
+    for (int item = warp; item < n_tblk * ncg; item += kWarps) {
+      const int cg = item % ncg, r = (item / ncg) * 32 + lane;
       if (r < w) {
         const float4* l4 = reinterpret_cast<const float4*>(s_lm + r * kp.lm_pitch);
-        const float4* d4 = reinterpret_cast<const float4*>(s_dct + c * kp.dct_pitch);
-        float acc = 0.0f;
+        const float4* d4 = reinterpret_cast<const float4*>(s_dct + 4 * cg * kp.dct_pitch);
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (int q = 0; q < nq; ++q) {
           const float4 lv = l4[q];
-          const float4 dv = d4[q];
-          acc = fmaf(lv.x, dv.x, acc);
-          acc = fmaf(lv.y, dv.y, acc);
-          acc = fmaf(lv.z, dv.z, acc);
-          acc = fmaf(lv.w, dv.w, acc);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 dv = d4[u * nq + q];
+            acc[u] = fmaf(lv.x, dv.x, acc[u]);
+            acc[u] = fmaf(lv.y, dv.y, acc[u]);
+            acc[u] = fmaf(lv.z, dv.z, acc[u]);
+            acc[u] = fmaf(lv.w, dv.w, acc[u]);
+          }
         }
-        store_out(kp, out_base + static_cast<long long>(c) * kp.out_frames + f0 + r, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (4 * cg + u < kp.n_mfcc)
+            store_out(kp, out_base + static_cast<long long>(4 * cg + u) * kp.out_frames + f0 + r, acc[u]);
       }
     }
     if (cs > 1) cluster.sync();
@@ -625,24 +653,29 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(c
     const int need_lo = min(f0, c_first - half), need_hi = max(o1 - 1, c_last + half);   // inclusive
     const int wn = need_hi - need_lo + 1;
     const int n_tblk = (wn + 31) / 32;
-    for (int item = warp; item < n_tblk * kp.n_mfcc; item += kWarps) {
-      const int c = item % kp.n_mfcc, r = (item / kp.n_mfcc) * 32 + lane;
+    for (int item = warp; item < n_tblk * ncg; item += kWarps) {
+      const int cg = item % ncg, r = (item / ncg) * 32 + lane;
       if (r < wn) {
         const int t = need_lo + r;
         const int owner = t / FC;
         const float* row = (owner == rank ? s_lm : cluster.map_shared_rank(s_lm, owner)) + (t - owner * FC) * kp.lm_pitch;
         const float4* l4 = reinterpret_cast<const float4*>(row);
-        const float4* d4 = reinterpret_cast<const float4*>(s_dct + c * kp.dct_pitch);
-        float acc = 0.0f;
+        const float4* d4 = reinterpret_cast<const float4*>(s_dct + 4 * cg * kp.dct_pitch);
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         for (int q = 0; q < nq; ++q) {
           const float4 lv = l4[q];
-          const float4 dv = d4[q];
-          acc = fmaf(lv.x, dv.x, acc);
-          acc = fmaf(lv.y, dv.y, acc);
-          acc = fmaf(lv.z, dv.z, acc);
-          acc = fmaf(lv.w, dv.w, acc);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 dv = d4[u * nq + q];
+            acc[u] = fmaf(lv.x, dv.x, acc[u]);
+            acc[u] = fmaf(lv.y, dv.y, acc[u]);
+            acc[u] = fmaf(lv.z, dv.z, acc[u]);
+            acc[u] = fmaf(lv.w, dv.w, acc[u]);
+          }
         }
-        s_cbuf[c * kp.cbuf_pitch + r] = acc;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (4 * cg + u < kp.n_mfcc) s_cbuf[(4 * cg + u) * kp.cbuf_pitch + r] = acc[u];
       }
     }
     __syncthreads();
