@@ -14,162 +14,129 @@ namespace asr {
 //   n < 8    : serial
 //   n <= 128 : 8 strided accumulators, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail serially
 //   else     : n2 = n/2 - (n/2 % 8) ; pairwise(a, n2) + pairwise(a+n2, n-n2)
-// The recursion tree only depends on n.  It is laid out as a binary heap in shared memory
-// (node i -> children 2i, 2i+1), leaves are summed one thread each, parents level by level.
-constexpr int kHeap = 512;        // 9 levels: enough for any sub-tree of <= kSubMax elements
-constexpr int kHeapLevels = 8;    // levels that can still split
-constexpr int kSubMax = 16384;    // elements staged in shared memory per sub-tree (64 KB)
+// The recursion tree only depends on n.  One WARP per clip walks it depth-first with an explicit
+// (offset, length, depth) stack, takes the leaves (n <= 128) four at a time - one leaf per group of 8
+// lanes, lane j of a group owning numpy's accumulator r[j] - and folds the leaf sums with a
+// (value, depth) stack: two entries of equal depth are siblings and merge into their parent, which is
+// exactly the order numpy adds them in.  No shared-memory staging, no CTA barriers.
+constexpr int kPowWarps = 8;
+constexpr int kPowStack = 40;     // > depth of the tree for any int32 length
 
-struct Heap {
-  int off[kHeap];
-  int len[kHeap];
-  float val[kHeap];
+struct PowScratch {               // per warp
+  int s_off[kPowStack], s_len[kPowStack], s_dep[kPowStack];
+  float v_val[kPowStack];
+  int v_dep[kPowStack];
+  int l_off[4], l_len[4], l_dep[4];
 };
 
-// Expand node 1 = (off0, n0): nodes longer than `limit` split the way numpy does.
-__device__ void heap_expand(Heap& h, const int off0, const int n0, const int limit) {
-  const int tid = threadIdx.x;
-  for (int i = tid; i < kHeap; i += blockDim.x) h.len[i] = 0;
-  __syncthreads();
-  if (tid == 0) { h.off[1] = off0; h.len[1] = n0; }
-  __syncthreads();
-  for (int d = 0; d < kHeapLevels; ++d) {
-    const int first = 1 << d;
-    for (int t = tid; t < first; t += blockDim.x) {
-      const int i = first + t;
-      const int n = h.len[i];
-      if (n > limit) {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        h.off[2 * i] = h.off[i];         h.len[2 * i] = n2;
-        h.off[2 * i + 1] = h.off[i] + n2; h.len[2 * i + 1] = n - n2;
-      }
-    }
-    __syncthreads();
-  }
+template <int DT>
+__device__ __forceinline__ float load_sq(const void* __restrict__ audio, const long long i) {
+  float x;
+  if (DT == ASR_I16) x = static_cast<float>(__ldg(reinterpret_cast<const short*>(audio) + i)) * (1.0f / 32768.0f);
+  else x = __ldg(reinterpret_cast<const float*>(audio) + i);
+  return __fmul_rn(x, x);        // sample**2, exact float32 product
 }
 
-// Sum parents bottom-up; a node is a parent iff its length exceeds `limit`.
-__device__ void heap_combine(Heap& h, const int limit) {
-  const int tid = threadIdx.x;
-  for (int d = kHeapLevels - 1; d >= 0; --d) {
-    const int first = 1 << d;
-    for (int t = tid; t < first; t += blockDim.x) {
-      const int i = first + t;
-      if (h.len[i] > limit) h.val[i] = __fadd_rn(h.val[2 * i], h.val[2 * i + 1]);
-    }
-    __syncthreads();
-  }
-}
-
-// One leaf (n <= 128) summed by a group of 8 lanes, lane j owning numpy's accumulator r[j]; the xor-shuffle
-// tree reproduces ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) (float addition is commutative), lane 0 adds the tail.
-__device__ __forceinline__ float leaf_sum8(const float* __restrict__ a, const int n, const int j, const unsigned gmask) {
+// One leaf (n <= 128) summed by a group of 8 lanes; the xor-shuffle tree reproduces
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) (float addition is commutative), lane 0 of the group adds the tail.
+template <int DT>
+__device__ __forceinline__ float leaf_sum8(const void* __restrict__ audio, const long long e0, const int n, const int j) {
+  float r = 0.0f;
   if (n < 8) {
-    float res = 0.0f;
     if (j == 0)
-      for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
-    return res;
+      for (int i = 0; i < n; ++i) r = __fadd_rn(r, load_sq<DT>(audio, e0 + i));
+  } else {
+    const int n8 = n - (n % 8);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (8 * i < n8) ? load_sq<DT>(audio, e0 + 8 * i + j) : 0.0f;
+    r = v[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i)
+      if (8 * i < n8) r = __fadd_rn(r, v[i]);
   }
-  const int n8 = n - (n % 8);
-  float r = a[j];
-  for (int i = 8; i < n8; i += 8) r = __fadd_rn(r, a[i + j]);
-  r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1));
-  r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 2));
-  r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 4));
-  if (j == 0)
-    for (int i = n8; i < n; ++i) r = __fadd_rn(r, a[i]);
+  // all 32 lanes shuffle (groups with no leaf carry zeros); xor < 8 stays inside the group
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+  if (n >= 8 && j == 0) {
+    const int n8 = n - (n % 8);
+    for (int i = n8; i < n; ++i) r = __fadd_rn(r, load_sq<DT>(audio, e0 + i));
+  }
   return r;
 }
 
-__global__ void __launch_bounds__(256) clip_power_kernel(const void* __restrict__ audio, const int dtype,
-                                                         const long long* __restrict__ offsets,
-                                                         const int* __restrict__ lengths, float* __restrict__ power,
-                                                         const int vec_ok) {
-  extern __shared__ __align__(16) float sq[];   // kSubMax squares
-  __shared__ Heap top, sub;
-  __shared__ int leaf_list[kHeap];
-  __shared__ int n_leaves;
-  const int b = blockIdx.x, tid = threadIdx.x;
+template <int DT>
+__global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* __restrict__ audio,
+                                                                     const long long* __restrict__ offsets,
+                                                                     const int* __restrict__ lengths,
+                                                                     float* __restrict__ power, const int n_clips) {
+  __shared__ PowScratch scratch[kPowWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kPowWarps + warp;
+  if (b >= n_clips) return;
+  PowScratch& sc = scratch[warp];
   const int L = lengths[b];
   const long long base = offsets[b];
-  if (L <= 0 || L > 4000000) {                  // np.mean of an empty array is nan; > 4M samples exceeds the heap depth
-    if (tid == 0) power[b] = __int_as_float(0x7fc00000);
+  if (L <= 0) {                                   // np.mean of an empty array is nan
+    if (lane == 0) power[b] = __int_as_float(0x7fc00000);
     return;
   }
-  heap_expand(top, 0, L, kSubMax);
-  for (int node = 1; node < kHeap; ++node) {
-    const int n = top.len[node];
-    if (n <= 0 || n > kSubMax) continue;          // absent or internal (uniform over the block)
-    const int off = top.off[node];
-    // ---- stage sample**2 (exact float32 products) for this sub-tree ----
-    const long long e0 = base + off;
-    if (vec_ok && (e0 & 7) == 0) {
-      const int n8 = n & ~7;
-      if (dtype == ASR_I16) {
-        const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const short*>(audio) + e0);
-        for (int g = tid; g < n8 / 8; g += blockDim.x) {
-          const int4 raw = __ldg(p + g);
-          const int w[4] = {raw.x, raw.y, raw.z, raw.w};
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float x0 = static_cast<float>(static_cast<short>(w[j])) * (1.0f / 32768.0f);
-            const float x1 = static_cast<float>(w[j] >> 16) * (1.0f / 32768.0f);
-            v[2 * j] = __fmul_rn(x0, x0);
-            v[2 * j + 1] = __fmul_rn(x1, x1);
-          }
-          float4* d = reinterpret_cast<float4*>(sq + 8 * g);
-          d[0] = make_float4(v[0], v[1], v[2], v[3]);
-          d[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-      } else {
-        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(audio) + e0);
-        for (int g = tid; g < n8 / 4; g += blockDim.x) {
-          const float4 x = __ldg(p + g);
-          reinterpret_cast<float4*>(sq)[g] = make_float4(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y), __fmul_rn(x.z, x.z),
-                                                        __fmul_rn(x.w, x.w));
+  const int g = lane >> 3, j = lane & 7;
+  int sp = 0, vp = 0;                             // stack pointers (uniform over the warp)
+  if (lane == 0) { sc.s_off[0] = 0; sc.s_len[0] = L; sc.s_dep[0] = 0; }
+  sp = 1;
+  __syncwarp();
+  while (sp > 0) {
+    // ---- lane 0 pops nodes until it holds up to 4 leaves (left-to-right order) ----
+    int n_leaf = 0;
+    if (lane == 0) {
+      while (sp > 0 && n_leaf < 4) {
+        --sp;
+        const int off = sc.s_off[sp], n = sc.s_len[sp], d = sc.s_dep[sp];
+        if (n > 128) {
+          int n2 = n / 2;
+          n2 -= n2 % 8;
+          sc.s_off[sp] = off + n2; sc.s_len[sp] = n - n2; sc.s_dep[sp] = d + 1;   // right child, visited later
+          sc.s_off[sp + 1] = off;  sc.s_len[sp + 1] = n2; sc.s_dep[sp + 1] = d + 1;
+          sp += 2;
+        } else {
+          sc.l_off[n_leaf] = off; sc.l_len[n_leaf] = n; sc.l_dep[n_leaf] = d;
+          ++n_leaf;
         }
       }
-      for (int i = n8 + tid; i < n; i += blockDim.x) {
-        float x;
-        if (dtype == ASR_I16) x = static_cast<float>(__ldg(reinterpret_cast<const short*>(audio) + e0 + i)) * (1.0f / 32768.0f);
-        else x = __ldg(reinterpret_cast<const float*>(audio) + e0 + i);
-        sq[i] = __fmul_rn(x, x);
-      }
-    } else {
-      for (int i = tid; i < n; i += blockDim.x) {
-        float x;
-        if (dtype == ASR_I16) x = static_cast<float>(__ldg(reinterpret_cast<const short*>(audio) + e0 + i)) * (1.0f / 32768.0f);
-        else x = __ldg(reinterpret_cast<const float*>(audio) + e0 + i);
-        sq[i] = __fmul_rn(x, x);
-      }
     }
-    if (tid == 0) n_leaves = 0;
-    heap_expand(sub, 0, n, 128);                   // barriers inside also publish sq[] and n_leaves
-    for (int i = 1 + tid; i < kHeap; i += blockDim.x) {
-      const int ln = sub.len[i];
-      if (ln > 0 && ln <= 128) leaf_list[atomicAdd(&n_leaves, 1)] = i;
-    }
-    __syncthreads();
+    n_leaf = __shfl_sync(0xffffffffu, n_leaf, 0);
+    sp = __shfl_sync(0xffffffffu, sp, 0);
+    __syncwarp();
+    float r = 0.0f;
     {
-      const int j = tid & 7;
-      const unsigned gmask = 0xFFu << (threadIdx.x & 24);
-      const int nl = n_leaves;
-      for (int li = tid >> 3; li < nl; li += blockDim.x >> 3) {
-        const int nd = leaf_list[li];
-        const float r = leaf_sum8(sq + sub.off[nd], sub.len[nd], j, gmask);
-        if (j == 0) sub.val[nd] = r;
+      const bool have = g < n_leaf;
+      const int off = have ? sc.l_off[g] : 0, n = have ? sc.l_len[g] : 0;
+      r = leaf_sum8<DT>(audio, base + off, n, j);
+    }
+    // ---- fold the leaf sums: equal depth on top of the value stack = siblings ----
+    const float r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 8);
+    const float r2 = __shfl_sync(0xffffffffu, r, 16), r3 = __shfl_sync(0xffffffffu, r, 24);
+    if (lane == 0) {
+      const float rs[4] = {r0, r1, r2, r3};
+      for (int q = 0; q < n_leaf; ++q) {
+        float v = rs[q];
+        int d = sc.l_dep[q];
+        while (vp > 0 && sc.v_dep[vp - 1] == d) {
+          --vp;
+          v = __fadd_rn(sc.v_val[vp], v);         // left + right
+          --d;
+        }
+        sc.v_val[vp] = v; sc.v_dep[vp] = d;
+        ++vp;
       }
     }
-    __syncthreads();
-    heap_combine(sub, 128);
-    if (tid == 0) top.val[node] = sub.val[1];
-    __syncthreads();
+    vp = __shfl_sync(0xffffffffu, vp, 0);
+    __syncwarp();
   }
-  heap_combine(top, kSubMax);
   // np.mean: float32 sum / count evaluated in float64, rounded to float32
-  if (tid == 0) power[b] = static_cast<float>(static_cast<double>(top.val[1]) / static_cast<double>(L));
+  if (lane == 0) power[b] = static_cast<float>(static_cast<double>(sc.v_val[0]) / static_cast<double>(L));
 }
 
 __global__ void snr_sigma_kernel(const float* __restrict__ power, const float snr_db, double* __restrict__ sigma,
@@ -291,14 +258,12 @@ extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_
     return ASR_ERR_INVALID;
   }
   if (n_clips == 0) return ASR_OK;
-  static bool attr_done = false;
-  if (!attr_done) {
-    ASR_CUDA_TRY(cudaFuncSetAttribute(clip_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubMax * 4));
-    attr_done = true;
-  }
-  clip_power_kernel<<<n_clips, 256, kSubMax * 4, as_stream(stream)>>>(
-      audio_dev, dtype, reinterpret_cast<const long long*>(offsets_dev), lengths_dev, power_dev,
-      (reinterpret_cast<uintptr_t>(audio_dev) & 15) == 0 ? 1 : 0);
+  const int blocks = (n_clips + kPowWarps - 1) / kPowWarps;
+  const long long* off = reinterpret_cast<const long long*>(offsets_dev);
+  if (dtype == ASR_I16)
+    clip_power_kernel<ASR_I16><<<blocks, kPowWarps * 32, 0, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips);
+  else
+    clip_power_kernel<ASR_F32><<<blocks, kPowWarps * 32, 0, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }

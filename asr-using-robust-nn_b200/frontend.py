@@ -148,6 +148,8 @@ class Noise:
 class MfccPlan:
     """Immutable tables for one parameter set (wraps ``asr_plan``)."""
 
+    LAUNCHES = 1        # kernels of libasr_b200 one `mfcc` call launches
+
     def __init__(self, params: MfccParams, device: Optional[int] = None):
         _require_cuda()
         self.params = params
@@ -312,10 +314,13 @@ def mix_rows_mixture(x: torch.Tensor, q: torch.Tensor, g: torch.Tensor, p: float
     return out
 
 
-def randn(seed: int, first_index: int, n: int, device="cuda") -> torch.Tensor:
+def randn(seed: int, first_index: int, n: int, device="cuda", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Seeded float64 standard-normal stream; element i depends only on (seed, first_index + i)."""
     _require_cuda()
-    out = torch.empty(n, dtype=torch.float64, device=device)
+    if out is None:
+        out = torch.empty(n, dtype=torch.float64, device=device)
+    elif out.dtype != torch.float64 or out.numel() != n or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError("out must be a contiguous float64 CUDA tensor of n elements")
     with torch.cuda.device(out.device):
         check(lib.asr_randn_f64(int(seed), int(first_index), int(n), out.data_ptr(), _stream()), "asr_randn_f64")
     return out
@@ -337,7 +342,13 @@ class Standardizer:
         self.device = torch.device(device)
         self.group = group
         self.distributed = distributed
-        self.mean = self.var = self.scale = None
+        D = self.n_cols
+        # persistent float64 work vectors (stable addresses: the fit can be captured in CUDA graphs)
+        self.acc1 = torch.zeros(D + 1, dtype=torch.float64, device=self.device)    # [sum x (D), n]
+        self.acc2 = torch.zeros(2 * D, dtype=torch.float64, device=self.device)    # [sum (x-mean), sum (x-mean)^2]
+        self.mean = torch.zeros(D, dtype=torch.float64, device=self.device)
+        self.var = torch.zeros(D, dtype=torch.float64, device=self.device)
+        self.scale = torch.ones(D, dtype=torch.float64, device=self.device)
         self.n_total = 0
 
     def _allreduce(self, t: torch.Tensor) -> None:
@@ -351,37 +362,62 @@ class Standardizer:
             raise ValueError("row blocks must be 2-D float32/float64 with unit column stride")
         return x.data_ptr(), _DT[x.dtype], x.shape[0], x.shape[1], x.stride(0)
 
+    # The fit is three launch groups separated by the two all-reduces (the only inter-GPU exchange of the path).
+    def pass1_local(self, blocks: Sequence[torch.Tensor]) -> None:
+        """acc1 = [column sums of this rank's rows, number of rows]."""
+        D = self.n_cols
+        rows = 0
+        with torch.cuda.device(self.device):
+            self.acc1.zero_()
+            for x in blocks:
+                p, dt, r, c, ld = self._mat(x)
+                if c != D:
+                    raise ValueError(f"row block has {c} columns, expected {D}")
+                if r == 0:
+                    continue
+                check(lib.asr_cmvn_colsum(p, dt, r, c, ld, self.acc1.data_ptr(), _stream()), "asr_cmvn_colsum")
+                rows += r
+            self.acc1[D:].fill_(float(rows))
+
+    def pass2_local(self, blocks: Sequence[torch.Tensor], n_total: int) -> None:
+        """mean from the (all-reduced) acc1, then acc2 = centred sums of this rank's rows."""
+        D = self.n_cols
+        self.n_total = int(n_total)
+        with torch.cuda.device(self.device):
+            check(lib.asr_cmvn_mean(self.acc1.data_ptr(), self.n_total, D, self.mean.data_ptr(), _stream()), "asr_cmvn_mean")
+            self.acc2.zero_()
+            for x in blocks:
+                p, dt, r, c, ld = self._mat(x)
+                if r == 0:
+                    continue
+                check(lib.asr_cmvn_colsum_centered(p, dt, r, c, ld, self.mean.data_ptr(), self.acc2.data_ptr(), _stream()),
+                      "asr_cmvn_colsum_centered")
+
+    def finish(self) -> None:
+        """var / scale from the (all-reduced) acc2."""
+        with torch.cuda.device(self.device):
+            check(lib.asr_cmvn_finalize(self.acc2.data_ptr(), self.mean.data_ptr(), self.n_total, self.n_cols,
+                                        self.var.data_ptr(), self.scale.data_ptr(), _stream()), "asr_cmvn_finalize")
+
     def fit(self, blocks: Sequence[torch.Tensor], n_total: Optional[int] = None) -> "Standardizer":
         """`n_total` (rows over ALL ranks) may be given when the caller knows it; that avoids the one
         device->host read of the all-reduced count and keeps the whole fit asynchronous."""
-        D = self.n_cols
-        blocks = [x for x in blocks if x.shape[0] > 0]
-        with torch.cuda.device(self.device):
-            acc1 = torch.zeros(D + 1, dtype=torch.float64, device=self.device)   # [sum x (D), n]
-            for x in blocks:
-                p, dt, r, c, ld = self._mat(x)
-                assert c == D
-                check(lib.asr_cmvn_colsum(p, dt, r, c, ld, acc1.data_ptr(), _stream()), "asr_cmvn_colsum")
-                acc1[D] += r
-            self._allreduce(acc1)
-            self.n_total = int(round(acc1[D].item())) if n_total is None else int(n_total)
-            self.mean = torch.empty(D, dtype=torch.float64, device=self.device)
-            check(lib.asr_cmvn_mean(acc1.data_ptr(), self.n_total, D, self.mean.data_ptr(), _stream()), "asr_cmvn_mean")
-            acc2 = torch.zeros(2 * D, dtype=torch.float64, device=self.device)
-            for x in blocks:
-                p, dt, r, c, ld = self._mat(x)
-                check(lib.asr_cmvn_colsum_centered(p, dt, r, c, ld, self.mean.data_ptr(), acc2.data_ptr(), _stream()),
-                      "asr_cmvn_colsum_centered")
-            self._allreduce(acc2)
-            self.var = torch.empty(D, dtype=torch.float64, device=self.device)
-            self.scale = torch.empty(D, dtype=torch.float64, device=self.device)
-            check(lib.asr_cmvn_finalize(acc2.data_ptr(), self.mean.data_ptr(), self.n_total, D, self.var.data_ptr(),
-                                        self.scale.data_ptr(), _stream()), "asr_cmvn_finalize")
+        self.pass1_local(blocks)
+        self._allreduce(self.acc1)
+        if n_total is None:
+            n_total = int(round(self.acc1[self.n_cols].item()))
+        self.pass2_local(blocks, n_total)
+        self._allreduce(self.acc2)
+        self.finish()
         return self
 
-    def transform(self, x: torch.Tensor, out_dtype=torch.float64) -> torch.Tensor:
+    def transform(self, x: torch.Tensor, out_dtype=torch.float64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         p, dt, r, c, ld = self._mat(x)
-        out = torch.empty((r, c), dtype=out_dtype, device=x.device)
+        if out is None:
+            out = torch.empty((r, c), dtype=out_dtype, device=x.device)
+        elif out.shape != (r, c) or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous {(r, c)} tensor")
+        out_dtype = out.dtype
         with torch.cuda.device(x.device):
             check(lib.asr_cmvn_apply(p, dt, r, c, ld, self.mean.data_ptr(), self.scale.data_ptr(), out.data_ptr(),
                                      _DT[out_dtype], _stream()), "asr_cmvn_apply")

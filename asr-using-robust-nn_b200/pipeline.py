@@ -5,6 +5,11 @@ into the MFCC launch -> dataset standardisation of the feature rows (two-pass co
 all-reduced over NCCL when sharded) -> standardised ``(B, n_mfcc*T)`` rows.  Mirrors the loop body
 of ``Voice digit recogniton/attacks.py:402-407`` (``black_box_attack_on_audio_dataset_snr`` then
 ``standardize_dataset``).
+
+The launches of one step are short (tens of microseconds each) and their number is fixed, so the step is
+captured once per (batch buffers, SNR) in CUDA graphs and replayed: one graph per launch group, the
+groups being separated by the two NCCL all-reduces of the standardisation when clips are sharded over
+several GPUs (a single graph for the whole step on one GPU).
 """
 from __future__ import annotations
 
@@ -15,57 +20,155 @@ import torch
 from .frontend import ClipBatch, MfccPlan, Noise, Standardizer, clip_power, snr_sigma_device, randn
 from .params import MfccParams
 
-# kernels of libasr_b200 launched by one `run_device` step (power, sigma, mfcc, 2x colsum(partial+final),
-# mean, finalize, apply); the e2e step adds the randn launch
-LAUNCHES_PER_STEP = 10
-LAUNCHES_PER_STEP_CLEAN = 8
+# kernels of libasr_b200 launched by one `run_device` step: power, sigma, mfcc launches, 2x colsum
+# (partial + final), mean, finalize, apply; the e2e step adds the randn launch
+LAUNCHES_PER_STEP_CLEAN = 7 + MfccPlan.LAUNCHES
+LAUNCHES_PER_STEP = LAUNCHES_PER_STEP_CLEAN + 2
+
+
+class _StepGraphs:
+    """Captured launch groups of one step for fixed buffers."""
+
+    def __init__(self):
+        self.graphs = []       # [g1] or [g1, g2, g3]
+        self.out = None
+        self.keep = None       # tensors the graphs reference
 
 
 class NoisyFeaturePipeline:
     def __init__(self, params: MfccParams, out_frames: int, device=None, distributed: bool = False, group=None,
-                 world_size: int = 1):
+                 world_size: int = 1, use_graphs: bool = True):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.plan = MfccPlan(params, self.device.index)
         self.out_frames = int(out_frames)
         self.rows = self.plan.feature_rows
         self.D = self.rows * self.out_frames
         self.world_size = world_size
+        self.distributed = distributed
         self.std = Standardizer(self.D, device=self.device, group=group, distributed=distributed)
+        self.use_graphs = use_graphs
         self._feats = None
-        self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch
+        self._cache: dict = {}
+        self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch (eager steps only)
 
     def _feat_buffer(self, B: int) -> torch.Tensor:
         if self._feats is None or self._feats.shape[0] != B:
             self._feats = torch.empty((B, self.rows, self.out_frames), dtype=torch.float32, device=self.device)
         return self._feats
 
-    def run_device(self, batch: ClipBatch, z: Optional[torch.Tensor], snr_db: Optional[float],
-                   standardize: bool = True, out_dtype=torch.float32) -> torch.Tensor:
-        """Inputs resident in HBM; everything is asynchronous on the current stream."""
+    # ---- the three launch groups of a step ----------------------------------------------------------
+    def _group1(self, batch, z, snr_db, feats):
         noise = None
         if snr_db is not None:
             sigma = snr_sigma_device(clip_power(batch), snr_db)
             noise = Noise.white(z, sigma)
-        feats = self._feat_buffer(batch.n_clips)
         if self.ev_mfcc is not None:
             self.ev_mfcc[0].record()
         self.plan.mfcc(batch, out_frames=self.out_frames, noise=noise, out=feats)
         if self.ev_mfcc is not None:
             self.ev_mfcc[1].record()
+        return noise
+
+    def run_device(self, batch: ClipBatch, z: Optional[torch.Tensor], snr_db: Optional[float],
+                   standardize: bool = True, out_dtype=torch.float32) -> torch.Tensor:
+        """Inputs resident in HBM; everything is asynchronous on the current stream."""
+        if self.use_graphs and self.ev_mfcc is None:
+            return self._run_graphed(batch, z, snr_db, standardize, out_dtype)
+        feats = self._feat_buffer(batch.n_clips)
+        self._group1(batch, z, snr_db, feats)
         flat = feats.view(batch.n_clips, self.D)
         if not standardize:
             return flat
         self.std.fit([flat], n_total=batch.n_clips * self.world_size)
         return self.std.transform(flat, out_dtype=out_dtype)
 
+    def _run_graphed(self, batch, z, snr_db, standardize, out_dtype):
+        key = (batch.audio.data_ptr(), batch.n_clips, batch.max_length, None if z is None else z.data_ptr(), snr_db,
+               standardize, out_dtype)
+        sg = self._cache.get(key)
+        if sg is None:
+            if len(self._cache) > 32:
+                self._cache.clear()
+            sg = self._capture(batch, z, snr_db, standardize, out_dtype)
+            self._cache[key] = sg
+        if len(sg.graphs) == 1:
+            sg.graphs[0].replay()
+        else:
+            sg.graphs[0].replay()
+            self.std._allreduce(self.std.acc1)
+            sg.graphs[1].replay()
+            self.std._allreduce(self.std.acc2)
+            sg.graphs[2].replay()
+        return sg.out
+
+    def _capture(self, batch, z, snr_db, standardize, out_dtype) -> _StepGraphs:
+        B = batch.n_clips
+        n_total = B * self.world_size
+        sg = _StepGraphs()
+        feats = torch.empty((B, self.rows, self.out_frames), dtype=torch.float32, device=self.device)
+        flat = feats.view(B, self.D)
+        out = torch.empty((B, self.D), dtype=out_dtype, device=self.device) if standardize else flat
+        sg.out, sg.keep = out, (batch, z, feats)
+        # warm the kernels once outside capture (lazy module loading is not capturable)
+        self._group1(batch, z, snr_db, feats)
+        if standardize:
+            self.std.fit([flat], n_total=n_total)
+            self.std.transform(flat, out=out)
+        torch.cuda.synchronize(self.device)
+        pool = torch.cuda.graph_pool_handle()
+
+        def cap(fn):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                fn()
+            sg.graphs.append(g)
+
+        def g1():
+            self._group1(batch, z, snr_db, feats)
+            if standardize:
+                self.std.pass1_local([flat])
+
+        def g2():
+            self.std.pass2_local([flat], n_total)
+
+        def g3():
+            self.std.finish()
+            self.std.transform(flat, out=out)
+
+        if not standardize:
+            cap(lambda: self._group1(batch, z, snr_db, feats))
+        elif self.distributed:
+            cap(g1); cap(g2); cap(g3)
+        else:
+            cap(lambda: (g1(), g2(), g3()))
+        return sg
+
     def run_host(self, audio_host: torch.Tensor, snr_db: Optional[float], seed: int, out_host: torch.Tensor,
                  first_index: int = 0) -> torch.Tensor:
         """End to end from PINNED host memory: (B, L) int16/float32 host tensor in, standardised
         float32 (B, D) rows written to the pinned `out_host`.  The noise stream is generated on the
         device from `seed` (element index = first_index + position in this shard)."""
-        dev_audio = audio_host.to(self.device, non_blocking=True)
+        dev_audio = self._h2d_buffer(audio_host)
+        dev_audio.copy_(audio_host, non_blocking=True)
         batch = ClipBatch.from_matrix(dev_audio)
-        z = randn(seed, first_index, dev_audio.numel(), device=self.device) if snr_db is not None else None
+        z = None
+        if snr_db is not None:
+            z = self._z_buffer(dev_audio.numel())
+            randn(seed, first_index, dev_audio.numel(), device=self.device, out=z)
         out = self.run_device(batch, z, snr_db)
         out_host.copy_(out, non_blocking=True)
         return out_host
+
+    def _h2d_buffer(self, audio_host: torch.Tensor) -> torch.Tensor:
+        b = getattr(self, "_h2d", None)
+        if b is None or b.shape != audio_host.shape or b.dtype != audio_host.dtype:
+            b = torch.empty(audio_host.shape, dtype=audio_host.dtype, device=self.device)
+            self._h2d = b
+        return b
+
+    def _z_buffer(self, n: int) -> torch.Tensor:
+        b = getattr(self, "_z", None)
+        if b is None or b.numel() != n:
+            b = torch.empty(n, dtype=torch.float64, device=self.device)
+            self._z = b
+        return b

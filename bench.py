@@ -256,32 +256,52 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # samples through warm-up and the timed region
+    for i in range(4 if noisy else 1):                              # setup: capture the step's CUDA graphs (one per SNR)
+        step(i)
     for i in range(W):
         step(i)
     sync_all()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(K):
-        pipe.ev_mfcc = ev[i]
         step(i)
     t_end.record()
-    pipe.ev_mfcc = None
     sync_all()
-    clocks = sampler.stop() if sampler else None
     ms_total = t_start.elapsed_time(t_end)
-    ms_mfcc = sum(a.elapsed_time(b) for a, b in ev) / K
     if dist is not None:
         tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
+    # keep the GPU under the same load until nvidia-smi (100 ms period) has samples; same count on every rank
+    n_extra = int(max(0.0, 1500.0 - ms_total) / max(ms_total / K, 1e-3))
+    for i in range(n_extra):
+        step(i)
+    sync_all()
+    clocks = sampler.stop() if sampler else None
     value = B * world * K / (ms_total * 1e-3)
+
+    # ---- the dominant kernel alone: the same MFCC launch (same buffers, same noise descriptor) K times,
+    #      a CUDA event pair around every launch on the launching stream ----
+    feats_k = torch.empty((B, pipe.rows, pipe.out_frames), dtype=torch.float32, device=dev)
+    noise_k = None
+    if noisy:
+        noise_k = A.Noise.white(z, A.snr_sigma_device(A.clip_power(batch), 10.0))
+    Kk = max(5, min(K, 50))
+    for _ in range(2):
+        pipe.plan.mfcc(batch, out_frames=pipe.out_frames, noise=noise_k, out=feats_k)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
+    for a_, b_ in ev:
+        a_.record()
+        pipe.plan.mfcc(batch, out_frames=pipe.out_frames, noise=noise_k, out=feats_k)
+        b_.record()
+    torch.cuda.synchronize()
+    ms_mfcc = sum(a_.elapsed_time(b_) for a_, b_ in ev) / Kk
 
     # ---------------- e2e: pinned host in -> pinned host out, copies in the timed region ----------------
     e2e = None
     if not args.no_e2e:
-        for i in range(2):
+        for i in range(4):
             pipe.run_host(audio_host, SNRS[i % 4] if noisy else None, 99, out_host, first_index=rank * B * L)
         sync_all()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -311,6 +331,8 @@ def main():
     tfl = flops * B / (ms_mfcc * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                 "traffic": ncu_traffic(args.workload, B), "kernel": "asr::mfcc_kernel", "kernel_ms": ms_mfcc,
+                "kernel_timing": f"mean of {Kk} launches of the step's MFCC kernel on the step's buffers, one CUDA event pair "
+                                 "per launch, taken right after the timed region (the step itself replays a CUDA graph)",
                 "kernel_share_of_step": ms_mfcc / (ms_total / K), "peak_source": peak_src,
                 "algorithmic_bytes_per_clip": byts, "algorithmic_flops_per_clip": flops,
                 "binding": "fp32 (non-tensor CUDA cores); the HBM fraction is reported because the schema asks for it",
