@@ -1,0 +1,81 @@
+"""The C-ABI library loads and exports every symbol ``include/asr_b200.h`` declares; the ctypes binding
+covers the same set; without a CUDA device the entry points fail loudly (there is no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "asr_b200.h")
+LIB = os.path.join(ROOT, "asr-using-robust-nn_b200", "libasr_b200.so")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][A-Za-z0-9_]*\s*\*?\s*(asr_[a-z0-9_]+)\s*\(", src, flags=re.M)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.dirname(LIB), "-j4"], check=True)
+    return ctypes.CDLL(LIB)
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    for must in ("asr_plan_create", "asr_plan_destroy", "asr_mfcc_batch", "asr_mfcc_batch_host", "asr_clip_power",
+                 "asr_snr_sigma", "asr_mix_white", "asr_mix_mixture", "asr_randn_f64", "asr_cmvn_colsum",
+                 "asr_cmvn_colsum_centered", "asr_cmvn_finalize", "asr_cmvn_apply", "asr_last_error", "asr_version"):
+        assert must in names
+    assert len(names) >= 24
+
+
+def test_library_exports_every_declared_symbol(lib):
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+
+
+def test_ctypes_binding_matches_header():
+    from asr_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+
+
+def test_version_and_struct_layout(lib):
+    from asr_b200 import _lib
+    lib.asr_version.restype = ctypes.c_int
+    assert lib.asr_version() == 100
+    assert ctypes.sizeof(_lib.MfccParamsC) == 18 * 4          # 12 int32 + 6 float, no padding
+    assert ctypes.sizeof(_lib.NoiseC) == 8 + 3 * 8 + 3 * 8
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU the plan cannot be created: ASR_ERR_CUDA and a message, never a silent CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from asr_b200 import _lib, params
+    h = ctypes.c_void_p()
+    pc = params.C1.to_c()
+    rc = _lib.lib.asr_plan_create(ctypes.byref(pc), ctypes.byref(h))
+    assert rc == -2 and not h.value
+    assert b"CUDA" in _lib.lib.asr_last_error()
+    import asr_b200 as A
+    with pytest.raises(A.AsrError):
+        A.MfccPlan(A.C1)
+    with pytest.raises(A.AsrError):
+        A.ClipBatch.from_arrays([__import__("numpy").zeros(100, "int16")])
+
+
+def test_invalid_parameters_are_rejected_before_any_cuda_call(lib):
+    from asr_b200 import _lib, params
+    h = ctypes.c_void_p()
+    for bad in (params.C1.replace(n_fft=4), params.C1.replace(n_mfcc=40), params.C1.replace(hop_length=0),
+                params.C1.replace(delta_orders=3), params.C1.replace(win_length=1024)):
+        pc = bad.to_c()
+        assert _lib.lib.asr_plan_create(ctypes.byref(pc), ctypes.byref(h)) == -1
+        assert _lib.lib.asr_last_error().startswith(b"asr_plan_create")

@@ -1,0 +1,133 @@
+"""CPU tests of the host-side logic above the C-ABI (no kernel is launched)."""
+import os
+import wave
+
+import numpy as np
+import pytest
+
+import asr_b200 as A
+from asr_b200 import audio_io, sharding
+from asr_b200.speaker import extract_features_construct_dataset as sr_efcd
+from asr_b200.voice_digit import extract_features_construct_dataset as vdr_efcd
+from oracle import librosa_ref as lr, noise_ref as nr, pipeline_ref as pr
+from synth import synth_clips, to_f32
+
+
+def test_presets_match_the_oracle_presets():
+    for name, p in A.PRESETS.items():
+        o = lr.PRESETS[name]
+        for f in ("sr", "n_fft", "win_length", "hop_length", "window", "center", "pad_mode", "fftfreq_mode", "n_mels",
+                  "fmin", "fmax", "n_mfcc", "top_db", "amin", "lifter", "preemph", "delta_orders", "delta_width"):
+            assert getattr(p, f) == getattr(o, f), (name, f)
+    # the reference's real parameter sets (VDR/extract...py:30 ; SR/extract...py:227-228)
+    assert (A.REF_VDR.n_fft, A.REF_VDR.hop_length, A.REF_VDR.n_mels, A.REF_VDR.n_mfcc, A.REF_VDR.window) == (2048, 512, 128, 20, "hann")
+    assert (A.REF_SR.n_fft, A.REF_SR.win_length, A.REF_SR.hop_length) == (441, 441, 220)
+
+
+@pytest.mark.parametrize("name", ["ref_vdr", "ref_sr", "c1", "c3", "c5"])
+def test_num_frames_rule(name):
+    p, o = A.PRESETS[name], lr.PRESETS[name]
+    for L in (0, 1, p.n_fft // 2, p.n_fft // 2 + 1, p.n_fft, 9000, 16000, 22050, 160000):
+        want = 0 if (o.pad_mode == "reflect" and L <= o.n_fft // 2) else lr.num_frames(o, L)
+        assert p.num_frames(L) == want
+    assert A.REF_VDR.num_frames(22050) == 44 and A.REF_SR.num_frames(22050) == 101      # comment at VDR/extract...py:17
+    assert A.C3.feature_rows == 60 and A.C1.feature_rows == 13
+
+
+def test_params_struct_round_trip():
+    c = A.C5.to_c()
+    assert (c.sr, c.n_fft, c.win_length, c.hop_length, c.window, c.n_mels, c.n_mfcc) == (16000, 1024, 1024, 160, 1, 80, 40)
+    assert (c.delta_orders, c.delta_width, c.center, c.pad_mode, c.fftfreq_mode) == (1, 9, 1, 0, 0)
+    assert abs(c.lifter - 22.0) < 1e-6 and abs(c.top_db - 80.0) < 1e-6
+
+
+def test_clip_layout_is_aligned_and_disjoint():
+    lengths = [1, 7, 8, 9, 16000, 3]
+    off, total = A.ClipBatch.layout(lengths)
+    assert off.dtype == np.int64 and (off % 8 == 0).all()
+    ends = off + np.asarray(lengths)
+    assert (off[1:] >= ends[:-1]).all() and total >= ends[-1] and total % 8 == 0
+    off0, total0 = A.ClipBatch.layout([])
+    assert len(off0) == 0 and total0 == 8
+
+
+def test_snr_sigma_host_is_the_reference_chain():
+    clips = to_f32(synth_clips(4, 4000, 16000, 3))
+    P = np.array([np.mean(c ** 2) for c in clips], dtype=np.float32)
+    for snr in (60, 30, 20, 15, 10, 5, 0):
+        got = A.snr_sigma_host(P, snr)
+        want = np.array([float(nr.snr_sigma(c, snr)) for c in clips])
+        assert got.dtype == np.float64 and np.array_equal(got, want)
+
+
+def test_sr_window_index_matches_reference_trim_split():
+    """SR/extract...py:211-222 via index arithmetic == slicing the waveform."""
+    sr = 50
+    lengths = [0, 49, 100, 149, 150, 151, 537, 1000]
+    fid, start = sr_efcd.window_index(lengths, sr)
+    k = 0
+    for i, n in enumerate(lengths):
+        y = np.arange(n, dtype=np.float32) + 1000 * i
+        for w in pr.sr_trim_split(y, sr):
+            assert fid[k] == i and np.array_equal(y[start[k]:start[k] + sr], w)
+            k += 1
+    assert k == len(fid)
+
+
+def test_file_listing_and_labels(tmp_path):
+    """Folders are classes, label = folder index (VDR/extract...py:118-140)."""
+    for d, n in (("zero", 2), ("one", 1), ("two", 3)):
+        os.makedirs(tmp_path / d)
+        for i in range(n):
+            (tmp_path / d / f"a{i}.wav").write_bytes(b"")
+        (tmp_path / d / "notes.txt").write_text("x")
+    files, labels = vdr_efcd.get_file_names_and_labels(str(tmp_path))
+    assert labels.dtype == np.int32 and len(files) == 6
+    assert sorted(set(labels)) == [0, 1, 2]
+    by = {os.path.basename(os.path.dirname(f)): l for f, l in zip(files, labels)}
+    assert by == {"one": 0, "two": 1, "zero": 2}            # sorted folder order
+    files2, labels2 = sr_efcd.get_file_names_and_labels(str(tmp_path))
+    assert list(files2) == list(files) and np.array_equal(labels, labels2)
+
+
+def test_wav_decode_and_resample(tmp_path):
+    sr = 16000
+    x = synth_clips(1, sr, sr, 2)[0]
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(sr)
+        w.writeframes(x.tobytes())
+    y, got_sr = audio_io.load(path, sr=None)
+    assert got_sr == sr and y.dtype == np.float32 and np.array_equal(y, x.astype(np.float32) / 32768.0)
+    y2, sr2 = audio_io.load(path, sr=22050)                 # librosa.load default: resample to 22 050 Hz
+    assert sr2 == 22050 and abs(len(y2) - 22050) <= 1 and y2.dtype == np.float32
+    st = np.stack([x, x], axis=1)                           # stereo -> mono mean
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(sr)
+        w.writeframes(st.tobytes())
+    y3, _ = audio_io.load(path, sr=None)
+    assert np.allclose(y3, y)
+
+
+@pytest.mark.parametrize("n,world", [(0, 1), (1, 2), (7, 2), (8192, 8), (1000003, 8), (5, 8)])
+def test_shard_bounds_partition(n, world):
+    prev = 0
+    sizes = []
+    for r in range(world):
+        lo, hi = sharding.shard_bounds(n, r, world)
+        assert lo == prev and hi >= lo
+        sizes.append(hi - lo)
+        prev = hi
+    assert prev == n and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(n, world, world)
+
+
+def test_first_sample_index_matches_the_packed_layout():
+    lengths = [16000, 15999, 3, 8, 22050, 100]
+    off, _ = A.ClipBatch.layout(lengths)
+    for world in (1, 2, 3):
+        for r in range(world):
+            lo, hi = sharding.shard_bounds(len(lengths), r, world)
+            want = int(off[lo]) if lo < len(lengths) else int(off[-1] + (lengths[-1] + 7) // 8 * 8)
+            assert sharding.first_sample_index(lengths, r, world) == want
