@@ -53,8 +53,12 @@ SIGNATURES = {
     "asr_plan_feature_rows": (_i32, [_vp]),
     "asr_plan_uses_fft": (_i32, [_vp]),
     "asr_plan_get_tables": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
-    "asr_mfcc_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(NoiseC), _vp, _i32, _i32, _vp, _vp]),
-    "asr_logmel_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(NoiseC), _vp, _i32, _vp, _vp]),
+    "asr_mfcc_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(NoiseC), _vp, _i32, _i32, _vp,
+                                 _vp, C.c_size_t, _vp]),
+    "asr_logmel_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(NoiseC), _vp, _i32, _vp,
+                                   _vp, C.c_size_t, _vp]),
+    "asr_mfcc_workspace_bytes": (C.c_size_t, [_vp, _i32, _i32]),
+    "asr_plan_launches": (_i32, [_vp]),
     "asr_clip_power": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "asr_snr_sigma": (C.c_int, [_vp, _f32, _vp, _i32, _vp]),
     "asr_mix_white": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),

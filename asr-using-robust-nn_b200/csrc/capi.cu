@@ -46,7 +46,8 @@ static std::vector<double> linspace(double a, double b, int n) {
 }
 
 // librosa.filters.mel(htk=False, norm='slaney', dtype=float32), row-major (n_mels, n_bins)
-static std::vector<float> mel_dense(const asr_mfcc_params& p, int n_bins) {
+static std::vector<float> mel_dense(const asr_mfcc_params& p, int n_bins, std::vector<double>* mel_f_out = nullptr,
+                                    std::vector<double>* fftfreqs_out = nullptr) {
   const double fmax = p.fmax > 0 ? static_cast<double>(p.fmax) : p.sr / 2.0;
   std::vector<double> fftfreqs(n_bins);
   if (p.fftfreq_mode == ASR_FFTFREQ_LINSPACE) {
@@ -68,6 +69,8 @@ static std::vector<float> mel_dense(const asr_mfcc_params& p, int n_bins) {
       w[static_cast<size_t>(i) * n_bins + k] = static_cast<float>(static_cast<double>(tri) * enorm);  // ... *= enorm
     }
   }
+  if (mel_f_out) *mel_f_out = mel_f;
+  if (fftfreqs_out) *fftfreqs_out = fftfreqs;
   return w;
 }
 
@@ -105,6 +108,124 @@ static bool savgol_taps(int width, int order, double* taps) {
     for (int j = 0; j < m; ++j) t += inv[order][j] * std::pow(static_cast<double>(x), j);
     taps[x + h] = fact * t;
   }
+  return true;
+}
+
+
+// ---- tables of the block-pipelined path (frames_kernel.cu), n_fft = 512 ------------------------------
+// Mel bank in "segment" form: the Slaney triangles overlap only their neighbours, so a bin between the
+// peaks of filters seg-1 and seg feeds the falling slope of seg-1 and the rising slope of seg.  Bins are
+// cut into kFrWarps ranges (one per warp); a range x segment intersection is a "piece" with two partial
+// sums (fall, rise); a filter is the sum of a short list of partials ("refs"), in ascending-bin order.
+static bool build_frames_tables(asr_plan* pl, const std::vector<double>& mel_f, const std::vector<double>& fftfreqs,
+                                const std::vector<float>& twp, const std::vector<float>& twu) {
+  const asr_mfcc_params& p = pl->prm;
+  const int n_bins = pl->n_bins, n_mels = p.n_mels;
+  pl->fr_ok = 0;
+  if (p.n_fft != 512 || !pl->fft_path || (p.hop_length & 1) || p.n_mfcc > 40) return true;
+  std::vector<int> seg(n_bins);
+  for (int k = 0; k < n_bins; ++k) {
+    int s = 0;
+    while (s < n_mels && mel_f[s + 1] <= fftfreqs[k]) ++s;
+    seg[k] = s;
+  }
+  for (int i = 0; i < n_mels; ++i)
+    for (int k = 0; k < n_bins; ++k)
+      if (pl->h_mel_dense[static_cast<size_t>(i) * n_bins + k] != 0.0f && i != seg[k] - 1 && i != seg[k]) return true;   // not neighbour-only
+  auto W = [&](int i, int k) { return (i >= 0 && i < n_mels) ? pl->h_mel_dense[static_cast<size_t>(i) * n_bins + k] : 0.0f; };
+  // pieces = whole segments (bins [k0, k1) of segment s), read as float4 groups starting at k0 & ~3
+  struct Piece { int k0, k1, seg, nq; };
+  std::vector<Piece> pieces;
+  int total_q = 0;
+  for (int sg = 0; sg <= n_mels; ++sg) {
+    int k0 = -1, k1 = -1;
+    for (int k = 0; k < n_bins; ++k)
+      if (seg[k] == sg) { if (k0 < 0) k0 = k; k1 = k + 1; }
+    Piece pc{0, 0, sg, 0};
+    if (k0 >= 0) { pc.k0 = k0; pc.k1 = k1; pc.nq = (k1 - (k0 & ~3) + 3) / 4; }
+    pieces.push_back(pc);                      // empty segments keep a piece: their partials must be written (zeros)
+    total_q += 2 * ((pc.nq + 1) / 2);
+  }
+  // contiguous groups of segments per warp, balanced by float4 groups (+2 per segment of fixed cost)
+  std::vector<int> wrange(2 * kFrWarps, 0);   // the last warp of the CTA is the scheduler warp: it gets no segments
+  {
+    const int n_work = kFrWarps - 1;
+    const double target = (total_q + 2.0 * pieces.size()) / n_work;
+    size_t pi = 0;
+    double acc = 0.0;
+    for (int w = 0; w < n_work; ++w) {
+      wrange[2 * w] = static_cast<int>(pi);
+      const double goal = target * (w + 1);
+      while (pi < pieces.size() && (w == n_work - 1 || acc + 0.5 * (2 * ((pieces[pi].nq + 1) / 2) + 2) <= goal)) {
+        acc += 2 * ((pieces[pi].nq + 1) / 2) + 2;
+        ++pi;
+      }
+      wrange[2 * w + 1] = static_cast<int>(pi) - wrange[2 * w];
+    }
+  }
+  std::vector<float> wtab;                    // per float4 group of bins: (fall, rise) x 4 = two float4
+  std::vector<int> ptab;                      // int4 per piece: first bin (multiple of 4), PAIRS of groups, weight offset (float4), fall-partial offset
+  for (const Piece& pc : pieces) {
+    const int ka = pc.k0 & ~3;
+    const int nq2 = (pc.nq + 1) / 2;          // the kernel takes the groups two at a time; a zero-weight group pads odd counts
+    ptab.push_back(ka); ptab.push_back(nq2); ptab.push_back(static_cast<int>(wtab.size() / 4)); ptab.push_back(2 * pc.seg * 33);
+    for (int i = 0; i < 8 * nq2; ++i) {
+      const int k = ka + i;
+      const bool in = k >= pc.k0 && k < pc.k1;
+      wtab.push_back(in ? W(pc.seg - 1, k) : 0.0f);
+      wtab.push_back(in ? W(pc.seg, k) : 0.0f);
+    }
+  }
+  std::vector<int> frange(2, 0), refs(1, 0);  // (unused by the segment form: filter j = part[2j+1] + part[2j+2])
+  pl->fr_n_refs = 2 * (n_mels + 1);
+  pl->fr_s_pitch = round4(n_bins + 7);        // float4 reads of pairs of 4-bin groups; pitch = 4 (mod 32) floats: lanes <-> frames conflict-free
+  if ((pl->fr_s_pitch % 32) != 4) pl->fr_s_pitch += (4 - pl->fr_s_pitch % 32 + 32) % 32;
+  pl->fr_xb_stride = pl->frame_stride;
+  pl->fr_lm_pitch = round4(n_mels);
+  // ---- blob: [frames-kernel tables][cepstra tables] ----
+  std::vector<float> blob;
+  auto put_f = [&](const float* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.insert(blob.end(), src, src + n);
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  auto put_i = [&](const int* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.resize(blob.size() + n);
+    if (n) std::memcpy(blob.data() + off, src, n * sizeof(int));
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  pl->fr_off_window = put_f(pl->h_window.data(), pl->h_window.size());
+  {
+    std::vector<float> wi(pl->h_window);
+    for (float& v : wi) v *= (1.0f / 32768.0f);
+    pl->fr_off_window_i16 = put_f(wi.data(), wi.size());
+  }
+  pl->fr_off_twp = put_f(twp.data(), twp.size());
+  pl->fr_off_twu = put_f(twu.data(), twu.size());
+  pl->fr_off_wtab = put_f(wtab.data(), wtab.size());
+  pl->fr_off_pieces = put_i(ptab.data(), ptab.size());
+  pl->fr_off_wrange = put_i(wrange.data(), wrange.size());
+  pl->fr_off_frange = put_i(frange.data(), frange.size());
+  pl->fr_off_refs = put_i(refs.data(), refs.size());
+  pl->fr_blob_f4 = static_cast<int>(blob.size() / 4);
+  // cepstra tables: DCT (lifter folded in) transposed to [lm_pitch][4*NC4] (zero rows / columns as padding), delta taps
+  const int nc4 = (p.n_mfcc + 3) / 4;
+  std::vector<float> dct_t(static_cast<size_t>(pl->fr_lm_pitch) * 4 * nc4, 0.0f);
+  for (int c = 0; c < p.n_mfcc; ++c)
+    for (int j = 0; j < n_mels; ++j) dct_t[static_cast<size_t>(j) * 4 * nc4 + c] = pl->h_dct[static_cast<size_t>(c) * n_mels + j];
+  pl->cep_blob_f4 = pl->fr_blob_f4;
+  const int dct_off = put_f(dct_t.data(), dct_t.size());
+  const int taps_off = put_f(pl->h_taps.data(), pl->h_taps.size());
+  pl->cep_tab_f4 = static_cast<int>(blob.size() / 4) - pl->cep_blob_f4;
+  pl->cep_off_taps = taps_off - dct_off;
+  pl->cep_off_cbuf = 4 * pl->cep_tab_f4;
+  pl->cep_smem_bytes = 4 * (pl->cep_off_cbuf + (p.delta_orders > 0 ? p.n_mfcc * 129 : 0));
+  if (cudaMalloc(reinterpret_cast<void**>(&pl->fr_blob_dev), blob.size() * sizeof(float)) != cudaSuccess) return false;
+  if (cudaMemcpy(pl->fr_blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  pl->fr_ok = 1;
   return true;
 }
 
@@ -184,7 +305,8 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
       pl->h_window[lpad + n] = static_cast<float>(wl == 1 ? 1.0 : a0 - a1 * std::cos(2.0 * kPi * n / wl));
   }
   // ---- mel bank: dense float32 (librosa) -> contiguous supports -> float4 tasks ----
-  pl->h_mel_dense = mel_dense(p, pl->n_bins);
+  std::vector<double> mel_f, fftfreqs;
+  pl->h_mel_dense = mel_dense(p, pl->n_bins, &mel_f, &fftfreqs);
   std::vector<MelTask> tasks;
   std::vector<float> melw;
   std::vector<int> ftasks(2 * p.n_mels, 0);
@@ -333,6 +455,15 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
     delete pl;
     return cuda_fail(e, "asr_plan_create (no usable CUDA device? there is no CPU fallback)");
   }
+  {
+    cudaDeviceProp prop;
+    pl->sm_count = (cudaGetDeviceProperties(&prop, pl->device) == cudaSuccess) ? prop.multiProcessorCount : 148;
+  }
+  if (!build_frames_tables(pl, mel_f, fftfreqs, twp, twu)) {
+    const cudaError_t e2 = cudaGetLastError();
+    asr_plan_destroy(pl);
+    return cuda_fail(e2, "asr_plan_create (frames-path tables)");
+  }
   *plan_out = pl;
   return ASR_OK;
 }
@@ -340,6 +471,8 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
 extern "C" void asr_plan_destroy(asr_plan* plan) {
   if (!plan) return;
   if (plan->blob_dev) cudaFree(plan->blob_dev);
+  if (plan->fr_blob_dev) cudaFree(plan->fr_blob_dev);
+  if (plan->ws_dev) cudaFree(plan->ws_dev);
   delete plan;
 }
 
@@ -368,9 +501,60 @@ extern "C" int asr_plan_get_tables(const asr_plan* plan, float* window, float* m
   return ASR_OK;
 }
 
+// ---- block-pipelined path: shared-memory layout, workspace layout, launch ----
+namespace {
+struct FrLayout { int sm_aud, sm_S, sm_xb, sm_part, aud_cap, max_runs, smem_bytes; };
+bool frames_layout(const asr_plan* plan, FrLayout* lo) {
+  const int hop = plan->prm.hop_length;
+  for (int runs = kFrMaxRuns; runs >= 1; --runs) {
+    int off = 4 * plan->fr_blob_f4;
+    lo->aud_cap = round4(kFrBlock * hop + runs * (512 - std::min(hop, 512)) + 4 * runs + 8);
+    lo->sm_aud = off; off += 2 * lo->aud_cap;
+    lo->sm_S = off; off += 2 * kFrBlock * plan->fr_s_pitch;
+    off = round4(off);
+    lo->sm_xb = off; off += kFrWarps * 2 * plan->fr_xb_stride;
+    lo->sm_part = off; off += 2 * plan->fr_n_refs * 33;
+    lo->max_runs = runs;
+    lo->smem_bytes = 4 * off;
+    if (lo->smem_bytes + 6144 <= kMaxSmemBytes) return true;     // + static shared memory (descriptor ring)
+  }
+  return false;
+}
+struct WsLayout { size_t off_fstart, off_nframes, off_clipmax, off_lm, bytes; };
+WsLayout ws_layout(const asr_plan* plan, int n_clips, int max_length) {
+  WsLayout w;
+  auto up = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+  const size_t frames = static_cast<size_t>(n_clips) * static_cast<size_t>(std::max(0, asr_plan_num_frames(plan, max_length)));
+  w.off_fstart = 0;
+  w.off_nframes = up(sizeof(int) * (static_cast<size_t>(n_clips) + 1));
+  w.off_clipmax = w.off_nframes + up(sizeof(int) * static_cast<size_t>(n_clips));
+  w.off_lm = w.off_clipmax + up(sizeof(float) * static_cast<size_t>(n_clips));
+  w.bytes = w.off_lm + up(sizeof(float) * frames * plan->fr_lm_pitch + 16);
+  return w;
+}
+bool frames_path_usable(const asr_plan* plan, int n_clips, int max_length, FrLayout* lo) {
+  if (!plan->fr_ok) return false;
+  const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
+  if (frames >= (1ll << 31) - 64) return false;                  // flattened frame index is int32
+  return frames_layout(plan, lo);
+}
+}  // namespace
+
+extern "C" size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips, int32_t max_length) {
+  FrLayout lo;
+  if (!plan || n_clips <= 0 || max_length < 0 || !frames_path_usable(plan, n_clips, max_length, &lo)) return 0;
+  return ws_layout(plan, n_clips, max_length).bytes;
+}
+
+extern "C" int32_t asr_plan_launches(const asr_plan* plan) {
+  FrLayout lo;
+  return (plan && plan->fr_ok && frames_layout(plan, &lo)) ? 3 : 1;
+}
+
 static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
                          const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
-                         void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev, void* stream,
+                         void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream,
                          int logmel_only, const char* who) {
   auto bad = [&](const char* m) { set_error(std::string(who) + ": " + m); return ASR_ERR_INVALID; };
   if (!plan) return bad("null plan");
@@ -405,6 +589,54 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
   {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     kp.vec_ok = al16(audio_dev) && (kp.noise_mode == ASR_NOISE_NONE || (al16(kp.z) && (kp.noise_mode != ASR_NOISE_MIXTURE || al16(kp.z2))));
+  }
+  // ---- n_fft = 512: block-pipelined path (frame prefix -> frames -> cepstra) ----
+  FrLayout flo;
+  if (frames_path_usable(plan, n_clips, max_length, &flo)) {
+    const WsLayout wl = ws_layout(plan, n_clips, max_length);
+    char* ws = static_cast<char*>(workspace_dev);
+    if (ws) {
+      if (workspace_bytes < wl.bytes || (reinterpret_cast<uintptr_t>(ws) & 15)) return bad("workspace too small or not 16-byte aligned");
+    } else {
+      asr_plan* mp = const_cast<asr_plan*>(plan);                // plan-owned scratch (documented: no concurrent launches)
+      if (mp->ws_bytes < wl.bytes) {
+        if (mp->ws_dev) ASR_CUDA_TRY(cudaFree(mp->ws_dev));
+        mp->ws_dev = nullptr; mp->ws_bytes = 0;
+        ASR_CUDA_TRY(cudaMalloc(&mp->ws_dev, wl.bytes));
+        mp->ws_bytes = wl.bytes;
+      }
+      ws = static_cast<char*>(mp->ws_dev);
+    }
+    FParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.audio = audio_dev; fp.offsets = kp.offsets; fp.lengths = lengths_dev; fp.dtype = dtype; fp.n_clips = n_clips;
+    fp.noise_mode = kp.noise_mode; fp.z = kp.z; fp.z2 = kp.z2; fp.sigma = kp.sigma;
+    fp.mix_p = kp.mix_p; fp.mix_s0 = kp.mix_s0; fp.mix_s1 = kp.mix_s1;
+    fp.out = out_dev; fp.out_f64 = out_dtype == ASR_F64; fp.out_frames = out_frames;
+    fp.out_rows = p.n_mfcc * (1 + p.delta_orders); fp.logmel_only = logmel_only; fp.status = status_dev;
+    fp.n_fft = p.n_fft; fp.hop = p.hop_length; fp.pad = plan->pad; fp.pad_mode = p.pad_mode;
+    fp.n_mels = p.n_mels; fp.n_mfcc = p.n_mfcc; fp.delta_orders = p.delta_orders; fp.delta_width = p.delta_width;
+    fp.top_db = p.top_db; fp.amin = p.amin; fp.preemph = p.preemph;
+    fp.blob = reinterpret_cast<const float4*>(plan->fr_blob_dev); fp.blob_f4 = plan->fr_blob_f4;
+    const bool unscaled_i16 = dtype == ASR_I16 && kp.noise_mode == ASR_NOISE_NONE;   // staged unscaled, 2^-15 in the window
+    fp.off_window = unscaled_i16 ? plan->fr_off_window_i16 : plan->fr_off_window;
+    fp.off_twp = plan->fr_off_twp; fp.off_twu = plan->fr_off_twu; fp.off_wtab = plan->fr_off_wtab;
+    fp.off_pieces = plan->fr_off_pieces; fp.off_wrange = plan->fr_off_wrange; fp.off_frange = plan->fr_off_frange;
+    fp.off_refs = plan->fr_off_refs;
+    fp.sm_aud = flo.sm_aud; fp.sm_S = flo.sm_S; fp.sm_xb = flo.sm_xb; fp.sm_part = flo.sm_part;
+    fp.aud_cap = flo.aud_cap; fp.s_pitch = plan->fr_s_pitch; fp.xb_stride = plan->fr_xb_stride;
+    fp.n_refs = plan->fr_n_refs; fp.max_runs = flo.max_runs;
+    fp.vec_ok = kp.vec_ok && p.preemph == 0.0f && (p.hop_length % 4) == 0 && (plan->pad % 4) == 0;
+    fp.fstart = reinterpret_cast<int*>(ws + wl.off_fstart);
+    fp.nframes = reinterpret_cast<int*>(ws + wl.off_nframes);
+    fp.clipmax = reinterpret_cast<float*>(ws + wl.off_clipmax);
+    fp.lm = reinterpret_cast<float*>(ws + wl.off_lm);
+    fp.lm_pitch = plan->fr_lm_pitch;
+    fp.cep_blob_f4 = plan->cep_blob_f4; fp.cep_tab_f4 = plan->cep_tab_f4;
+    fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
+    ASR_CUDA_TRY(launch_frames_path(fp, plan->sm_count, flo.smem_bytes, plan->cep_smem_bytes,
+                                    std::max(1, asr_plan_num_frames(plan, max_length)), as_stream(stream)));
+    return ASR_OK;
   }
   kp.out = out_dev;
   kp.out_f64 = out_dtype == ASR_F64;
@@ -464,16 +696,18 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
 
 extern "C" int asr_mfcc_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
                               const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
-                              void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev, void* stream) {
+                              void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev,
+                              void* workspace_dev, size_t workspace_bytes, void* stream) {
   return launch_common(plan, audio_dev, dtype, offsets_dev, lengths_dev, n_clips, max_length, noise, out_dev,
-                       out_dtype, out_frames, status_dev, stream, 0, "asr_mfcc_batch");
+                       out_dtype, out_frames, status_dev, workspace_dev, workspace_bytes, stream, 0, "asr_mfcc_batch");
 }
 
 extern "C" int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
                                 const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
-                                float* out_dev, int32_t out_frames, int32_t* status_dev, void* stream) {
+                                float* out_dev, int32_t out_frames, int32_t* status_dev,
+                                void* workspace_dev, size_t workspace_bytes, void* stream) {
   return launch_common(plan, audio_dev, dtype, offsets_dev, lengths_dev, n_clips, max_length, noise, out_dev, ASR_F32,
-                       out_frames, status_dev, stream, 1, "asr_logmel_batch");
+                       out_frames, status_dev, workspace_dev, workspace_bytes, stream, 1, "asr_logmel_batch");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -490,7 +724,9 @@ struct Slot {
   float* power = nullptr;
   double* sigma = nullptr;
   double* z = nullptr;
+  void* ws = nullptr;
   void release() {
+    if (ws) cudaFree(ws);
     if (audio) cudaFree(audio);
     if (offsets) cudaFree(offsets);
     if (lengths) cudaFree(lengths);
@@ -564,6 +800,8 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
       if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.sigma), sizeof(double) * max_clips);
       if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.z), sizeof(double) * std::max<size_t>(1, max_span));
     }
+    const size_t ws_bytes = asr_mfcc_workspace_bytes(plan, max_clips, max_len);
+    if (e == cudaSuccess && ws_bytes) e = cudaMalloc(&sl.ws, ws_bytes);
     if (e != cudaSuccess) fail(e, "asr_mfcc_batch_host (allocation)");
   }
   for (size_t k = 0; k + 1 < cuts.size() && rc == ASR_OK; ++k) {
@@ -591,7 +829,8 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
       nz.mode = ASR_NOISE_WHITE; nz.z_dev = sl.z; nz.sigma_dev = sl.sigma;
     }
     rc = asr_mfcc_batch(plan, sl.audio, dtype, reinterpret_cast<const int64_t*>(sl.offsets), sl.lengths, nc, max_len,
-                        snr_mode ? &nz : nullptr, sl.out, out_dtype, out_frames, sl.status, sl.st);
+                        snr_mode ? &nz : nullptr, sl.out, out_dtype, out_frames, sl.status, sl.ws,
+                        sl.ws ? asr_mfcc_workspace_bytes(plan, max_clips, max_len) : 0, sl.st);
     if (rc != ASR_OK) break;
     e = cudaMemcpyAsync(static_cast<char*>(out_host) + static_cast<size_t>(a) * out_per_clip * osz, sl.out,
                         out_per_clip * osz * nc, cudaMemcpyDeviceToHost, sl.st);

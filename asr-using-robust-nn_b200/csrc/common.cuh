@@ -73,6 +73,52 @@ struct KParams {
   int cbuf_pitch;
 };
 
+// ---- block-pipelined path for n_fft = 512 (frames_kernel.cu) ----
+constexpr int kFrWarps = 16;
+constexpr int kFrThreads = kFrWarps * 32;
+constexpr int kFrBlock = 32;        // frames per block
+constexpr int kFrMaxRuns = 4;       // runs of consecutive frames (of one clip) per block, at most
+
+struct FParams {
+  // ---- batch ----
+  const void* audio;
+  const long long* offsets;
+  const int* lengths;
+  int dtype;
+  int n_clips;
+  // ---- fused noise ----
+  int noise_mode;
+  const double* z;
+  const double* z2;
+  const double* sigma;
+  double mix_p, mix_s0, mix_s1;
+  // ---- output ----
+  void* out;
+  int out_f64, out_frames, out_rows, logmel_only;
+  int* status;
+  // ---- plan scalars ----
+  int n_fft, hop, pad, pad_mode, n_mels, n_mfcc, delta_orders, delta_width;
+  float top_db, amin, preemph;
+  // ---- tables (global blob; the first blob_f4 float4 are copied to shared memory by the frames kernel) ----
+  const float4* blob;
+  int blob_f4;
+  int off_window, off_twp, off_twu, off_wtab, off_pieces, off_wrange, off_frange, off_refs;
+  // ---- frames kernel shared-memory layout (floats) ----
+  int sm_aud, sm_S, sm_xb, sm_part;
+  int aud_cap, s_pitch, xb_stride, n_refs, max_runs, vec_ok;
+  // ---- workspace ----
+  float* lm;          // [total frames][lm_pitch] log-mel rows (unclamped)
+  int lm_pitch;
+  float* clipmax;     // [n_clips]
+  int* fstart;        // [n_clips + 1] flattened index of each clip's first frame
+  int* nframes;       // [n_clips]
+  // ---- cepstra kernel tables: float4 offset inside the blob, size, shared-memory offsets (floats) ----
+  int cep_blob_f4, cep_tab_f4, cep_off_cbuf, cep_off_taps;
+};
+
+cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_bytes, int cep_smem_bytes, int max_frames,
+                               cudaStream_t stream);
+
 // host-side launcher (mfcc_kernel.cu)
 cudaError_t launch_mfcc(const KParams& kp, int smem_bytes, cudaStream_t stream);
 cudaError_t mfcc_kernel_init();   // opt-in shared memory attributes, once per process/device
@@ -96,4 +142,16 @@ struct asr_plan {
   int device;
   // host copies for table-level parity tests
   std::vector<float> h_window, h_mel_dense, h_dct, h_taps;
+  // ---- block-pipelined path (n_fft = 512): tables and layout; fr_ok = 0 -> the per-clip kernel is used ----
+  int fr_ok;
+  int sm_count;
+  float* fr_blob_dev;
+  int fr_blob_f4;          // part copied to shared memory by the frames kernel
+  int fr_off_window, fr_off_window_i16, fr_off_twp, fr_off_twu, fr_off_wtab, fr_off_pieces, fr_off_wrange, fr_off_frange,
+      fr_off_refs;
+  int fr_n_refs, fr_s_pitch, fr_xb_stride, fr_lm_pitch;
+  int cep_blob_f4, cep_tab_f4, cep_off_cbuf, cep_off_taps, cep_smem_bytes;
+  // plan-owned workspace for callers that pass none (grown on demand; not safe for concurrent launches)
+  void* ws_dev;
+  size_t ws_bytes;
 };

@@ -1,0 +1,743 @@
+// Block-pipelined MFCC front end for n_fft = 512 on sm_100a: three launches per batch.
+//
+//   frame_prefix_kernel   per clip: frame count T_b, status, prefix sum of T (the flattened frame index),
+//                         clip maximum initialised to -inf
+//   frames512_kernel      persistent, one 512-thread CTA per SM.  The frames of ALL clips form one flat
+//                         list; a CTA owns a contiguous range of it and walks it in blocks of 32 frames.
+//                         Per block, software-pipelined over one __syncthreads per iteration:
+//                           stage   (block i+1) samples of the block's frames -> shared memory, ONCE per sample:
+//                                   dtype decode, [float64 noise mix], [pre-emphasis], reflect / zero padding
+//                           fft     (block i)   2 frames per warp: window, 256-point complex FFT in registers
+//                                   (radix-2 passes, one shared-memory exchange), shuffle unpack, |X|^2
+//                                   -> S[frame][bin] in shared memory
+//                           mel     (block i-1) lanes <-> frames, warps <-> bin ranges: every bin feeds the falling
+//                                   slope of one filter and the rising slope of the next (Slaney triangles), weights
+//                                   are warp-uniform shared-memory broadcasts -> partial sums per (range, segment)
+//                           combine (block i-2) lanes <-> filters: partials -> 10*log10 -> log-mel row in HBM/L2,
+//                                   clip-wide maximum by atomic max
+//   cepstra_kernel        per clip tile: top_db clamp against the clip maximum, DCT-II (ortho) x lifter,
+//                         [delta, delta-delta], truncate / zero-pad to out_frames, float32 or float64 rows.
+//
+// The clip-wide maximum of power_to_db(top_db=80) is a dependency across all frames of a clip, hence the
+// split after the log; the log-mel rows (n_mels floats per frame) stay in the 126 MB L2 between the launches.
+// Arithmetic restated from librosa.feature.mfcc (oracle/librosa_ref.py); call sites replaced:
+// VDR/extract_features_construct_dataset.py:30, VDR/attacks.py:114,267 (and the SR twins for even n_fft).
+#include <cstring>
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace asr {
+
+// ------------------------------------------------------------------------------------------------
+// frame of 512 staged samples (float32, 8-byte aligned) x window -> pass-1 operands of lane l (bit-reversed)
+__device__ __forceinline__ void fft512_load(const float* __restrict__ xs, const float2* __restrict__ win2, const int l,
+                                            float (&re)[16], float (&im)[16]) {
+  const float2* xs2 = reinterpret_cast<const float2*>(xs);
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const int n = l + 16 * n2;
+    const float2 x = xs2[n];
+    const float2 w = win2[n];
+    re[brev<16>(n2)] = x.x * w.x;
+    im[brev<16>(n2)] = x.y * w.y;
+  }
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, const float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// T_b, status, exclusive prefix sum of T_b over the clips (single CTA; thread t owns a contiguous chunk).
+__global__ void __launch_bounds__(1024) frame_prefix_kernel(const FParams fp) {
+  __shared__ int s_sum[1024];
+  const int tid = threadIdx.x;
+  const int per = (fp.n_clips + 1023) / 1024;
+  const int lo = min(fp.n_clips, tid * per), hi = min(fp.n_clips, lo + per);
+  int local = 0;
+  for (int b = lo; b < hi; ++b) {
+    const int L = fp.lengths[b];
+    const long long padded = static_cast<long long>(L) + 2 * fp.pad;
+    int T = padded < fp.n_fft ? 0 : static_cast<int>(1 + (padded - fp.n_fft) / fp.hop);
+    int st = ASR_CLIP_OK;
+    if (T <= 0 || (fp.pad_mode == ASR_PAD_REFLECT && fp.pad > 0 && L <= fp.pad) || (fp.preemph != 0.0f && L < 2))
+      st = ASR_CLIP_TOO_SHORT;
+    else if (fp.delta_orders > 0 && !fp.logmel_only && T < fp.delta_width)
+      st = ASR_CLIP_TOO_FEW_FRAMES;
+    if (st != ASR_CLIP_OK) T = 0;
+    if (fp.status) fp.status[b] = st;
+    fp.clipmax[b] = __int_as_float(0xff800000);
+    fp.nframes[b] = T;
+    local += T;
+  }
+  s_sum[tid] = local;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {            // Hillis-Steele inclusive scan
+    const int v = tid >= o ? s_sum[tid - o] : 0;
+    __syncthreads();
+    s_sum[tid] += v;
+    __syncthreads();
+  }
+  int run = s_sum[tid] - local;
+  for (int b = lo; b < hi; ++b) {
+    fp.fstart[b] = run;
+    run += fp.nframes[b];
+  }
+  if (tid == 1023) fp.fstart[fp.n_clips] = s_sum[1023];
+}
+
+// ------------------------------------------------------------------------------------------------
+// sample decode (+ additive noise, float64 with two roundings) at GLOBAL element index i
+template <int DT>
+__device__ __forceinline__ float clean_at(const FParams& fp, const long long i) {
+  if (DT == ASR_I16) return static_cast<float>(__ldg(reinterpret_cast<const short*>(fp.audio) + i)) * (1.0f / 32768.0f);
+  if (DT == ASR_F32) return __ldg(reinterpret_cast<const float*>(fp.audio) + i);
+  return static_cast<float>(__ldg(reinterpret_cast<const double*>(fp.audio) + i));
+}
+
+template <int DT>
+__device__ __forceinline__ float value_at(const FParams& fp, const long long i, const double sig) {
+  if (fp.noise_mode == ASR_NOISE_NONE) return clean_at<DT>(fp, i);
+  double xd;
+  if (DT == ASR_F64) xd = __ldg(reinterpret_cast<const double*>(fp.audio) + i);
+  else xd = static_cast<double>(clean_at<DT>(fp, i));
+  double nz;
+  if (fp.noise_mode == ASR_NOISE_WHITE) {
+    nz = __dmul_rn(sig, __ldg(fp.z + i));
+  } else {
+    const double sel = (fabs(__ldg(fp.z + i)) < fp.mix_p) ? fp.mix_s1 : fp.mix_s0;
+    nz = __dmul_rn(sel, __ldg(fp.z2 + i));
+  }
+  return static_cast<float>(__dadd_rn(xd, nz));
+}
+
+// signal at ORIGINAL index o of the clip after [noise] and [pre-emphasis]
+template <int DT>
+__device__ __forceinline__ float signal_at(const FParams& fp, const long long base, const int o, const double sig) {
+  const float x = value_at<DT>(fp, base + o, sig);
+  if (fp.preemph == 0.0f) return x;
+  if (o > 0) return __fadd_rn(x, __fmul_rn(-fp.preemph, value_at<DT>(fp, base + o - 1, sig)));
+  // librosa.effects.preemphasis: lfilter state zi = 2*y[0]-y[1]  ->  out[0] = y[0] + zi
+  const float y1 = value_at<DT>(fp, base + 1, sig);
+  return __fadd_rn(x, __fadd_rn(2.0f * x, -y1));
+}
+
+// signal at padded position p (reflect / zero padding)
+template <int DT>
+__device__ __forceinline__ float padded_at(const FParams& fp, const long long base, const int L, const int p,
+                                           const double sig) {
+  int o = p - fp.pad;
+  if (o < 0) { if (fp.pad_mode != ASR_PAD_REFLECT) return 0.0f; o = -o; }
+  else if (o >= L) { if (fp.pad_mode != ASR_PAD_REFLECT) return 0.0f; o = 2 * (L - 1) - o; }
+  return signal_at<DT>(fp, base, o, sig);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staging units: 4 consecutive samples starting at a global index that is a multiple of 4, inside the clip,
+// no pre-emphasis.  The loads are issued early (unit_load*) and consumed after the mel phase (unit_convert),
+// so their latency is covered by the warp's own work.
+template <int DT> struct UnitRaw;
+template <> struct UnitRaw<ASR_I16> { int2 a; };
+template <> struct UnitRaw<ASR_F32> { float4 a; };
+template <> struct UnitRaw<ASR_F64> { double2 a[2]; };
+struct UnitZ { double2 z[2]; };
+
+template <int DT>
+__device__ __forceinline__ void unit_load(const FParams& fp, const long long e, UnitRaw<DT>& r) {
+  if constexpr (DT == ASR_I16) {
+    r.a = __ldg(reinterpret_cast<const int2*>(reinterpret_cast<const short*>(fp.audio) + e));
+  } else if constexpr (DT == ASR_F32) {
+    r.a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(fp.audio) + e));
+  } else {
+    const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(fp.audio) + e);
+    r.a[0] = __ldg(p); r.a[1] = __ldg(p + 1);
+  }
+}
+__device__ __forceinline__ void unit_load_z(const double* __restrict__ z, const long long e, UnitZ& r) {
+  const double2* p = reinterpret_cast<const double2*>(z + e);
+  r.z[0] = __ldg(p); r.z[1] = __ldg(p + 1);
+}
+
+// Clean int16 stays unscaled (the window table carries the exact 2^-15); the int16 -> float conversion is
+// exact integer-in-mantissa arithmetic on the FMA/ALU pipes: bits(2^23 + (s + 32768)) - (2^23 + 32768) = s.
+// Noise: float64(x) + s*z with two roundings, then one rounding to float32.  For the mixture, zz holds the
+// selector stream q and gg the carrier g.
+template <int DT>
+__device__ __forceinline__ float4 unit_convert(const FParams& fp, const UnitRaw<DT>& r, const UnitZ& zz, const UnitZ& gg,
+                                               const double sig) {
+  float v[4];
+  double xd[4];
+  if constexpr (DT == ASR_I16) {
+    const unsigned w[2] = {static_cast<unsigned>(r.a.x), static_cast<unsigned>(r.a.y)};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const unsigned x = w[j] ^ 0x80008000u;
+      v[2 * j] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7410)) - 8421376.0f;
+      v[2 * j + 1] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7432)) - 8421376.0f;
+    }
+    if (fp.noise_mode == ASR_NOISE_NONE) return make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xd[j] = static_cast<double>(v[j] * (1.0f / 32768.0f));
+  } else if constexpr (DT == ASR_F32) {
+    if (fp.noise_mode == ASR_NOISE_NONE) return r.a;
+    xd[0] = static_cast<double>(r.a.x); xd[1] = static_cast<double>(r.a.y);
+    xd[2] = static_cast<double>(r.a.z); xd[3] = static_cast<double>(r.a.w);
+  } else {
+    xd[0] = r.a[0].x; xd[1] = r.a[0].y; xd[2] = r.a[1].x; xd[3] = r.a[1].y;
+    if (fp.noise_mode == ASR_NOISE_NONE)
+      return make_float4(static_cast<float>(xd[0]), static_cast<float>(xd[1]), static_cast<float>(xd[2]), static_cast<float>(xd[3]));
+  }
+  if (fp.noise_mode == ASR_NOISE_WHITE) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      v[2 * j] = static_cast<float>(__dadd_rn(xd[2 * j], __dmul_rn(sig, zz.z[j].x)));
+      v[2 * j + 1] = static_cast<float>(__dadd_rn(xd[2 * j + 1], __dmul_rn(sig, zz.z[j].y)));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double s0 = (fabs(zz.z[j].x) < fp.mix_p) ? fp.mix_s1 : fp.mix_s0;
+      const double s1 = (fabs(zz.z[j].y) < fp.mix_p) ? fp.mix_s1 : fp.mix_s0;
+      v[2 * j] = static_cast<float>(__dadd_rn(xd[2 * j], __dmul_rn(s0, gg.z[j].x)));
+      v[2 * j + 1] = static_cast<float>(__dadd_rn(xd[2 * j + 1], __dmul_rn(s1, gg.z[j].y)));
+    }
+  }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block descriptors (shared memory ring).  A block = up to 32 frame slots made of at most max_runs runs of
+// consecutive frames of one clip; a run's samples are staged contiguously.
+struct FRun {
+  long long base;   // element offset of the clip
+  int L;            // clip length
+  int clip;
+  int p0;           // padded position of the first staged sample (t0 * hop)
+  int count;        // staged samples: (n - 1) * hop + 512
+  int aud0;         // staged position of padded sample p0
+  int unit0;        // first linear unit index of the run when it is staged by 4-sample units, else -1
+};
+struct FBlock {
+  int n_runs, n_slots, fin, n_units;
+  int refill, pad0, pad1, pad2;   // >= 0: reload the clip-metadata cache starting at this clip before the next iteration
+  FRun run[kFrMaxRuns];
+  int slot_aud[kFrBlock];    // staged position of the slot's first sample (0 for empty slots)
+  int slot_g[kFrBlock];      // flattened frame index
+  int slot_clip[kFrBlock];
+};
+constexpr int kFrRing = 8;
+constexpr int kClipCache = 64;    // clips whose (offset, length, frame count) are cached in shared memory
+struct ClipMeta { long long off; int L; int T; };
+constexpr int kWorkWarps = kFrWarps - 1;          // the last warp assembles block descriptors instead of staging / mel / combine
+constexpr int kWorkThreads = kWorkWarps * 32;
+constexpr int kPfUnits = 3;                       // staging units per worker thread whose loads are issued ahead
+
+// linear unit index -> (run, staged position, original sample index); false if u is past the block's units
+__device__ __forceinline__ bool locate_unit(const FParams& fp, const FBlock& blk, const int u, int& r, int& dst, int& orig) {
+  r = -1;
+#pragma unroll
+  for (int rr = 0; rr < kFrMaxRuns; ++rr)
+    if (rr < blk.n_runs && blk.run[rr].unit0 >= 0 && u >= blk.run[rr].unit0) r = rr;
+  if (r < 0) return false;
+  const FRun& run = blk.run[r];
+  const int local = u - run.unit0;
+  if (local >= (run.count >> 2)) return false;
+  dst = run.aud0 + 4 * local;
+  orig = run.p0 - fp.pad + 4 * local;
+  return true;
+}
+
+template <int DT>
+struct StagePf {
+  UnitRaw<DT> raw[kPfUnits];
+  UnitZ z[kPfUnits];
+  int have;
+};
+
+// issue the global loads of units wtid + k * kWorkThreads, k < kPfUnits (consumed later by stage_finish)
+template <int DT>
+__device__ __forceinline__ void stage_issue(const FParams& fp, const FBlock& blk, const int wtid, StagePf<DT>& pf) {
+  pf.have = 0;
+#pragma unroll
+  for (int k = 0; k < kPfUnits; ++k) {
+    const int u = wtid + k * kWorkThreads;
+    int r, dst, orig;
+    if (u < blk.n_units && locate_unit(fp, blk, u, r, dst, orig) && orig >= 0 && orig + 4 <= blk.run[r].L) {
+      const long long e = blk.run[r].base + orig;
+      unit_load<DT>(fp, e, pf.raw[k]);
+      if (fp.noise_mode == ASR_NOISE_WHITE) unit_load_z(fp.z, e, pf.z[k]);
+      pf.have |= 1 << k;
+    }
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ void stage_unit(const FParams& fp, const FBlock& blk, float* __restrict__ aud, const int u,
+                                           const bool have, const UnitRaw<DT>& raw_in, const UnitZ& z_in) {
+  // clean int16 is staged UNSCALED (the window table carries the exact 2^-15); scaling by 2^15 is exact
+  const float scale = (DT == ASR_I16 && fp.noise_mode == ASR_NOISE_NONE) ? 32768.0f : 1.0f;
+  int r, dst, orig;
+  if (!locate_unit(fp, blk, u, r, dst, orig)) return;
+  const FRun& run = blk.run[r];
+  const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
+  float4 v;
+  if (orig >= 0 && orig + 4 <= run.L) {
+    const long long e = run.base + orig;
+    if (have && fp.noise_mode != ASR_NOISE_MIXTURE) {
+      v = unit_convert<DT>(fp, raw_in, z_in, z_in, sig);
+    } else {
+      UnitRaw<DT> raw;
+      UnitZ zz, gg;
+      unit_load<DT>(fp, e, raw);
+      if (fp.noise_mode != ASR_NOISE_NONE) unit_load_z(fp.z, e, zz);
+      if (fp.noise_mode == ASR_NOISE_MIXTURE) unit_load_z(fp.z2, e, gg);
+      v = unit_convert<DT>(fp, raw, zz, gg, sig);
+    }
+  } else {
+    v.x = padded_at<DT>(fp, run.base, run.L, orig + fp.pad, sig) * scale;
+    v.y = padded_at<DT>(fp, run.base, run.L, orig + fp.pad + 1, sig) * scale;
+    v.z = padded_at<DT>(fp, run.base, run.L, orig + fp.pad + 2, sig) * scale;
+    v.w = padded_at<DT>(fp, run.base, run.L, orig + fp.pad + 3, sig) * scale;
+  }
+  *reinterpret_cast<float4*>(aud + dst) = v;
+}
+
+// store what stage_issue loaded, then everything of the block the prefetched units do not cover
+// (n_threads participants, `first` = first unit not prefetched)
+template <int DT>
+__device__ __forceinline__ void stage_rest(const FParams& fp, const FBlock& blk, float* __restrict__ aud, const int wtid,
+                                           const int n_threads, const int first) {
+  StagePf<DT> none;
+  for (int u = first + wtid; u < blk.n_units; u += n_threads) stage_unit<DT>(fp, blk, aud, u, false, none.raw[0], none.z[0]);
+  // runs that cannot be staged by units (odd alignment, pre-emphasis): sample by sample
+  const float scale = (DT == ASR_I16 && fp.noise_mode == ASR_NOISE_NONE) ? 32768.0f : 1.0f;
+  for (int r = 0; r < blk.n_runs; ++r) {
+    const FRun& run = blk.run[r];
+    if (run.unit0 >= 0) continue;
+    const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
+    for (int i = wtid; i < run.count; i += n_threads)
+      aud[run.aud0 + i] = padded_at<DT>(fp, run.base, run.L, run.p0 + i, sig) * scale;
+  }
+}
+
+__device__ __forceinline__ float fast_log2(const float x) {     // x >= amin > 0: no denormal handling needed
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(kFrThreads, 1) frames512_kernel(const __grid_constant__ FParams fp) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ FBlock ring[kFrRing];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- this CTA's range of the flattened frame list ----
+  const int total = __ldg(fp.fstart + fp.n_clips);
+  const int n_blocks = (total + kFrBlock - 1) / kFrBlock;
+  const int per = (n_blocks + gridDim.x - 1) / gridDim.x;
+  const long long gb = static_cast<long long>(blockIdx.x) * per * kFrBlock;
+  if (gb >= total) return;
+  const int g_begin = static_cast<int>(gb);
+  const int g_end = static_cast<int>(min(static_cast<long long>(total), gb + static_cast<long long>(per) * kFrBlock));
+
+  // ---- tables: global blob -> shared ----
+  {
+    float4* dst = reinterpret_cast<float4*>(smem);
+    for (int i = tid; i < fp.blob_f4; i += kFrThreads) dst[i] = __ldg(fp.blob + i);
+  }
+  const float2* s_win2 = reinterpret_cast<const float2*>(smem + fp.off_window);
+  const float* s_twp = smem + fp.off_twp;
+  const float2* s_twu = reinterpret_cast<const float2*>(smem + fp.off_twu);
+  const float4* s_wtab = reinterpret_cast<const float4*>(smem + fp.off_wtab);
+  const int4* s_pieces = reinterpret_cast<const int4*>(smem + fp.off_pieces);
+  float* s_aud = smem + fp.sm_aud;          // [2][aud_cap]
+  float* s_S = smem + fp.sm_S;              // [2][32][s_pitch]
+  float* s_xb = smem + fp.sm_xb;            // [16 warps][2][xb_stride]
+  float* s_part = smem + fp.sm_part;        // [2][n_refs][33]
+  for (int i = tid; i < 2 * kFrBlock * fp.s_pitch; i += kFrThreads) s_S[i] = 0.0f;    // incl. the zero tail of every row
+
+  // ---- block cursor (lane 0 of the last warp) over a shared-memory cache of the clips' metadata ----
+  constexpr int kAsmWarp = kFrWarps - 1;
+  __shared__ ClipMeta s_meta[kClipCache];
+  int b_cur = 0, t_cur = 0, g_cur = g_begin, cache_base = 0;
+  {
+    int lo = 0, hi = fp.n_clips;                       // largest b with fstart[b] <= g_begin (every thread: uniform)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(fp.fstart + mid) <= g_begin) lo = mid; else hi = mid;
+    }
+    b_cur = lo;
+    t_cur = g_begin - __ldg(fp.fstart + lo);
+    cache_base = lo;
+  }
+  auto load_meta = [&](const int base) {               // all threads
+    if (tid < kClipCache) {
+      const int b = min(base + tid, fp.n_clips - 1);
+      s_meta[tid].off = __ldg(fp.offsets + b);
+      s_meta[tid].L = __ldg(fp.lengths + b);
+      s_meta[tid].T = __ldg(fp.nframes + b);
+    }
+  };
+  load_meta(cache_base);
+  __syncthreads();
+  auto assemble_runs = [&](FBlock& blk) {              // cursor thread
+    int n_slots = 0, n_runs = 0, aud = 0, n_units = 0;
+#pragma unroll 1
+    for (int c = 0; c < kFrMaxRuns; ++c) {
+      const int b = b_cur;
+      if (b >= fp.n_clips || b >= cache_base + kClipCache || n_slots >= kFrBlock || n_runs >= fp.max_runs || g_cur >= g_end) break;
+      const ClipMeta cm = s_meta[b - cache_base];
+      if (t_cur < cm.T) {
+        const int n = min(min(kFrBlock - n_slots, cm.T - t_cur), g_end - g_cur);
+        FRun& run = blk.run[n_runs];
+        run.base = cm.off;
+        run.L = cm.L;
+        run.clip = b;
+        run.p0 = t_cur * fp.hop;
+        run.count = (n - 1) * fp.hop + 512;
+        const long long e0 = run.base + static_cast<long long>(run.p0) - fp.pad;
+        const bool vec = fp.vec_ok && (e0 & 3) == 0;
+        run.unit0 = vec ? n_units : -1;
+        if (vec) n_units += run.count >> 2;
+        run.aud0 = (aud + 3) & ~3;
+        aud = run.aud0 + run.count;
+        // slot tables of this run are filled by the lanes of the warp afterwards: stash what they need
+        blk.slot_g[n_runs] = g_cur; blk.slot_clip[n_runs] = n_slots;       // (temporarily: g0 and slot0 of run r)
+        n_slots += n; t_cur += n; g_cur += n; ++n_runs;
+      }
+      if (t_cur >= cm.T) { ++b_cur; t_cur = 0; }       // clip finished (or empty): the next one continues the block
+    }
+    blk.n_runs = n_runs; blk.n_slots = n_slots; blk.fin = g_cur >= g_end ? 1 : 0; blk.n_units = n_units;
+    blk.refill = -1;
+    if (g_cur < g_end && b_cur + kFrMaxRuns > cache_base + kClipCache) { blk.refill = b_cur; cache_base = b_cur; }
+  };
+  auto fill_slots = [&](FBlock& blk) {                 // all lanes of the cursor warp
+    int g0[kFrMaxRuns], s0[kFrMaxRuns];
+#pragma unroll
+    for (int r = 0; r < kFrMaxRuns; ++r) { g0[r] = blk.slot_g[r]; s0[r] = blk.slot_clip[r]; }
+    const int n_runs = blk.n_runs, n_slots = blk.n_slots;
+    __syncwarp();
+    int aud = 0, g = 0, clip = -1;
+    if (lane < n_slots) {
+#pragma unroll
+      for (int r = 0; r < kFrMaxRuns; ++r)
+        if (r < n_runs && lane >= s0[r]) {
+          aud = blk.run[r].aud0 + (lane - s0[r]) * fp.hop;
+          g = g0[r] + lane - s0[r];
+          clip = blk.run[r].clip;
+        }
+    }
+    blk.slot_aud[lane] = aud; blk.slot_g[lane] = g; blk.slot_clip[lane] = clip;
+  };
+  for (int i = 0; i < 2; ++i) {
+    if (warp == kAsmWarp) {
+      if (lane == 0) assemble_runs(ring[i]);
+      __syncwarp();
+      fill_slots(ring[i]);
+    }
+    __syncthreads();                                   // also: tables and the zeroed S
+    if (ring[i].refill >= 0) { load_meta(ring[i].refill); __syncthreads(); }
+  }
+  stage_rest<DT>(fp, ring[0], s_aud, tid, kFrThreads, 0);
+  __syncthreads();
+
+  // ---- per-thread constants of the phases ----
+  const int part_buf = fp.n_refs * 33;                 // floats per partial buffer
+  const bool comb_lane = lane < fp.n_mels;
+  const float* comb_pj = s_part + (comb_lane ? (2 * lane + 1) * 33 : 0);   // rise partial of filter `lane`; fall of it is 33 further
+  const int2 mel_range = warp < kWorkWarps ? reinterpret_cast<const int2*>(smem + fp.off_wrange)[warp] : make_int2(0, 0);
+  const int fft_h = lane >> 4, fft_l = lane & 15;
+  const int fft_slot = 8 * (warp >> 2) + (warp & 3) + 4 * fft_h;   // half-warps 4 slots apart: complementary bank halves of S
+  float* const fft_xb = s_xb + (warp * 2 + fft_h) * fp.xb_stride;
+  const int s_buf = kFrBlock * fp.s_pitch;
+  int cm_clip0 = -1, cm_clip1 = -1, cm_clip2 = -1;     // combine: clip whose maximum is being accumulated (per slot position)
+  float cm_max0 = -3.0e38f, cm_max1 = -3.0e38f, cm_max2 = -3.0e38f;
+  auto flush_max = [&](const int clip, float mx) {
+    if (clip >= 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) atomic_max_float(fp.clipmax + clip, mx);
+    }
+  };
+  auto combine_slot = [&](const FBlock& blk, const float* part, const int slot, int& cm_clip, float& cm_max) {
+    const int clip = blk.slot_clip[slot];
+    if (clip != cm_clip) { flush_max(cm_clip, cm_max); cm_clip = clip; cm_max = -3.0e38f; }
+    float* row = fp.lm + static_cast<long long>(blk.slot_g[slot]) * fp.lm_pitch;
+    if (fp.lm_pitch <= 32) {                            // one pass: lane j <-> filter j (lanes >= n_mels write the zero pad columns)
+      float db = 0.0f;
+      if (comb_lane) {
+        const float m = comb_pj[(part - s_part) + slot] + comb_pj[(part - s_part) + 33 + slot];
+        db = 3.01029995663981195f * fast_log2(fmaxf(fp.amin, m));
+        cm_max = fmaxf(cm_max, db);
+      }
+      if (lane < fp.lm_pitch) row[lane] = db;
+    } else {
+#pragma unroll 1
+      for (int j = lane; j < fp.lm_pitch; j += 32) {
+        float db = 0.0f;
+        if (j < fp.n_mels) {
+          const float m = part[(2 * j + 1) * 33 + slot] + part[(2 * j + 2) * 33 + slot];
+          db = 3.01029995663981195f * fast_log2(fmaxf(fp.amin, m));
+          cm_max = fmaxf(cm_max, db);
+        }
+        row[j] = db;
+      }
+    }
+  };
+
+  const FBlock* b_comb = &ring[kFrRing - 2];           // block it-2 (not live before it = 2)
+  const FBlock* b_mel = &ring[kFrRing - 1];            // block it-1
+  const FBlock* b_fft = &ring[0];                      // block it
+  const FBlock* b_stage = &ring[1];                    // block it+1
+  for (int it = 0;; ++it) {
+    const int par = it & 1;
+    const int n_comb = it >= 2 ? b_comb->n_slots : 0;
+    const int n_mel = it >= 1 ? b_mel->n_slots : 0;
+    const int n_fft = b_fft->n_slots;
+    if (n_comb == 0 && n_mel == 0 && n_fft == 0 && b_fft->fin) break;      // uniform over the CTA
+    FBlock* nb;
+    if (warp == kAsmWarp) {
+      // ---- scheduler warp: descriptor of block it+2 while the others stage / combine / mel ----
+      nb = &ring[(it + 2) % kFrRing];
+      if (lane == 0) assemble_runs(*nb);
+      __syncwarp();
+      fill_slots(*nb);
+    } else {
+      // ---- stage (block it+1): loads of this thread's first units are issued now, consumed after the mel phase ----
+      float* const aud_next = s_aud + (par ^ 1) * fp.aud_cap;
+      StagePf<DT> pf;
+      stage_issue<DT>(fp, *b_stage, tid, pf);
+
+      // ---- combine (block it-2): lanes <-> filters; warp w takes slots w, w+15, w+30.
+      //      filter j = rising slope over segment j + falling slope over segment j+1 ----
+      if (n_comb > 0) {
+        const float* part = s_part + par * part_buf;
+        if (warp < n_comb) combine_slot(*b_comb, part, warp, cm_clip0, cm_max0);
+        if (warp + kWorkWarps < n_comb) combine_slot(*b_comb, part, warp + kWorkWarps, cm_clip1, cm_max1);
+        if (warp + 2 * kWorkWarps < n_comb) combine_slot(*b_comb, part, warp + 2 * kWorkWarps, cm_clip2, cm_max2);
+      }
+
+      // ---- mel (block it-1): lanes <-> frames, this warp's segments ----
+      if (n_mel > 0) {
+        const float* S = s_S + (par ^ 1) * s_buf + lane * fp.s_pitch;      // S buffer of block it-1
+        float* part = s_part + (par ^ 1) * part_buf + lane;
+#pragma unroll 1
+        for (int pi = mel_range.x; pi < mel_range.x + mel_range.y; ++pi) {
+          const int4 pc = s_pieces[pi];                 // (first bin (multiple of 4), PAIRS of float4 groups, weight offset (float4), fall-partial offset)
+          const float4* sp = reinterpret_cast<const float4*>(S + pc.x);
+          const float4* wt = s_wtab + pc.z;
+          float a = 0.0f, b = 0.0f;
+#pragma unroll 1
+          for (int q = 0; q < pc.y; ++q) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float4 sv = sp[2 * q + u];
+              const float4 w01 = wt[4 * q + 2 * u], w23 = wt[4 * q + 2 * u + 1];
+              a = fmaf(w01.x, sv.x, a); b = fmaf(w01.y, sv.x, b);
+              a = fmaf(w01.z, sv.y, a); b = fmaf(w01.w, sv.y, b);
+              a = fmaf(w23.x, sv.z, a); b = fmaf(w23.y, sv.z, b);
+              a = fmaf(w23.z, sv.w, a); b = fmaf(w23.w, sv.w, b);
+            }
+          }
+          part[pc.w] = a;                               // falling slope of filter seg-1
+          part[pc.w + 33] = b;                          // rising slope of filter seg
+        }
+      }
+
+      // ---- stage (block it+1): convert and store ----
+#pragma unroll
+      for (int k = 0; k < kPfUnits; ++k) {
+        const int u = tid + k * kWorkThreads;
+        if (u < b_stage->n_units) stage_unit<DT>(fp, *b_stage, aud_next, u, (pf.have >> k) & 1, pf.raw[k], pf.z[k]);
+      }
+      if (b_stage->n_slots > 0) stage_rest<DT>(fp, *b_stage, aud_next, tid, kWorkThreads, kPfUnits * kWorkThreads);
+    }
+
+    // ---- fft (block it) ----
+    if (n_fft > 0) {
+      const float* xs = s_aud + par * fp.aud_cap + b_fft->slot_aud[fft_slot];
+      float re[16], im[16];
+      fft512_load(xs, s_win2, fft_l, re, im);
+      frame_power_fft<512, false>(re, im, s_twp, s_twu, fft_xb, s_S + par * s_buf + fft_slot * fp.s_pitch, fft_l);
+    }
+
+    nb = &ring[(it + 2) % kFrRing];
+    b_comb = b_mel; b_mel = b_fft; b_fft = b_stage; b_stage = nb;
+    __syncthreads();
+    if (nb->refill >= 0) { load_meta(nb->refill); __syncthreads(); }   // rare: the cursor ran past the cached clips
+  }
+  flush_max(cm_clip0, cm_max0);
+  flush_max(cm_clip1, cm_max1);
+  flush_max(cm_clip2, cm_max2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cepstra: grid (clip, time tile).  Thread <-> frame: clamp the log-mel row, DCT-II x lifter from a
+// transposed table (one float4 = 4 coefficients of one mel band, broadcast), [Savitzky-Golay deltas
+// through shared memory], coalesced stores along time.
+constexpr int kCepThreads = 128;
+
+template <int NC4>   // NC4 = ceil(n_mfcc / 4), 1..16
+__global__ void __launch_bounds__(kCepThreads) cepstra_kernel(const __grid_constant__ FParams fp) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int T = __ldg(fp.nframes + b);
+  const int rows = fp.logmel_only ? fp.n_mels : fp.out_rows;
+  const long long out_base = static_cast<long long>(b) * rows * fp.out_frames;
+  const int half = (fp.delta_orders > 0 && !fp.logmel_only) ? fp.delta_width / 2 : 0;
+  const int tile = kCepThreads - 2 * half;             // output frames per CTA
+  const int t_lo = blockIdx.y * tile;                   // first output frame of this tile
+  auto store = [&](const long long idx, const float v) {
+    if (fp.out_f64) reinterpret_cast<double*>(fp.out)[idx] = static_cast<double>(v);
+    else reinterpret_cast<float*>(fp.out)[idx] = v;
+  };
+  const int t_out = min(T, fp.out_frames);              // frames carrying data; the rest is zero padding
+  // ---- zero padding in the feature domain (VDR/extract...py:36-37), also clips that cannot be framed ----
+  {
+    const int z_lo = max(t_out, t_lo), z_hi = min(fp.out_frames, t_lo + tile);
+    const int w = z_hi - z_lo;
+    for (int e = tid; w > 0 && e < rows * w; e += kCepThreads)
+      store(out_base + static_cast<long long>(e / w) * fp.out_frames + z_lo + e % w, 0.0f);
+  }
+  if (t_lo >= t_out) return;
+
+  float* s_dct = smem;                                  // [n_mels][4*NC4] transposed, lifter folded in
+  float* s_cep = smem + fp.cep_off_cbuf;                // [n_mfcc][kCepThreads+1]
+  const float* s_taps = smem + fp.cep_off_taps;
+  if (!fp.logmel_only) {
+    const float4* src = fp.blob + fp.cep_blob_f4;
+    float4* dst = reinterpret_cast<float4*>(smem);
+    for (int i = tid; i < fp.cep_tab_f4; i += kCepThreads) dst[i] = __ldg(src + i);
+  }
+  const float thr = (fp.top_db >= 0.0f) ? __ldg(fp.clipmax + b) - fp.top_db : -3.0e38f;
+  const int g0 = __ldg(fp.fstart + b);
+  // frame handled by this thread: centre frames of the tile plus the delta halo, clamped into the clip
+  const int c_lo = half > 0 ? min(max(t_lo, half), T - 1 - half) - half : t_lo;   // first frame whose cepstrum the tile needs
+  const int t = c_lo + tid;
+  const bool live = t < T && t >= 0;
+  __syncthreads();
+
+  if (fp.logmel_only) {
+    if (live && t < t_out && tid < tile) {
+      const float* row = fp.lm + static_cast<long long>(g0 + t) * fp.lm_pitch;
+      for (int j = 0; j < fp.n_mels; ++j)
+        store(out_base + static_cast<long long>(j) * fp.out_frames + t, fmaxf(__ldcg(row + j), thr));
+    }
+    return;
+  }
+
+  float acc[4 * NC4];
+#pragma unroll
+  for (int c = 0; c < 4 * NC4; ++c) acc[c] = 0.0f;
+  if (live) {
+    const float4* row4 = reinterpret_cast<const float4*>(fp.lm + static_cast<long long>(g0 + t) * fp.lm_pitch);
+    const float4* d4 = reinterpret_cast<const float4*>(s_dct);
+    for (int jq = 0; jq < fp.lm_pitch / 4; ++jq) {
+      const float4 v4 = __ldcg(row4 + jq);
+      const float v[4] = {fmaxf(v4.x, thr), fmaxf(v4.y, thr), fmaxf(v4.z, thr), fmaxf(v4.w, thr)};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = 4 * jq + u;                        // rows j >= n_mels of the table are zero
+#pragma unroll
+        for (int c4 = 0; c4 < NC4; ++c4) {
+          const float4 d = d4[j * NC4 + c4];
+          acc[4 * c4] = fmaf(v[u], d.x, acc[4 * c4]);
+          acc[4 * c4 + 1] = fmaf(v[u], d.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(v[u], d.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(v[u], d.w, acc[4 * c4 + 3]);
+        }
+      }
+    }
+  }
+  if (half == 0) {
+    if (live && t < t_out) {
+#pragma unroll
+      for (int c = 0; c < 4 * NC4; ++c)
+        if (c < fp.n_mfcc) store(out_base + static_cast<long long>(c) * fp.out_frames + t, acc[c]);
+    }
+    return;
+  }
+  // ---- deltas: librosa.feature.delta = savgol_filter(width, polyorder=order, deriv=order, mode='interp'):
+  //      interior taps everywhere, with the window centre clamped to [half, T-1-half] at the edges ----
+  const int cp = kCepThreads + 1;
+#pragma unroll
+  for (int c = 0; c < 4 * NC4; ++c)
+    if (c < fp.n_mfcc) s_cep[c * cp + tid] = acc[c];
+  __syncthreads();
+  const int to = t_lo + tid;                             // output frame of this thread
+  if (tid < tile && to < t_out) {
+    const int tc = min(max(to, half), T - 1 - half);
+    const int i0 = tc - half - c_lo;                     // first tap position in s_cep
+    for (int c = 0; c < fp.n_mfcc; ++c) {
+      const float* cr = s_cep + c * cp;
+      store(out_base + static_cast<long long>(c) * fp.out_frames + to, cr[to - c_lo]);
+      for (int o = 1; o <= fp.delta_orders; ++o) {
+        const float* taps = s_taps + (o - 1) * fp.delta_width;
+        float v = 0.0f;
+        for (int j = 0; j < fp.delta_width; ++j) v = fmaf(taps[j], cr[i0 + j], v);
+        store(out_base + static_cast<long long>(o * fp.n_mfcc + c) * fp.out_frames + to, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+static cudaError_t launch_frames_dt(const FParams& fp, int grid, int smem_bytes, cudaStream_t stream) {
+  static int granted = 0;                      // the kernel also has static shared memory: ask for what is needed
+  if (smem_bytes > granted) {
+    cudaError_t e = cudaFuncSetAttribute(frames512_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    granted = smem_bytes;
+  }
+  frames512_kernel<DT><<<grid, kFrThreads, smem_bytes, stream>>>(fp);
+  return cudaGetLastError();
+}
+
+template <int NC4>
+static cudaError_t launch_cep_n(const FParams& fp, dim3 grid, int smem_bytes, cudaStream_t stream) {
+  static int granted = 48 * 1024;
+  if (smem_bytes > granted) {
+    cudaError_t e = cudaFuncSetAttribute(cepstra_kernel<NC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    granted = smem_bytes;
+  }
+  cepstra_kernel<NC4><<<grid, kCepThreads, smem_bytes, stream>>>(fp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_bytes, int cep_smem_bytes, int max_frames,
+                               cudaStream_t stream) {
+  frame_prefix_kernel<<<1, 1024, 0, stream>>>(fp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  switch (fp.dtype) {
+    case ASR_I16: e = launch_frames_dt<ASR_I16>(fp, sm_count, frames_smem_bytes, stream); break;
+    case ASR_F32: e = launch_frames_dt<ASR_F32>(fp, sm_count, frames_smem_bytes, stream); break;
+    default: e = launch_frames_dt<ASR_F64>(fp, sm_count, frames_smem_bytes, stream); break;
+  }
+  if (e != cudaSuccess) return e;
+  const int half = (fp.delta_orders > 0 && !fp.logmel_only) ? fp.delta_width / 2 : 0;
+  const int tile = kCepThreads - 2 * half;
+  const int span = max(max_frames, fp.out_frames);
+  const dim3 grid(fp.n_clips, (span + tile - 1) / tile);
+  switch ((fp.n_mfcc + 3) / 4) {
+    case 1: return launch_cep_n<1>(fp, grid, cep_smem_bytes, stream);
+    case 2: return launch_cep_n<2>(fp, grid, cep_smem_bytes, stream);
+    case 3: return launch_cep_n<3>(fp, grid, cep_smem_bytes, stream);
+    case 4: return launch_cep_n<4>(fp, grid, cep_smem_bytes, stream);
+    case 5: return launch_cep_n<5>(fp, grid, cep_smem_bytes, stream);
+    case 6: return launch_cep_n<6>(fp, grid, cep_smem_bytes, stream);
+    case 7: return launch_cep_n<7>(fp, grid, cep_smem_bytes, stream);
+    case 8: return launch_cep_n<8>(fp, grid, cep_smem_bytes, stream);
+    case 9: return launch_cep_n<9>(fp, grid, cep_smem_bytes, stream);
+    case 10: return launch_cep_n<10>(fp, grid, cep_smem_bytes, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace asr

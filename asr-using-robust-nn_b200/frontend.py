@@ -148,7 +148,6 @@ class Noise:
 class MfccPlan:
     """Immutable tables for one parameter set (wraps ``asr_plan``)."""
 
-    LAUNCHES = 1        # kernels of libasr_b200 one `mfcc` call launches
 
     def __init__(self, params: MfccParams, device: Optional[int] = None):
         _require_cuda()
@@ -158,6 +157,7 @@ class MfccPlan:
         with torch.cuda.device(self.device):
             pc = params.to_c()
             check(lib.asr_plan_create(C.byref(pc), C.byref(self._h)), "asr_plan_create")
+        self._ws = {}       # stream -> scratch tensor (the n_fft = 512 path keeps log-mel rows there between its launches)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -168,6 +168,22 @@ class MfccPlan:
     @property
     def feature_rows(self) -> int:
         return lib.asr_plan_feature_rows(self._h)
+
+    @property
+    def launches(self) -> int:
+        """Kernels one `mfcc` call launches (1, or 3 on the block-pipelined n_fft = 512 path)."""
+        return lib.asr_plan_launches(self._h)
+
+    def _workspace(self, n_clips: int, max_length: int, device) -> Optional[torch.Tensor]:
+        need = lib.asr_mfcc_workspace_bytes(self._h, n_clips, max_length)
+        if need == 0:
+            return None
+        key = torch.cuda.current_stream().cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
 
     @property
     def uses_fft(self) -> bool:
@@ -202,7 +218,8 @@ class MfccPlan:
                     B, batch.max_length, C.byref(nz) if nz is not None else None, out.data_ptr()]
             if fn is lib.asr_mfcc_batch:
                 args.append(_DT[out.dtype])
-            args += [out_frames, status.data_ptr(), _stream()]
+            ws = self._workspace(B, batch.max_length, dev)
+            args += [out_frames, status.data_ptr(), _ptr(ws), 0 if ws is None else ws.numel(), _stream()]
             check(fn(*args), what)
         return out, status
 

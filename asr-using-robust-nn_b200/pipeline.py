@@ -20,10 +20,10 @@ import torch
 from .frontend import ClipBatch, MfccPlan, Noise, Standardizer, clip_power, snr_sigma_device, randn
 from .params import MfccParams
 
-# kernels of libasr_b200 launched by one `run_device` step: power, sigma, mfcc launches, 2x colsum
-# (partial + final), mean, finalize, apply; the e2e step adds the randn launch
-LAUNCHES_PER_STEP_CLEAN = 7 + MfccPlan.LAUNCHES
-LAUNCHES_PER_STEP = LAUNCHES_PER_STEP_CLEAN + 2
+# kernels of libasr_b200 launched by one `run_device` step besides the MFCC launches (`plan.launches`):
+# 2x colsum (partial + final), mean, finalize, apply; + power and sigma when noisy; the e2e step adds randn
+LAUNCHES_CMVN = 7
+LAUNCHES_NOISE = 2
 
 
 class _StepGraphs:
@@ -50,6 +50,9 @@ class NoisyFeaturePipeline:
         self._feats = None
         self._cache: dict = {}
         self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch (eager steps only)
+
+    def launches_per_step(self, noisy: bool, standardize: bool = True) -> int:
+        return self.plan.launches + (LAUNCHES_NOISE if noisy else 0) + (LAUNCHES_CMVN if standardize else 0)
 
     def _feat_buffer(self, B: int) -> torch.Tensor:
         if self._feats is None or self._feats.shape[0] != B:

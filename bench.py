@@ -220,7 +220,7 @@ def main():
     # ---------------- B200 arm ----------------
     import torch
     import asr_b200 as A
-    from asr_b200.pipeline import NoisyFeaturePipeline, LAUNCHES_PER_STEP, LAUNCHES_PER_STEP_CLEAN
+    from asr_b200.pipeline import NoisyFeaturePipeline
     from synth import synth_clips
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the asr_b200 path has no CPU fallback")
@@ -344,7 +344,7 @@ def main():
         cpu = {"value": n / times[0], "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n} clips of the same workload (numpy/scipy restatement of librosa 0.9 + the reference's "
                          f"noise code, one clip per call, {cores} processes, BLAS threads 1), {times[0]:.1f} s"}
-    launches = (LAUNCHES_PER_STEP if noisy else LAUNCHES_PER_STEP_CLEAN) * K
+    launches = pipe.launches_per_step(noisy) * K
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(config, l2="inputs per step exceed L2 (audio "

@@ -22,6 +22,7 @@
 #ifndef ASR_B200_H_
 #define ASR_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -139,15 +140,27 @@ int asr_plan_get_tables(const asr_plan* plan, float* window /*n_fft*/, float* me
  *                flattening a clip's block row-major gives the reference's (n_mfcc*T,) row
  *                (VDR/extract...py:149).  Frames >= T are zero (VDR/extract...py:36-37).
  *   status_dev   int32 [n_clips] or NULL
+ *   workspace_dev / workspace_bytes
+ *                scratch of at least asr_mfcc_workspace_bytes(plan, n_clips, max_length) bytes (16-byte aligned):
+ *                flattened frame index, clip maxima and the log-mel rows between the two stages of the n_fft = 512
+ *                path.  NULL: the plan's own scratch is used (grown with cudaMalloc on demand - then calls on
+ *                one plan must not overlap in time; pass a workspace per stream to run them concurrently).
  */
 int asr_mfcc_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
                    const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
-                   void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev, void* stream);
+                   void* out_dev, int32_t out_dtype, int32_t out_frames, int32_t* status_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Bytes of scratch the two entry points above/below need for such a batch (0: none needed). */
+size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips, int32_t max_length);
+/* Kernel launches one asr_mfcc_batch call makes with this plan (1, or 3 on the n_fft = 512 path). */
+int32_t asr_plan_launches(const asr_plan* plan);
 
 /* Stage-level probe for parity tests: the clamped log-mel matrix [n_clips][n_mels][out_frames] (float32). */
 int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
                      const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
-                     float* out_dev, int32_t out_frames, int32_t* status_dev, void* stream);
+                     float* out_dev, int32_t out_frames, int32_t* status_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- noise path (VDR/attacks.py:73-86,145-183,222-245 ; SR/attacks.py:81-94,149-189,228-251) ---- */
 
