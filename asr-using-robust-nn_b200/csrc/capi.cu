@@ -147,9 +147,9 @@ static bool build_frames_tables(asr_plan* pl, const std::vector<double>& mel_f, 
     total_q += 2 * ((pc.nq + 1) / 2);
   }
   // contiguous groups of segments per warp, balanced by float4 groups (+2 per segment of fixed cost)
-  std::vector<int> wrange(2 * kFrWarps, 0);   // the last warp of the CTA is the scheduler warp: it gets no segments
+  std::vector<int> wrange(2 * kFrWarps, 0);
   {
-    const int n_work = kFrWarps - 1;
+    const int n_work = kFrMelWarps;             // the last warp assembles block descriptors instead
     const double target = (total_q + 2.0 * pieces.size()) / n_work;
     size_t pi = 0;
     double acc = 0.0;
@@ -533,7 +533,7 @@ WsLayout ws_layout(const asr_plan* plan, int n_clips, int max_length) {
   return w;
 }
 bool frames_path_usable(const asr_plan* plan, int n_clips, int max_length, FrLayout* lo) {
-  if (!plan->fr_ok) return false;
+  if (!plan->fr_ok || plan->path == ASR_PATH_CLIP) return false;
   const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
   if (frames >= (1ll << 31) - 64) return false;                  // flattened frame index is int32
   return frames_layout(plan, lo);
@@ -546,9 +546,19 @@ extern "C" size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips
   return ws_layout(plan, n_clips, max_length).bytes;
 }
 
-extern "C" int32_t asr_plan_launches(const asr_plan* plan) {
+static bool frames_path_wanted(const asr_plan* plan, bool noisy) {
+  return plan->path == ASR_PATH_FRAMES || (plan->path == ASR_PATH_AUTO && noisy);
+}
+
+extern "C" int32_t asr_plan_launches(const asr_plan* plan, int32_t noisy) {
   FrLayout lo;
-  return (plan && plan->fr_ok && frames_layout(plan, &lo)) ? 3 : 1;
+  return (plan && plan->fr_ok && plan->path != ASR_PATH_CLIP && frames_path_wanted(plan, noisy != 0) && frames_layout(plan, &lo)) ? 3 : 1;
+}
+
+extern "C" int asr_plan_set_path(asr_plan* plan, int32_t path) {
+  if (!plan || path < ASR_PATH_AUTO || path > ASR_PATH_FRAMES) { set_error("asr_plan_set_path: bad argument"); return ASR_ERR_INVALID; }
+  plan->path = path;
+  return ASR_OK;
 }
 
 static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
@@ -592,7 +602,7 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
   }
   // ---- n_fft = 512: block-pipelined path (frame prefix -> frames -> cepstra) ----
   FrLayout flo;
-  if (frames_path_usable(plan, n_clips, max_length, &flo)) {
+  if (frames_path_wanted(plan, kp.noise_mode != ASR_NOISE_NONE) && frames_path_usable(plan, n_clips, max_length, &flo)) {
     const WsLayout wl = ws_layout(plan, n_clips, max_length);
     char* ws = static_cast<char*>(workspace_dev);
     if (ws) {

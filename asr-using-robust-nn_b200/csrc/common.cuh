@@ -74,8 +74,10 @@ struct KParams {
 };
 
 // ---- block-pipelined path for n_fft = 512 (frames_kernel.cu) ----
-constexpr int kFrWarps = 16;
+constexpr int kFrWarps = 16;        // every warp: staging share, combine (2 slots), FFT (2 frames) per block
 constexpr int kFrThreads = kFrWarps * 32;
+constexpr int kFrMelWarps = 15;     // warps 0..14 share the mel segments; warp 15 assembles the block descriptors instead
+constexpr int kFrAllThreads = kFrThreads;
 constexpr int kFrBlock = 32;        // frames per block
 constexpr int kFrMaxRuns = 4;       // runs of consecutive frames (of one clip) per block, at most
 
@@ -144,6 +146,7 @@ struct asr_plan {
   std::vector<float> h_window, h_mel_dense, h_dct, h_taps;
   // ---- block-pipelined path (n_fft = 512): tables and layout; fr_ok = 0 -> the per-clip kernel is used ----
   int fr_ok;
+  int path;                // asr_path
   int sm_count;
   float* fr_blob_dev;
   int fr_blob_f4;          // part copied to shared memory by the frames kernel

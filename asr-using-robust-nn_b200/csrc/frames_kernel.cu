@@ -229,95 +229,58 @@ struct FBlock {
 constexpr int kFrRing = 8;
 constexpr int kClipCache = 64;    // clips whose (offset, length, frame count) are cached in shared memory
 struct ClipMeta { long long off; int L; int T; };
-constexpr int kWorkWarps = kFrWarps - 1;          // the last warp assembles block descriptors instead of staging / mel / combine
-constexpr int kWorkThreads = kWorkWarps * 32;
-constexpr int kPfUnits = 3;                       // staging units per worker thread whose loads are issued ahead
+constexpr int kStageBatch = 3;                    // units per producer thread whose loads are in flight together
 
-// linear unit index -> (run, staged position, original sample index); false if u is past the block's units
-__device__ __forceinline__ bool locate_unit(const FParams& fp, const FBlock& blk, const int u, int& r, int& dst, int& orig) {
-  r = -1;
-#pragma unroll
-  for (int rr = 0; rr < kFrMaxRuns; ++rr)
-    if (rr < blk.n_runs && blk.run[rr].unit0 >= 0 && u >= blk.run[rr].unit0) r = rr;
-  if (r < 0) return false;
-  const FRun& run = blk.run[r];
-  const int local = u - run.unit0;
-  if (local >= (run.count >> 2)) return false;
-  dst = run.aud0 + 4 * local;
-  orig = run.p0 - fp.pad + 4 * local;
-  return true;
-}
-
+// Producer warps: stage the samples of every run of the block, once per sample.  Loads of a batch of units are
+// issued back to back, then converted and stored; nobody else waits on these warps until the iteration barrier.
 template <int DT>
-struct StagePf {
-  UnitRaw<DT> raw[kPfUnits];
-  UnitZ z[kPfUnits];
-  int have;
-};
-
-// issue the global loads of units wtid + k * kWorkThreads, k < kPfUnits (consumed later by stage_finish)
-template <int DT>
-__device__ __forceinline__ void stage_issue(const FParams& fp, const FBlock& blk, const int wtid, StagePf<DT>& pf) {
-  pf.have = 0;
-#pragma unroll
-  for (int k = 0; k < kPfUnits; ++k) {
-    const int u = wtid + k * kWorkThreads;
-    int r, dst, orig;
-    if (u < blk.n_units && locate_unit(fp, blk, u, r, dst, orig) && orig >= 0 && orig + 4 <= blk.run[r].L) {
-      const long long e = blk.run[r].base + orig;
-      unit_load<DT>(fp, e, pf.raw[k]);
-      if (fp.noise_mode == ASR_NOISE_WHITE) unit_load_z(fp.z, e, pf.z[k]);
-      pf.have |= 1 << k;
-    }
-  }
-}
-
-template <int DT>
-__device__ __forceinline__ void stage_unit(const FParams& fp, const FBlock& blk, float* __restrict__ aud, const int u,
-                                           const bool have, const UnitRaw<DT>& raw_in, const UnitZ& z_in) {
+__device__ __forceinline__ void stage_block(const FParams& fp, const FBlock& blk, float* __restrict__ aud, const int ptid,
+                                            const int n_threads) {
   // clean int16 is staged UNSCALED (the window table carries the exact 2^-15); scaling by 2^15 is exact
-  const float scale = (DT == ASR_I16 && fp.noise_mode == ASR_NOISE_NONE) ? 32768.0f : 1.0f;
-  int r, dst, orig;
-  if (!locate_unit(fp, blk, u, r, dst, orig)) return;
-  const FRun& run = blk.run[r];
-  const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
-  float4 v;
-  if (orig >= 0 && orig + 4 <= run.L) {
-    const long long e = run.base + orig;
-    if (have && fp.noise_mode != ASR_NOISE_MIXTURE) {
-      v = unit_convert<DT>(fp, raw_in, z_in, z_in, sig);
-    } else {
-      UnitRaw<DT> raw;
-      UnitZ zz, gg;
-      unit_load<DT>(fp, e, raw);
-      if (fp.noise_mode != ASR_NOISE_NONE) unit_load_z(fp.z, e, zz);
-      if (fp.noise_mode == ASR_NOISE_MIXTURE) unit_load_z(fp.z2, e, gg);
-      v = unit_convert<DT>(fp, raw, zz, gg, sig);
-    }
-  } else {
-    v.x = padded_at<DT>(fp, run.base, run.L, orig + fp.pad, sig) * scale;
-    v.y = padded_at<DT>(fp, run.base, run.L, orig + fp.pad + 1, sig) * scale;
-    v.z = padded_at<DT>(fp, run.base, run.L, orig + fp.pad + 2, sig) * scale;
-    v.w = padded_at<DT>(fp, run.base, run.L, orig + fp.pad + 3, sig) * scale;
-  }
-  *reinterpret_cast<float4*>(aud + dst) = v;
-}
-
-// store what stage_issue loaded, then everything of the block the prefetched units do not cover
-// (n_threads participants, `first` = first unit not prefetched)
-template <int DT>
-__device__ __forceinline__ void stage_rest(const FParams& fp, const FBlock& blk, float* __restrict__ aud, const int wtid,
-                                           const int n_threads, const int first) {
-  StagePf<DT> none;
-  for (int u = first + wtid; u < blk.n_units; u += n_threads) stage_unit<DT>(fp, blk, aud, u, false, none.raw[0], none.z[0]);
-  // runs that cannot be staged by units (odd alignment, pre-emphasis): sample by sample
   const float scale = (DT == ASR_I16 && fp.noise_mode == ASR_NOISE_NONE) ? 32768.0f : 1.0f;
   for (int r = 0; r < blk.n_runs; ++r) {
     const FRun& run = blk.run[r];
-    if (run.unit0 >= 0) continue;
     const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
-    for (int i = wtid; i < run.count; i += n_threads)
-      aud[run.aud0 + i] = padded_at<DT>(fp, run.base, run.L, run.p0 + i, sig) * scale;
+    float* dst = aud + run.aud0;
+    if (run.unit0 < 0) {      // odd alignment or pre-emphasis: sample by sample
+      for (int i = ptid; i < run.count; i += n_threads) dst[i] = padded_at<DT>(fp, run.base, run.L, run.p0 + i, sig) * scale;
+      continue;
+    }
+    const int nu = run.count >> 2, orig0 = run.p0 - fp.pad;
+    for (int u0 = ptid; u0 < nu; u0 += n_threads * kStageBatch) {
+      UnitRaw<DT> raw[kStageBatch];
+      UnitZ zz[kStageBatch];
+      unsigned inside = 0;
+#pragma unroll
+      for (int k = 0; k < kStageBatch; ++k) {
+        const int u = u0 + k * n_threads, orig = orig0 + 4 * u;
+        if (u < nu && orig >= 0 && orig + 4 <= run.L) {
+          const long long e = run.base + orig;
+          unit_load<DT>(fp, e, raw[k]);
+          if (fp.noise_mode != ASR_NOISE_NONE) unit_load_z(fp.z, e, zz[k]);
+          inside |= 1u << k;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kStageBatch; ++k) {
+        const int u = u0 + k * n_threads;
+        if (u < nu) {
+          float4 v;
+          if ((inside >> k) & 1u) {
+            UnitZ gg = zz[k];
+            if (fp.noise_mode == ASR_NOISE_MIXTURE) unit_load_z(fp.z2, run.base + orig0 + 4 * u, gg);   // carrier stream (rare path: not batched)
+            v = unit_convert<DT>(fp, raw[k], zz[k], gg, sig);
+          } else {
+            const int p = run.p0 + 4 * u;
+            v.x = padded_at<DT>(fp, run.base, run.L, p, sig) * scale;
+            v.y = padded_at<DT>(fp, run.base, run.L, p + 1, sig) * scale;
+            v.z = padded_at<DT>(fp, run.base, run.L, p + 2, sig) * scale;
+            v.w = padded_at<DT>(fp, run.base, run.L, p + 3, sig) * scale;
+          }
+          *reinterpret_cast<float4*>(dst + 4 * u) = v;
+        }
+      }
+    }
   }
 }
 
@@ -329,7 +292,7 @@ __device__ __forceinline__ float fast_log2(const float x) {     // x >= amin > 0
 
 // ------------------------------------------------------------------------------------------------
 template <int DT>
-__global__ void __launch_bounds__(kFrThreads, 1) frames512_kernel(const __grid_constant__ FParams fp) {
+__global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __grid_constant__ FParams fp) {
   extern __shared__ __align__(16) float smem[];
   __shared__ FBlock ring[kFrRing];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -346,7 +309,7 @@ __global__ void __launch_bounds__(kFrThreads, 1) frames512_kernel(const __grid_c
   // ---- tables: global blob -> shared ----
   {
     float4* dst = reinterpret_cast<float4*>(smem);
-    for (int i = tid; i < fp.blob_f4; i += kFrThreads) dst[i] = __ldg(fp.blob + i);
+    for (int i = tid; i < fp.blob_f4; i += kFrAllThreads) dst[i] = __ldg(fp.blob + i);
   }
   const float2* s_win2 = reinterpret_cast<const float2*>(smem + fp.off_window);
   const float* s_twp = smem + fp.off_twp;
@@ -357,10 +320,10 @@ __global__ void __launch_bounds__(kFrThreads, 1) frames512_kernel(const __grid_c
   float* s_S = smem + fp.sm_S;              // [2][32][s_pitch]
   float* s_xb = smem + fp.sm_xb;            // [16 warps][2][xb_stride]
   float* s_part = smem + fp.sm_part;        // [2][n_refs][33]
-  for (int i = tid; i < 2 * kFrBlock * fp.s_pitch; i += kFrThreads) s_S[i] = 0.0f;    // incl. the zero tail of every row
+  for (int i = tid; i < 2 * kFrBlock * fp.s_pitch; i += kFrAllThreads) s_S[i] = 0.0f;    // incl. the zero tail of every row
 
   // ---- block cursor (lane 0 of the last warp) over a shared-memory cache of the clips' metadata ----
-  constexpr int kAsmWarp = kFrWarps - 1;
+  constexpr int kAsmWarp = kFrMelWarps;               // this warp assembles the block descriptors instead of taking mel segments
   __shared__ ClipMeta s_meta[kClipCache];
   int b_cur = 0, t_cur = 0, g_cur = g_begin, cache_base = 0;
   {
@@ -441,20 +404,20 @@ __global__ void __launch_bounds__(kFrThreads, 1) frames512_kernel(const __grid_c
     __syncthreads();                                   // also: tables and the zeroed S
     if (ring[i].refill >= 0) { load_meta(ring[i].refill); __syncthreads(); }
   }
-  stage_rest<DT>(fp, ring[0], s_aud, tid, kFrThreads, 0);
+  stage_block<DT>(fp, ring[0], s_aud, tid, kFrAllThreads);
   __syncthreads();
 
   // ---- per-thread constants of the phases ----
   const int part_buf = fp.n_refs * 33;                 // floats per partial buffer
   const bool comb_lane = lane < fp.n_mels;
   const float* comb_pj = s_part + (comb_lane ? (2 * lane + 1) * 33 : 0);   // rise partial of filter `lane`; fall of it is 33 further
-  const int2 mel_range = warp < kWorkWarps ? reinterpret_cast<const int2*>(smem + fp.off_wrange)[warp] : make_int2(0, 0);
+  const int2 mel_range = warp < kFrMelWarps ? reinterpret_cast<const int2*>(smem + fp.off_wrange)[warp] : make_int2(0, 0);
   const int fft_h = lane >> 4, fft_l = lane & 15;
   const int fft_slot = 8 * (warp >> 2) + (warp & 3) + 4 * fft_h;   // half-warps 4 slots apart: complementary bank halves of S
   float* const fft_xb = s_xb + (warp * 2 + fft_h) * fp.xb_stride;
   const int s_buf = kFrBlock * fp.s_pitch;
-  int cm_clip0 = -1, cm_clip1 = -1, cm_clip2 = -1;     // combine: clip whose maximum is being accumulated (per slot position)
-  float cm_max0 = -3.0e38f, cm_max1 = -3.0e38f, cm_max2 = -3.0e38f;
+  int cm_clip[2] = {-1, -1};                           // combine: clip whose maximum is being accumulated (per slot position)
+  float cm_max[2] = {-3.0e38f, -3.0e38f};
   auto flush_max = [&](const int clip, float mx) {
     if (clip >= 0) {
 #pragma unroll
@@ -499,61 +462,50 @@ __global__ void __launch_bounds__(kFrThreads, 1) frames512_kernel(const __grid_c
     const int n_fft = b_fft->n_slots;
     if (n_comb == 0 && n_mel == 0 && n_fft == 0 && b_fft->fin) break;      // uniform over the CTA
     FBlock* nb;
+    // ---- descriptor of block it+2 (one warp, in place of its mel share) ----
     if (warp == kAsmWarp) {
-      // ---- scheduler warp: descriptor of block it+2 while the others stage / combine / mel ----
       nb = &ring[(it + 2) % kFrRing];
       if (lane == 0) assemble_runs(*nb);
       __syncwarp();
       fill_slots(*nb);
-    } else {
-      // ---- stage (block it+1): loads of this thread's first units are issued now, consumed after the mel phase ----
-      float* const aud_next = s_aud + (par ^ 1) * fp.aud_cap;
-      StagePf<DT> pf;
-      stage_issue<DT>(fp, *b_stage, tid, pf);
+    }
+    // ---- stage (block it+1): samples -> shared memory, once per sample ----
+    if (b_stage->n_slots > 0) stage_block<DT>(fp, *b_stage, s_aud + (par ^ 1) * fp.aud_cap, tid, kFrThreads);
 
-      // ---- combine (block it-2): lanes <-> filters; warp w takes slots w, w+15, w+30.
-      //      filter j = rising slope over segment j + falling slope over segment j+1 ----
-      if (n_comb > 0) {
-        const float* part = s_part + par * part_buf;
-        if (warp < n_comb) combine_slot(*b_comb, part, warp, cm_clip0, cm_max0);
-        if (warp + kWorkWarps < n_comb) combine_slot(*b_comb, part, warp + kWorkWarps, cm_clip1, cm_max1);
-        if (warp + 2 * kWorkWarps < n_comb) combine_slot(*b_comb, part, warp + 2 * kWorkWarps, cm_clip2, cm_max2);
-      }
-
-      // ---- mel (block it-1): lanes <-> frames, this warp's segments ----
-      if (n_mel > 0) {
-        const float* S = s_S + (par ^ 1) * s_buf + lane * fp.s_pitch;      // S buffer of block it-1
-        float* part = s_part + (par ^ 1) * part_buf + lane;
-#pragma unroll 1
-        for (int pi = mel_range.x; pi < mel_range.x + mel_range.y; ++pi) {
-          const int4 pc = s_pieces[pi];                 // (first bin (multiple of 4), PAIRS of float4 groups, weight offset (float4), fall-partial offset)
-          const float4* sp = reinterpret_cast<const float4*>(S + pc.x);
-          const float4* wt = s_wtab + pc.z;
-          float a = 0.0f, b = 0.0f;
-#pragma unroll 1
-          for (int q = 0; q < pc.y; ++q) {
+    // ---- combine (block it-2): lanes <-> filters; warp w takes slots w and w+16.
+    //      filter j = rising slope over segment j + falling slope over segment j+1 ----
+    if (n_comb > 0) {
+      const float* part = s_part + par * part_buf;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float4 sv = sp[2 * q + u];
-              const float4 w01 = wt[4 * q + 2 * u], w23 = wt[4 * q + 2 * u + 1];
-              a = fmaf(w01.x, sv.x, a); b = fmaf(w01.y, sv.x, b);
-              a = fmaf(w01.z, sv.y, a); b = fmaf(w01.w, sv.y, b);
-              a = fmaf(w23.x, sv.z, a); b = fmaf(w23.y, sv.z, b);
-              a = fmaf(w23.z, sv.w, a); b = fmaf(w23.w, sv.w, b);
-            }
+      for (int h = 0; h < 2; ++h)
+        if (warp + kFrWarps * h < n_comb) combine_slot(*b_comb, part, warp + kFrWarps * h, cm_clip[h], cm_max[h]);
+    }
+
+    // ---- mel (block it-1): lanes <-> frames, this warp's segments ----
+    if (n_mel > 0) {
+      const float* S = s_S + (par ^ 1) * s_buf + lane * fp.s_pitch;      // S buffer of block it-1
+      float* part = s_part + (par ^ 1) * part_buf + lane;
+#pragma unroll 1
+      for (int pi = mel_range.x; pi < mel_range.x + mel_range.y; ++pi) {
+        const int4 pc = s_pieces[pi];                 // (first bin (multiple of 4), PAIRS of float4 groups, weight offset (float4), fall-partial offset)
+        const float4* sp = reinterpret_cast<const float4*>(S + pc.x);
+        const float4* wt = s_wtab + pc.z;
+        float a = 0.0f, b = 0.0f;
+#pragma unroll 1
+        for (int q = 0; q < pc.y; ++q) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 sv = sp[2 * q + u];
+            const float4 w01 = wt[4 * q + 2 * u], w23 = wt[4 * q + 2 * u + 1];
+            a = fmaf(w01.x, sv.x, a); b = fmaf(w01.y, sv.x, b);
+            a = fmaf(w01.z, sv.y, a); b = fmaf(w01.w, sv.y, b);
+            a = fmaf(w23.x, sv.z, a); b = fmaf(w23.y, sv.z, b);
+            a = fmaf(w23.z, sv.w, a); b = fmaf(w23.w, sv.w, b);
           }
-          part[pc.w] = a;                               // falling slope of filter seg-1
-          part[pc.w + 33] = b;                          // rising slope of filter seg
         }
+        part[pc.w] = a;                               // falling slope of filter seg-1
+        part[pc.w + 33] = b;                          // rising slope of filter seg
       }
-
-      // ---- stage (block it+1): convert and store ----
-#pragma unroll
-      for (int k = 0; k < kPfUnits; ++k) {
-        const int u = tid + k * kWorkThreads;
-        if (u < b_stage->n_units) stage_unit<DT>(fp, *b_stage, aud_next, u, (pf.have >> k) & 1, pf.raw[k], pf.z[k]);
-      }
-      if (b_stage->n_slots > 0) stage_rest<DT>(fp, *b_stage, aud_next, tid, kWorkThreads, kPfUnits * kWorkThreads);
     }
 
     // ---- fft (block it) ----
@@ -569,9 +521,8 @@ __global__ void __launch_bounds__(kFrThreads, 1) frames512_kernel(const __grid_c
     __syncthreads();
     if (nb->refill >= 0) { load_meta(nb->refill); __syncthreads(); }   // rare: the cursor ran past the cached clips
   }
-  flush_max(cm_clip0, cm_max0);
-  flush_max(cm_clip1, cm_max1);
-  flush_max(cm_clip2, cm_max2);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) flush_max(cm_clip[h], cm_max[h]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -694,7 +645,7 @@ static cudaError_t launch_frames_dt(const FParams& fp, int grid, int smem_bytes,
     if (e != cudaSuccess) return e;
     granted = smem_bytes;
   }
-  frames512_kernel<DT><<<grid, kFrThreads, smem_bytes, stream>>>(fp);
+  frames512_kernel<DT><<<grid, kFrAllThreads, smem_bytes, stream>>>(fp);
   return cudaGetLastError();
 }
 

@@ -75,10 +75,11 @@ __device__ __forceinline__ void load_frame_global(const KParams& kp, const long 
 #pragma unroll
     for (int n2 = 0; n2 < P; ++n2) {
       const int n = l + G * n2;
-      const int v = __ldg(p + n);
+      const unsigned v = static_cast<unsigned>(__ldg(p + n)) ^ 0x80008000u;
       const float2 w = win2_i16[n];                        // window / 32768 (exact power-of-two scaling)
-      re[brev<P>(n2)] = static_cast<float>(static_cast<short>(v)) * w.x;
-      im[brev<P>(n2)] = static_cast<float>(v >> 16) * w.y;
+      // exact int16 -> float on the ALU/FMA pipes: bits(2^23 + (s + 32768)) - (2^23 + 32768) = s
+      re[brev<P>(n2)] = (__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7410)) - 8421376.0f) * w.x;
+      im[brev<P>(n2)] = (__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7432)) - 8421376.0f) * w.y;
     }
   } else if (DT == ASR_F32) {
     const float2* p = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(kp.audio) + e_start);

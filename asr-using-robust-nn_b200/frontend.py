@@ -149,7 +149,8 @@ class MfccPlan:
     """Immutable tables for one parameter set (wraps ``asr_plan``)."""
 
 
-    def __init__(self, params: MfccParams, device: Optional[int] = None):
+    def __init__(self, params: MfccParams, device: Optional[int] = None, path: str = "auto"):
+        """`path`: "auto", "clip" (one CTA per clip) or "frames" (block-pipelined n_fft = 512 path); see asr_path."""
         _require_cuda()
         self.params = params
         self.device = torch.cuda.current_device() if device is None else int(device)
@@ -157,6 +158,7 @@ class MfccPlan:
         with torch.cuda.device(self.device):
             pc = params.to_c()
             check(lib.asr_plan_create(C.byref(pc), C.byref(self._h)), "asr_plan_create")
+        check(lib.asr_plan_set_path(self._h, {"auto": 0, "clip": 1, "frames": 2}[path]), "asr_plan_set_path")
         self._ws = {}       # stream -> scratch tensor (the n_fft = 512 path keeps log-mel rows there between its launches)
 
     def __del__(self):
@@ -169,10 +171,9 @@ class MfccPlan:
     def feature_rows(self) -> int:
         return lib.asr_plan_feature_rows(self._h)
 
-    @property
-    def launches(self) -> int:
+    def launches(self, noisy: bool = False) -> int:
         """Kernels one `mfcc` call launches (1, or 3 on the block-pipelined n_fft = 512 path)."""
-        return lib.asr_plan_launches(self._h)
+        return lib.asr_plan_launches(self._h, int(noisy))
 
     def _workspace(self, n_clips: int, max_length: int, device) -> Optional[torch.Tensor]:
         need = lib.asr_mfcc_workspace_bytes(self._h, n_clips, max_length)

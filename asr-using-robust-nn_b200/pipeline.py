@@ -52,7 +52,7 @@ class NoisyFeaturePipeline:
         self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch (eager steps only)
 
     def launches_per_step(self, noisy: bool, standardize: bool = True) -> int:
-        return self.plan.launches + (LAUNCHES_NOISE if noisy else 0) + (LAUNCHES_CMVN if standardize else 0)
+        return self.plan.launches(noisy) + (LAUNCHES_NOISE if noisy else 0) + (LAUNCHES_CMVN if standardize else 0)
 
     def _feat_buffer(self, B: int) -> torch.Tensor:
         if self._feats is None or self._feats.shape[0] != B:

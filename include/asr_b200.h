@@ -153,8 +153,15 @@ int asr_mfcc_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, c
 
 /* Bytes of scratch the two entry points above/below need for such a batch (0: none needed). */
 size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips, int32_t max_length);
-/* Kernel launches one asr_mfcc_batch call makes with this plan (1, or 3 on the n_fft = 512 path). */
-int32_t asr_plan_launches(const asr_plan* plan);
+/* Kernel path of asr_mfcc_batch / asr_logmel_batch.  Two implementations exist for n_fft = 512 with an even hop:
+ *   ASR_PATH_CLIP    one CTA (or cluster) per clip, everything in one launch (the only path for other n_fft);
+ *   ASR_PATH_FRAMES  block-pipelined: frame prefix -> frames (persistent, all clips' frames as one list) -> cepstra.
+ * ASR_PATH_AUTO (default) takes FRAMES when noise is fused into the launch (each sample and its noise are then
+ * read and mixed once instead of once per overlapping frame) and CLIP otherwise.  Tests force either path. */
+typedef enum asr_path { ASR_PATH_AUTO = 0, ASR_PATH_CLIP = 1, ASR_PATH_FRAMES = 2 } asr_path;
+int asr_plan_set_path(asr_plan* plan, int32_t path);
+/* Kernel launches one asr_mfcc_batch call makes with this plan: 1 (CLIP) or 3 (FRAMES); `noisy` as in the call. */
+int32_t asr_plan_launches(const asr_plan* plan, int32_t noisy);
 
 /* Stage-level probe for parity tests: the clamped log-mel matrix [n_clips][n_mels][out_frames] (float32). */
 int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,

@@ -18,6 +18,18 @@ pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 ATOL, RTOL = 2e-3, 2e-5
+PATH = "auto"
+
+
+@pytest.fixture(params=["clip", "frames"], autouse=True)
+def _kernel_path(request):
+    """Every test runs on both kernel paths: one CTA per clip, and the block-pipelined n_fft = 512 path
+    (presets with another n_fft only have the first; "frames" then falls back to it)."""
+    global PATH
+    PATH = request.param
+    yield
+    PATH = "auto"
+
 
 
 def _o():
@@ -38,7 +50,7 @@ def _close(got, ref, atol=ATOL, rtol=RTOL):
 
 def _run(preset, clips, out_frames=None, dtype=None, **kw):
     import asr_b200 as A
-    plan = A.MfccPlan(A.PRESETS[preset].replace(**kw) if kw else A.PRESETS[preset])
+    plan = A.MfccPlan(A.PRESETS[preset].replace(**kw) if kw else A.PRESETS[preset], path=PATH)
     batch = A.ClipBatch.from_arrays(clips, dtype=dtype)
     out, status = plan.mfcc(batch, out_frames=out_frames)
     torch.cuda.synchronize()
@@ -148,7 +160,7 @@ def test_logmel_stage():
     lr = _o()
     import asr_b200 as A
     clips = to_f32(synth_clips(2, 16000, 16000, 8))
-    plan = A.MfccPlan(A.C1)
+    plan = A.MfccPlan(A.C1, path=PATH)
     out, st = plan.logmel(A.ClipBatch.from_arrays(clips))
     ref = np.stack([lr.log_mel(c, lr.C1) for c in clips])
     _close(out.cpu().numpy(), ref, atol=1e-3, rtol=0)
@@ -178,7 +190,7 @@ def test_large_batch_properties_c1():
     """BASELINE-size batch (1024 clips): order independence and determinism instead of a CPU oracle pass."""
     import asr_b200 as A
     clips = synth_clips(1024, 16000, 16000, 123)
-    plan = A.MfccPlan(A.C1)
+    plan = A.MfccPlan(A.C1, path=PATH)
     a, st = plan.mfcc(A.ClipBatch.from_arrays(clips))
     perm = np.random.default_rng(0).permutation(1024)
     b, _ = plan.mfcc(A.ClipBatch.from_arrays([clips[i] for i in perm]))
@@ -190,3 +202,60 @@ def test_large_batch_properties_c1():
     lr = _o()
     for i in (0, 511, 1023):
         _close(a[i:i + 1].cpu().numpy(), lr.mfcc(to_f32([clips[i]])[0], lr.C1)[None])
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.float32, np.float64])
+def test_fused_noise_c1(dtype):
+    """White (per-clip sigma) and Gaussian-mixture noise fused into the launch == oracle mix -> oracle MFCC, on both
+    kernel paths and for every input dtype; ragged lengths so blocks of the frames path straddle clips."""
+    import asr_b200 as A
+    from oracle import noise_ref as nr
+    lr = _o()
+    lengths = [16000, 8000, 16000, 4321, 12000]
+    clips = synth_clips(len(lengths), 0, 16000, 91, lengths=lengths)
+    if dtype == np.int16:
+        host = clips
+        xs = to_f32(clips)
+    else:
+        xs = [c.astype(dtype) for c in to_f32(clips)]
+        host = xs
+    rng = np.random.default_rng(5)
+    zs = [rng.standard_normal(n) for n in lengths]
+    gs = [rng.standard_normal(n) for n in lengths]
+    sig = np.array([0.01, 0.02, 0.005, 0.03, 0.0], dtype=np.float64)
+    plan = A.MfccPlan(A.C1, path=PATH)
+    batch = A.ClipBatch.from_arrays(host)
+    zd = A.ClipBatch.from_arrays(zs).audio
+    gd = A.ClipBatch.from_arrays(gs).audio
+    out, st = plan.mfcc(batch, noise=A.Noise.white(zd, torch.from_numpy(sig).cuda()))
+    assert int(st.max()) == 0
+    ref = [lr.mfcc(nr.add_white_noise_z(x, s, z).astype(np.float64), lr.C1) for x, s, z in zip(xs, sig, zs)]
+    for i, r in enumerate(ref):
+        _close(out[i:i + 1, :, :r.shape[1]].cpu().numpy(), r[None], atol=3e-3)
+        assert (out[i, :, r.shape[1]:] == 0).all()
+    out, st = plan.mfcc(batch, noise=A.Noise.mixture(zd, gd, 0.01, 0.004))
+    ref = [lr.mfcc(nr.add_noise_z(x, 0.01, 0.004, q, g).astype(np.float64), lr.C1) for x, q, g in zip(xs, zs, gs)]
+    for i, r in enumerate(ref):
+        _close(out[i:i + 1, :, :r.shape[1]].cpu().numpy(), r[None], atol=3e-3)
+
+
+def test_many_tiny_and_empty_clips():
+    """Clips of a few frames, clips that cannot be framed and long clips in one batch: the frames path packs up to
+    four runs into a 32-frame block and must neither drop nor duplicate a frame."""
+    import asr_b200 as A
+    lr = _o()
+    rng = np.random.default_rng(17)
+    lengths = [300, 100, 16000, 257, 400, 0, 700, 320, 5000, 258, 100, 100, 100, 900, 16000, 480, 330, 260] * 3
+    clips = synth_clips(len(lengths), 0, 16000, 92, lengths=[max(1, n) for n in lengths])
+    clips = [c[:n] for c, n in zip(clips, lengths)]
+    plan = A.MfccPlan(A.C1, path=PATH)
+    out, st = plan.mfcc(A.ClipBatch.from_arrays(clips), out_frames=101)
+    st = st.cpu().numpy()
+    for i, (c, n) in enumerate(zip(clips, lengths)):
+        if n <= 256:
+            assert st[i] == 1 and (out[i] == 0).all()
+        else:
+            assert st[i] == 0
+            r = lr.mfcc(to_f32([c])[0], lr.C1)
+            _close(out[i:i + 1, :, :r.shape[1]].cpu().numpy(), r[None])
+            assert (out[i, :, r.shape[1]:] == 0).all()
