@@ -150,28 +150,47 @@ class NoisyFeaturePipeline:
                  first_index: int = 0) -> torch.Tensor:
         """End to end from PINNED host memory: (B, L) int16/float32 host tensor in, standardised
         float32 (B, D) rows written to the pinned `out_host`.  The noise stream is generated on the
-        device from `seed` (element index = first_index + position in this shard)."""
-        dev_audio = self._h2d_buffer(audio_host)
-        dev_audio.copy_(audio_host, non_blocking=True)
-        batch = ClipBatch.from_matrix(dev_audio)
-        z = None
-        if snr_db is not None:
-            z = self._z_buffer(dev_audio.numel())
-            randn(seed, first_index, dev_audio.numel(), device=self.device, out=z)
-        out = self.run_device(batch, z, snr_db)
-        out_host.copy_(out, non_blocking=True)
+        device from `seed` (element index = first_index + position in this shard).
+
+        Three streams (host->device copy, compute, device->host copy) and two sets of device buffers: the
+        upload of call i+1 overlaps the kernels of call i and the download of call i-1.  The caller's current
+        stream is made to wait for this call's download, so `torch.cuda.current_stream().synchronize()` (or
+        an event recorded after the call) covers it."""
+        hs = self._host_slots(audio_host)
+        k = self._host_turn
+        self._host_turn ^= 1
+        sl = hs[k]
+        cur = torch.cuda.current_stream(self.device)
+        self._s_h2d.wait_event(sl["computed"])            # the kernels of the call that last used this slot are done
+        with torch.cuda.stream(self._s_h2d):
+            sl["audio"].copy_(audio_host, non_blocking=True)
+            sl["uploaded"].record()
+        self._s_comp.wait_event(sl["uploaded"])
+        self._s_comp.wait_event(sl["downloaded"])          # this slot's output buffer has been read back
+        with torch.cuda.stream(self._s_comp):
+            batch = ClipBatch.from_matrix(sl["audio"])
+            z = None
+            if snr_db is not None:
+                z = sl["z"]
+                randn(seed, first_index, z.numel(), device=self.device, out=z)
+            out = self.run_device(batch, z, snr_db)
+            sl["computed"].record()
+        self._s_d2h.wait_event(sl["computed"])
+        with torch.cuda.stream(self._s_d2h):
+            out_host.copy_(out, non_blocking=True)
+            sl["downloaded"].record()
+        cur.wait_event(sl["downloaded"])
         return out_host
 
-    def _h2d_buffer(self, audio_host: torch.Tensor) -> torch.Tensor:
-        b = getattr(self, "_h2d", None)
-        if b is None or b.shape != audio_host.shape or b.dtype != audio_host.dtype:
-            b = torch.empty(audio_host.shape, dtype=audio_host.dtype, device=self.device)
-            self._h2d = b
-        return b
-
-    def _z_buffer(self, n: int) -> torch.Tensor:
-        b = getattr(self, "_z", None)
-        if b is None or b.numel() != n:
-            b = torch.empty(n, dtype=torch.float64, device=self.device)
-            self._z = b
-        return b
+    def _host_slots(self, audio_host: torch.Tensor):
+        hs = getattr(self, "_hs", None)
+        if hs is None or hs[0]["audio"].shape != audio_host.shape or hs[0]["audio"].dtype != audio_host.dtype:
+            self._s_h2d, self._s_comp, self._s_d2h = (torch.cuda.Stream(self.device) for _ in range(3))
+            hs = []
+            for _ in range(2):
+                hs.append({"audio": torch.empty(audio_host.shape, dtype=audio_host.dtype, device=self.device),
+                           "z": torch.empty(audio_host.numel(), dtype=torch.float64, device=self.device),
+                           "uploaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "downloaded": torch.cuda.Event()})
+            self._hs = hs
+            self._host_turn = 0
+        return hs

@@ -1,0 +1,61 @@
+"""The C2 step as the bench runs it: graph-replayed device pipeline and the three-stream host pipeline."""
+import numpy as np
+import pytest
+import torch
+
+from synth import synth_clips, to_f32
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference_step(clips_i16, snr, z_host):
+    from oracle import librosa_ref as lr, noise_ref as nr, cmvn_ref as cr
+    rows = []
+    for c, z in zip(to_f32(clips_i16), z_host):
+        x = nr.add_white_noise_with_snr_z(c, snr, z) if snr is not None else c
+        rows.append(lr.mfcc(np.asarray(x), lr.C1).astype(np.float64).flatten())
+    rows = np.stack(rows)
+    a, b, c = cr.standardize_dataset(rows[:1], rows[1:2], rows[2:])
+    return np.concatenate([a, b, c])
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_device_step_matches_oracle(use_graphs):
+    import asr_b200 as A
+    from asr_b200.pipeline import NoisyFeaturePipeline
+    B, L = 24, 16000
+    clips = synth_clips(B, L, 16000, 501)
+    audio = torch.from_numpy(np.stack(clips)).cuda()
+    batch = A.ClipBatch.from_matrix(audio)
+    z = A.randn(7, 0, B * L)
+    zh = z.cpu().numpy().reshape(B, L)
+    pipe = NoisyFeaturePipeline(A.C1, 101, use_graphs=use_graphs)
+    for snr in (10, 0, 10):                      # the third call replays the graph captured by the first
+        out = pipe.run_device(batch, z, snr).cpu().numpy()
+        ref = _reference_step(clips, snr, zh)
+        # standardised units: the per-column scale divides the 3e-3 feature tolerance by a std of order 1..10
+        assert np.abs(out - ref).max() < 2e-2
+        assert np.abs(out - ref).mean() < 2e-4
+    out = pipe.run_device(batch, None, None).cpu().numpy()
+    ref = _reference_step(clips, None, zh)
+    assert np.abs(out - ref).max() < 2e-2
+
+
+def test_host_pipeline_slots_do_not_race():
+    """Consecutive run_host calls with different inputs and SNRs: each result equals the eager device step."""
+    import asr_b200 as A
+    from asr_b200.pipeline import NoisyFeaturePipeline
+    B, L = 64, 16000
+    pipe = NoisyFeaturePipeline(A.C1, 101)
+    eager = NoisyFeaturePipeline(A.C1, 101, use_graphs=False)
+    hosts = [torch.from_numpy(np.stack(synth_clips(B, L, 16000, 600 + i))).pin_memory() for i in range(3)]
+    outs = [torch.empty((B, pipe.D), dtype=torch.float32).pin_memory() for _ in range(6)]
+    snrs = [0, 5, 10, 20, None, 5]
+    for i in range(6):
+        pipe.run_host(hosts[i % 3], snrs[i], 99, outs[i], first_index=1000 * i)
+    torch.cuda.current_stream().synchronize()
+    for i in range(6):
+        dev = hosts[i % 3].cuda()
+        z = A.randn(99, 1000 * i, B * L) if snrs[i] is not None else None
+        want = eager.run_device(A.ClipBatch.from_matrix(dev), z, snrs[i]).cpu()
+        assert torch.equal(outs[i], want), i
