@@ -66,22 +66,53 @@ __device__ __forceinline__ float leaf_sum8(const void* __restrict__ audio, const
   return r;
 }
 
-template <int DT>
-__global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* __restrict__ audio,
-                                                                     const long long* __restrict__ offsets,
-                                                                     const int* __restrict__ lengths,
-                                                                     float* __restrict__ power, const int n_clips) {
-  __shared__ PowScratch scratch[kPowWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kPowWarps + warp;
-  if (b >= n_clips) return;
-  PowScratch& sc = scratch[warp];
-  const int L = lengths[b];
-  const long long base = offsets[b];
-  if (L <= 0) {                                   // np.mean of an empty array is nan
-    if (lane == 0) power[b] = __int_as_float(0x7fc00000);
-    return;
+// Leaf table of a length: (offset, length, merges after the leaf) in left-to-right order.  Built once per CTA for
+// the length of its first clip (a batch usually holds one length) and replayed by every warp whose clip has that
+// length; other clips walk the tree themselves (clip_power_walk).
+constexpr int kPowMaxLeaves = 640;       // covers lengths up to ~80 000 samples; longer clips take the walking path
+
+struct PowTable {
+  int n_leaves, length;
+  unsigned short off8[kPowMaxLeaves];    // leaf offset / 8 (every leaf starts on a multiple of 8)
+  unsigned char len[kPowMaxLeaves];      // leaf length, 1..128 -> stored minus 1... (0 marks an empty clip)
+  unsigned char merges[kPowMaxLeaves];
+};
+
+__device__ void pow_table_build(PowTable& tb, const int L, PowScratch& sc, const int lane) {
+  // lane 0 walks the tree; depth stack only (no values)
+  if (lane == 0) {
+    int sp = 0, vp = 0, n = 0;
+    bool ok = L > 0 && L <= 8 * 65535;
+    if (ok) { sc.s_off[0] = 0; sc.s_len[0] = L; sc.s_dep[0] = 0; sp = 1; }
+    while (sp > 0 && ok) {
+      --sp;
+      const int off = sc.s_off[sp], len = sc.s_len[sp], d = sc.s_dep[sp];
+      if (len > 128) {
+        int n2 = len / 2;
+        n2 -= n2 % 8;
+        sc.s_off[sp] = off + n2; sc.s_len[sp] = len - n2; sc.s_dep[sp] = d + 1;
+        sc.s_off[sp + 1] = off;  sc.s_len[sp + 1] = n2;  sc.s_dep[sp + 1] = d + 1;
+        sp += 2;
+      } else {
+        if (n >= kPowMaxLeaves) { ok = false; break; }
+        int k = 0, dd = d;
+        while (vp > 0 && sc.v_dep[vp - 1] == dd) { --vp; --dd; ++k; }
+        sc.v_dep[vp++] = dd;
+        tb.off8[n] = static_cast<unsigned short>(off >> 3);
+        tb.len[n] = static_cast<unsigned char>(len - 1);
+        tb.merges[n] = static_cast<unsigned char>(k);
+        ++n;
+      }
+    }
+    tb.n_leaves = ok ? n : 0;
+    tb.length = ok ? L : -1;
   }
+}
+
+// generic path: one warp walks the tree of its clip (any length)
+template <int DT>
+__device__ void clip_power_walk(const void* __restrict__ audio, const long long base, const int L, PowScratch& sc,
+                                const int lane, float* __restrict__ out) {
   const int g = lane >> 3, j = lane & 7;
   int sp = 0, vp = 0;                             // stack pointers (uniform over the warp)
   if (lane == 0) { sc.s_off[0] = 0; sc.s_len[0] = L; sc.s_dep[0] = 0; }
@@ -136,7 +167,84 @@ __global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* 
     __syncwarp();
   }
   // np.mean: float32 sum / count evaluated in float64, rounded to float32
-  if (lane == 0) power[b] = static_cast<float>(static_cast<double>(sc.v_val[0]) / static_cast<double>(L));
+  if (lane == 0) *out = static_cast<float>(static_cast<double>(sc.v_val[0]) / static_cast<double>(L));
+}
+
+// table path: leaves four at a time (one per group of 8 lanes), the loads of the next four are in flight while
+// the current four are summed; lane 0 replays the merge counts.
+template <int DT>
+__device__ void clip_power_replay(const void* __restrict__ audio, const long long base, const int L, const PowTable& tb,
+                                  PowScratch& sc, const int lane, float* __restrict__ out) {
+  const int g = lane >> 3, j = lane & 7;
+  const int nl = tb.n_leaves;
+  float cur[16], nxt[16];
+  auto fetch = [&](const int leaf, float (&v)[16]) {
+    const bool have = leaf < nl;
+    const int off = have ? 8 * tb.off8[leaf] : 0, n = have ? tb.len[leaf] + 1 : 0;
+    const int n8 = n - (n % 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (8 * i < n8) ? load_sq<DT>(audio, base + off + 8 * i + j) : 0.0f;
+  };
+  int vp = 0;
+  fetch(g, cur);
+  for (int l0 = 0; l0 < nl; l0 += 4) {
+    fetch(l0 + 4 + g, nxt);
+    const int leaf = l0 + g;
+    const bool have = leaf < nl;
+    const int off = have ? 8 * tb.off8[leaf] : 0, n = have ? tb.len[leaf] + 1 : 0;
+    const int n8 = n - (n % 8);
+    float r = 0.0f;
+    if (n >= 8) {
+      r = cur[0];
+#pragma unroll
+      for (int i = 1; i < 16; ++i)
+        if (8 * i < n8) r = __fadd_rn(r, cur[i]);
+    }
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    if (j == 0) {
+      if (n < 8) { r = 0.0f; for (int i = 0; i < n; ++i) r = __fadd_rn(r, load_sq<DT>(audio, base + off + i)); }
+      else for (int i = n8; i < n; ++i) r = __fadd_rn(r, load_sq<DT>(audio, base + off + i));
+    }
+    const float r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 8);
+    const float r2 = __shfl_sync(0xffffffffu, r, 16), r3 = __shfl_sync(0xffffffffu, r, 24);
+    if (lane == 0) {
+      const float rs[4] = {r0, r1, r2, r3};
+      for (int q = 0; q < 4 && l0 + q < nl; ++q) {
+        float v = rs[q];
+        for (int k = tb.merges[l0 + q]; k > 0; --k) v = __fadd_rn(sc.v_val[--vp], v);   // left + right
+        sc.v_val[vp++] = v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+  }
+  __syncwarp();
+  if (lane == 0) *out = static_cast<float>(static_cast<double>(sc.v_val[0]) / static_cast<double>(L));
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* __restrict__ audio,
+                                                                     const long long* __restrict__ offsets,
+                                                                     const int* __restrict__ lengths,
+                                                                     float* __restrict__ power, const int n_clips) {
+  __shared__ PowScratch scratch[kPowWarps];
+  __shared__ PowTable table;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.x * kPowWarps;
+  if (warp == 0) pow_table_build(table, lengths[b0], scratch[0], lane);
+  __syncthreads();
+  const int b = b0 + warp;
+  if (b >= n_clips) return;
+  const int L = lengths[b];
+  const long long base = offsets[b];
+  if (L <= 0) {                                   // np.mean of an empty array is nan
+    if (lane == 0) power[b] = __int_as_float(0x7fc00000);
+    return;
+  }
+  if (table.n_leaves > 0 && table.length == L) clip_power_replay<DT>(audio, base, L, table, scratch[warp], lane, power + b);
+  else clip_power_walk<DT>(audio, base, L, scratch[warp], lane, power + b);
 }
 
 __global__ void snr_sigma_kernel(const float* __restrict__ power, const float snr_db, double* __restrict__ sigma,

@@ -29,6 +29,18 @@ def test_clip_power_bit_exact_many_lengths():
     assert np.array_equal(got16.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("L", [1, 7, 8, 9, 100, 128, 129, 1000, 4097, 16000, 22050, 70001, 90000])
+def test_clip_power_bit_exact_equal_length_batches(L):
+    """Batches of one length take the table-replay path of the power kernel (90 000 samples exceed the table and
+    walk the tree); both must reproduce numpy's pairwise order bit for bit."""
+    import asr_b200 as A
+    clips16 = synth_clips(19, L, 16000, 12 + L)
+    ref = np.array([np.mean(c ** 2) for c in to_f32(clips16)], dtype=np.float32)
+    for clips in (clips16, to_f32(clips16)):
+        got = A.clip_power(A.ClipBatch.from_arrays(clips)).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
 def test_snr_sigma_device_matches_host_chain():
     import asr_b200 as A
     from oracle import noise_ref as nr
