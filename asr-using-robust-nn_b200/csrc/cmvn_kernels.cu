@@ -91,19 +91,34 @@ __global__ void cmvn_finalize_kernel(const double* __restrict__ acc2, const doub
   scale[c] = (v <= upper) ? 1.0 : __dsqrt_rn(v);
 }
 
-__global__ void __launch_bounds__(256) cmvn_apply_kernel(const void* __restrict__ x, const int dtype,
-                                                         const long long n_rows, const int n_cols, const long long ld,
-                                                         const double* __restrict__ mean,
-                                                         const double* __restrict__ scale, void* __restrict__ out,
-                                                         const int out_f64) {
-  const long long total = n_rows * n_cols;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / n_cols;
-    const int c = static_cast<int>(i - r * n_cols);
-    const double v = __ddiv_rn(__dsub_rn(load_x(x, dtype, r * ld + c), mean[c]), scale[c]);
-    if (out_f64) reinterpret_cast<double*>(out)[i] = v;
-    else reinterpret_cast<float*>(out)[i] = static_cast<float>(v);
+// out[r][c] = (x[r][c] - mean[c]) / scale[c] in float64 (sklearn: X -= mean_; X /= scale_), thread <-> column.
+__global__ void __launch_bounds__(kColTile * kRowLanes) cmvn_apply_kernel(
+    const void* __restrict__ x, const int dtype, const long long n_rows, const int n_cols, const long long ld,
+    const double* __restrict__ mean, const double* __restrict__ scale, void* __restrict__ out, const int out_f64,
+    const long long rows_per_slab) {
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * kColTile + lane;
+  if (c >= n_cols) return;
+  const long long r0 = blockIdx.y * rows_per_slab;
+  const long long r1 = min(n_rows, r0 + rows_per_slab);
+  const double m = mean[c], sc = scale[c];
+  long long r = r0 + rl;
+  for (; r + 3 * kRowLanes < r1; r += 4 * kRowLanes) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = load_x(x, dtype, (r + u * kRowLanes) * ld + c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double y = __ddiv_rn(__dsub_rn(v[u], m), sc);
+      const long long o = (r + u * kRowLanes) * n_cols + c;
+      if (out_f64) reinterpret_cast<double*>(out)[o] = y;
+      else reinterpret_cast<float*>(out)[o] = static_cast<float>(y);
+    }
+  }
+  for (; r < r1; r += kRowLanes) {
+    const double y = __ddiv_rn(__dsub_rn(load_x(x, dtype, r * ld + c), m), sc);
+    if (out_f64) reinterpret_cast<double*>(out)[r * n_cols + c] = y;
+    else reinterpret_cast<float*>(out)[r * n_cols + c] = static_cast<float>(y);
   }
 }
 
@@ -193,10 +208,12 @@ extern "C" int asr_cmvn_apply(const void* x_dev, int32_t dtype, int64_t n_rows, 
     return ASR_ERR_INVALID;
   }
   if (n_rows == 0) return ASR_OK;
-  const int64_t total = n_rows * n_cols;
-  const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
-  cmvn_apply_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x_dev, dtype, n_rows, n_cols, ld, mean_dev, scale_dev,
-                                                           out_dev, out_dtype == ASR_F64);
+  const int col_blocks = (n_cols + kColTile - 1) / kColTile;
+  int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((148 * 16 + col_blocks - 1) / col_blocks, (n_rows + 31) / 32));
+  const int64_t rows_per_slab = (n_rows + slabs - 1) / slabs;
+  slabs = (n_rows + rows_per_slab - 1) / rows_per_slab;
+  cmvn_apply_kernel<<<dim3(col_blocks, static_cast<unsigned>(slabs)), kColTile * kRowLanes, 0, as_stream(stream)>>>(
+      x_dev, dtype, n_rows, n_cols, ld, mean_dev, scale_dev, out_dev, out_dtype == ASR_F64, rows_per_slab);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }

@@ -78,34 +78,69 @@ struct PowTable {
   unsigned char merges[kPowMaxLeaves];
 };
 
-__device__ void pow_table_build(PowTable& tb, const int L, PowScratch& sc, const int lane) {
-  // lane 0 walks the tree; depth stack only (no values)
-  if (lane == 0) {
-    int sp = 0, vp = 0, n = 0;
-    bool ok = L > 0 && L <= 8 * 65535;
-    if (ok) { sc.s_off[0] = 0; sc.s_len[0] = L; sc.s_dep[0] = 0; sp = 1; }
-    while (sp > 0 && ok) {
-      --sp;
-      const int off = sc.s_off[sp], len = sc.s_len[sp], d = sc.s_dep[sp];
-      if (len > 128) {
-        int n2 = len / 2;
-        n2 -= n2 % 8;
-        sc.s_off[sp] = off + n2; sc.s_len[sp] = len - n2; sc.s_dep[sp] = d + 1;
-        sc.s_off[sp + 1] = off;  sc.s_len[sp + 1] = n2;  sc.s_dep[sp + 1] = d + 1;
-        sp += 2;
-      } else {
-        if (n >= kPowMaxLeaves) { ok = false; break; }
-        int k = 0, dd = d;
-        while (vp > 0 && sc.v_dep[vp - 1] == dd) { --vp; --dd; ++k; }
-        sc.v_dep[vp++] = dd;
-        tb.off8[n] = static_cast<unsigned short>(off >> 3);
-        tb.len[n] = static_cast<unsigned char>(len - 1);
-        tb.merges[n] = static_cast<unsigned char>(k);
-        ++n;
+// Built by one warp, level by level: every node longer than 128 splits the way numpy does, the order of the nodes is
+// kept (ballot + popcount give the output positions), until only leaves remain.  `buf` = 6 * kPowMaxLeaves ints.
+__device__ void pow_table_build(PowTable& tb, const int L, int* __restrict__ buf, const int lane) {
+  constexpr int cap = kPowMaxLeaves;
+  int* A = buf;             // [off | len | depth] x cap
+  int* B = buf + 3 * cap;
+  bool ok = L > 0 && L <= 8 * 65535;
+  int n = 1;
+  if (lane == 0) { A[0] = 0; A[cap] = L; A[2 * cap] = 0; }
+  __syncwarp();
+  bool any = ok && L > 128;
+  while (any) {
+    int out = 0;
+    bool more = false, overflow = false;
+    for (int c = 0; c < n; c += 32) {
+      const int i = c + lane;
+      const bool valid = i < n;
+      const int off = valid ? A[i] : 0, len = valid ? A[cap + i] : 0, d = valid ? A[2 * cap + i] : 0;
+      const bool split = len > 128;
+      const unsigned m = __ballot_sync(0xffffffffu, split);
+      const int pos = out + lane + __popc(m & ((1u << lane) - 1u));
+      if (valid) {
+        if (pos + 1 >= cap) {
+          overflow = true;
+        } else if (split) {
+          int n2 = len / 2;
+          n2 -= n2 % 8;
+          B[pos] = off;          B[cap + pos] = n2;           B[2 * cap + pos] = d + 1;
+          B[pos + 1] = off + n2; B[cap + pos + 1] = len - n2; B[2 * cap + pos + 1] = d + 1;
+          more = more || n2 > 128 || len - n2 > 128;
+        } else {
+          B[pos] = off; B[cap + pos] = len; B[2 * cap + pos] = d;
+        }
       }
+      out += min(32, n - c) + __popc(m);
     }
-    tb.n_leaves = ok ? n : 0;
-    tb.length = ok ? L : -1;
+    if (__any_sync(0xffffffffu, overflow)) { ok = false; break; }
+    any = __any_sync(0xffffffffu, more);
+    n = out;
+    int* t = A; A = B; B = t;
+    __syncwarp();
+  }
+  if (ok && n <= cap) {
+    for (int i = lane; i < n; i += 32) {
+      tb.off8[i] = static_cast<unsigned short>(A[i] >> 3);
+      tb.len[i] = static_cast<unsigned char>(A[cap + i] - 1);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      // merges after each leaf: the depths on the value stack are strictly increasing -> a bit mask is the stack
+      unsigned stack = 0;
+      for (int i = 0; i < n; ++i) {
+        int d = A[2 * cap + i], k = 0;
+        while (stack & (1u << d)) { stack &= ~(1u << d); --d; ++k; }
+        stack |= 1u << d;
+        tb.merges[i] = static_cast<unsigned char>(k);
+      }
+      tb.n_leaves = n;
+      tb.length = L;
+    }
+  } else if (lane == 0) {
+    tb.n_leaves = 0;
+    tb.length = -1;
   }
 }
 
@@ -224,27 +259,145 @@ __device__ void clip_power_replay(const void* __restrict__ audio, const long lon
   if (lane == 0) *out = static_cast<float>(static_cast<double>(sc.v_val[0]) / static_cast<double>(L));
 }
 
+// Vector variant of the table path for 16-byte aligned clips: a group of 8 lanes loads its leaf row by row with
+// 16-byte loads (lane j: rows j and j+8 of 8 samples), squares go through a per-warp shared-memory tile
+// ([row][8], pitch 12: conflict-free both ways), lane j then reads column j = numpy's accumulator r[j].
+// Rows past the end of a short leaf hold +0.0; adding it is exact, so the row loop needs no predicates.
+constexpr int kPowTileGroup = 200;        // floats per group tile (16 rows x pitch 12, + 8: groups 8 banks apart)
+
+template <int DT> struct PowRaw;
+template <> struct PowRaw<ASR_I16> { int4 a, b; };
+template <> struct PowRaw<ASR_F32> { float4 a0, a1, b0, b1; };
+
+template <int DT>
+__device__ __forceinline__ void pow_rows_load(const void* __restrict__ audio, const long long e, const bool va,
+                                              const bool vb, PowRaw<DT>& r) {
+  if constexpr (DT == ASR_I16) {
+    const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const short*>(audio) + e);
+    r.a = va ? __ldg(p) : make_int4(0, 0, 0, 0);
+    r.b = vb ? __ldg(p + 8) : make_int4(0, 0, 0, 0);
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(audio) + e);
+    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    r.a0 = va ? __ldg(p) : z; r.a1 = va ? __ldg(p + 1) : z;
+    r.b0 = vb ? __ldg(p + 16) : z; r.b1 = vb ? __ldg(p + 17) : z;
+  }
+}
+
+// squares of one row of 8 samples -> two float4
+template <int DT>
+__device__ __forceinline__ void pow_row_squares(const PowRaw<DT>& r, const int which, float4& lo, float4& hi) {
+  float v[8];
+  if constexpr (DT == ASR_I16) {
+    const int4 q = which ? r.b : r.a;
+    const unsigned w[4] = {static_cast<unsigned>(q.x), static_cast<unsigned>(q.y), static_cast<unsigned>(q.z),
+                           static_cast<unsigned>(q.w)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned x = w[k] ^ 0x80008000u;    // exact int16 -> float: bits(2^23 + (s + 32768)) - (2^23 + 32768)
+      const float s0 = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7410)) - 8421376.0f;
+      const float s1 = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7432)) - 8421376.0f;
+      // (s/32768)^2 rounded to float32 == round(s*s) * 2^-30 (scaling by a power of two commutes with rounding)
+      v[2 * k] = __fmul_rn(__fmul_rn(s0, s0), 9.313225746154785e-10f);
+      v[2 * k + 1] = __fmul_rn(__fmul_rn(s1, s1), 9.313225746154785e-10f);
+    }
+  } else {
+    const float4 x0 = which ? r.b0 : r.a0, x1 = which ? r.b1 : r.a1;
+    v[0] = __fmul_rn(x0.x, x0.x); v[1] = __fmul_rn(x0.y, x0.y); v[2] = __fmul_rn(x0.z, x0.z); v[3] = __fmul_rn(x0.w, x0.w);
+    v[4] = __fmul_rn(x1.x, x1.x); v[5] = __fmul_rn(x1.y, x1.y); v[6] = __fmul_rn(x1.z, x1.z); v[7] = __fmul_rn(x1.w, x1.w);
+  }
+  lo = make_float4(v[0], v[1], v[2], v[3]);
+  hi = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+template <int DT>
+__device__ void clip_power_replay_vec(const void* __restrict__ audio, const long long base, const int L,
+                                      const PowTable& tb, PowScratch& sc, float* __restrict__ tile, const int lane,
+                                      float* __restrict__ out) {
+  const int g = lane >> 3, j = lane & 7;
+  const int nl = tb.n_leaves;
+  float* tg = tile + g * kPowTileGroup;
+  PowRaw<DT> cur, nxt;
+  auto issue = [&](const int leaf, PowRaw<DT>& r) {
+    const bool have = leaf < nl;
+    const int off = have ? 8 * tb.off8[leaf] : 0, n = have ? tb.len[leaf] + 1 : 0;
+    const int rows = n >> 3;                       // full rows of 8
+    pow_rows_load<DT>(audio, base + off + 8 * j, j < rows, j + 8 < rows, r);
+  };
+  int vp = 0;
+  issue(g, cur);
+  for (int l0 = 0; l0 < nl; l0 += 4) {
+    issue(l0 + 4 + g, nxt);
+    {
+      float4 lo, hi;
+      pow_row_squares<DT>(cur, 0, lo, hi);
+      *reinterpret_cast<float4*>(tg + 12 * j) = lo;
+      *reinterpret_cast<float4*>(tg + 12 * j + 4) = hi;
+      pow_row_squares<DT>(cur, 1, lo, hi);
+      *reinterpret_cast<float4*>(tg + 12 * (j + 8)) = lo;
+      *reinterpret_cast<float4*>(tg + 12 * (j + 8) + 4) = hi;
+    }
+    __syncwarp();
+    float r = tg[j];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) r = __fadd_rn(r, tg[12 * i + j]);
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    {
+      const int leaf = l0 + g;
+      const int n = leaf < nl ? tb.len[leaf] + 1 : 0;
+      if ((n & 7) != 0 && j == 0) {                 // tail of the (last) leaf, serially like numpy; n < 8: the whole leaf
+        const int off = 8 * tb.off8[leaf];
+        if (n < 8) r = 0.0f;
+        for (int i = n & ~7; i < n; ++i) r = __fadd_rn(r, load_sq<DT>(audio, base + off + i));
+      }
+    }
+    const float r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 8);
+    const float r2 = __shfl_sync(0xffffffffu, r, 16), r3 = __shfl_sync(0xffffffffu, r, 24);
+    if (lane == 0) {
+      const float rs[4] = {r0, r1, r2, r3};
+      for (int q = 0; q < 4 && l0 + q < nl; ++q) {
+        float v = rs[q];
+        for (int k = tb.merges[l0 + q]; k > 0; --k) v = __fadd_rn(sc.v_val[--vp], v);   // left + right
+        sc.v_val[vp++] = v;
+      }
+    }
+    cur = nxt;
+    __syncwarp();                                   // the tile is rewritten next round
+  }
+  if (lane == 0) *out = static_cast<float>(static_cast<double>(sc.v_val[0]) / static_cast<double>(L));
+}
+
+// Persistent CTAs: the leaf table is built once per CTA, every warp then takes clips b0 + warp, b0 + 8 * gridDim.x ...
 template <int DT>
 __global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* __restrict__ audio,
                                                                      const long long* __restrict__ offsets,
                                                                      const int* __restrict__ lengths,
-                                                                     float* __restrict__ power, const int n_clips) {
+                                                                     float* __restrict__ power, const int n_clips,
+                                                                     const int aligned) {
   __shared__ PowScratch scratch[kPowWarps];
   __shared__ PowTable table;
+  __shared__ __align__(16) float tiles[kPowWarps][4 * kPowTileGroup];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b0 = blockIdx.x * kPowWarps;
-  if (warp == 0) pow_table_build(table, lengths[b0], scratch[0], lane);
+  static_assert(kPowWarps * 4 * kPowTileGroup >= 6 * kPowMaxLeaves, "the tiles double as the build buffer");
+  if (warp == 0) pow_table_build(table, lengths[min(n_clips - 1, blockIdx.x * kPowWarps)], reinterpret_cast<int*>(&tiles[0][0]), lane);
   __syncthreads();
-  const int b = b0 + warp;
-  if (b >= n_clips) return;
-  const int L = lengths[b];
-  const long long base = offsets[b];
-  if (L <= 0) {                                   // np.mean of an empty array is nan
-    if (lane == 0) power[b] = __int_as_float(0x7fc00000);
-    return;
+  for (int b = blockIdx.x * kPowWarps + warp; b < n_clips; b += gridDim.x * kPowWarps) {
+    const int L = lengths[b];
+    const long long base = offsets[b];
+    if (L <= 0) {                                 // np.mean of an empty array is nan
+      if (lane == 0) power[b] = __int_as_float(0x7fc00000);
+      continue;
+    }
+    if (table.n_leaves > 0 && table.length == L) {
+      if (aligned && (base & 7) == 0) clip_power_replay_vec<DT>(audio, base, L, table, scratch[warp], tiles[warp], lane, power + b);
+      else clip_power_replay<DT>(audio, base, L, table, scratch[warp], lane, power + b);
+    } else {
+      clip_power_walk<DT>(audio, base, L, scratch[warp], lane, power + b);
+    }
+    __syncwarp();
   }
-  if (table.n_leaves > 0 && table.length == L) clip_power_replay<DT>(audio, base, L, table, scratch[warp], lane, power + b);
-  else clip_power_walk<DT>(audio, base, L, scratch[warp], lane, power + b);
 }
 
 __global__ void snr_sigma_kernel(const float* __restrict__ power, const float snr_db, double* __restrict__ sigma,
@@ -366,12 +519,13 @@ extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_
     return ASR_ERR_INVALID;
   }
   if (n_clips == 0) return ASR_OK;
-  const int blocks = (n_clips + kPowWarps - 1) / kPowWarps;
+  const int blocks = std::min((n_clips + kPowWarps - 1) / kPowWarps, 148 * 4);
   const long long* off = reinterpret_cast<const long long*>(offsets_dev);
+  const int aligned = (reinterpret_cast<uintptr_t>(audio_dev) & 15) == 0 ? 1 : 0;
   if (dtype == ASR_I16)
-    clip_power_kernel<ASR_I16><<<blocks, kPowWarps * 32, 0, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips);
+    clip_power_kernel<ASR_I16><<<blocks, kPowWarps * 32, 0, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
   else
-    clip_power_kernel<ASR_F32><<<blocks, kPowWarps * 32, 0, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips);
+    clip_power_kernel<ASR_F32><<<blocks, kPowWarps * 32, 0, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }
