@@ -2,6 +2,7 @@
 // the fused-MFCC launch and the host-buffer pipeline.  See include/asr_b200.h for the contract.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include "common.cuh"
@@ -644,6 +645,7 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.lm_pitch = plan->fr_lm_pitch;
     fp.cep_blob_f4 = plan->cep_blob_f4; fp.cep_tab_f4 = plan->cep_tab_f4;
     fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
+    { const char* dbg = std::getenv("ASR_B200_DBG_SKIP"); fp.dbg_skip = dbg ? std::atoi(dbg) : 0; }
     ASR_CUDA_TRY(launch_frames_path(fp, plan->sm_count, flo.smem_bytes, plan->cep_smem_bytes,
                                     std::max(1, asr_plan_num_frames(plan, max_length)), as_stream(stream)));
     return ASR_OK;

@@ -116,6 +116,7 @@ struct FParams {
   int* nframes;       // [n_clips]
   // ---- cepstra kernel tables: float4 offset inside the blob, size, shared-memory offsets (floats) ----
   int cep_blob_f4, cep_tab_f4, cep_off_cbuf, cep_off_taps;
+  int dbg_skip;       // timing experiments only (ASR_B200_DBG_SKIP): bit 0 stage, 1 combine, 2 mel, 3 fft are skipped
 };
 
 cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_bytes, int cep_smem_bytes, int max_frames,

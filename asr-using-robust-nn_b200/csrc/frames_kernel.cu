@@ -216,7 +216,8 @@ struct FRun {
   int p0;           // padded position of the first staged sample (t0 * hop)
   int count;        // staged samples: (n - 1) * hop + 512
   int aud0;         // staged position of padded sample p0
-  int unit0;        // first linear unit index of the run when it is staged by 4-sample units, else -1
+  int unit0;        // first linear unit index of the run (runs staged by 4-sample units; the others hold 0 units)
+  int nu;           // units of the run: count / 4, or 0 when the run is staged sample by sample
 };
 struct FBlock {
   int n_runs, n_slots, fin, n_units;
@@ -242,7 +243,7 @@ __device__ __forceinline__ void stage_block(const FParams& fp, const FBlock& blk
     const FRun& run = blk.run[r];
     const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
     float* dst = aud + run.aud0;
-    if (run.unit0 < 0) {      // odd alignment or pre-emphasis: sample by sample
+    if (run.nu == 0) {        // odd alignment or pre-emphasis: sample by sample
       for (int i = ptid; i < run.count; i += n_threads) dst[i] = padded_at<DT>(fp, run.base, run.L, run.p0 + i, sig) * scale;
       continue;
     }
@@ -281,6 +282,110 @@ __device__ __forceinline__ void stage_block(const FParams& fp, const FBlock& blk
         }
       }
     }
+  }
+}
+
+// Split form of stage_block for the steady state: the loads of a thread's first kStageBatch units are issued
+// before the combine and mel phases and consumed after them, so their latency is covered by the warp's own work.
+template <int DT>
+struct StagePf {
+  UnitRaw<DT> raw[kStageBatch];
+  UnitZ zz[kStageBatch];
+  int dst[kStageBatch];       // staged position of the unit, -1: no such unit
+  int orig[kStageBatch];      // original sample index of the unit's first sample
+  int run[kStageBatch];
+  unsigned inside;
+};
+
+template <int DT>
+__device__ __forceinline__ void stage_issue(const FParams& fp, const FBlock& blk, const int tid, StagePf<DT>& pf) {
+  pf.inside = 0;
+#pragma unroll
+  for (int k = 0; k < kStageBatch; ++k) {
+    const int u = tid + k * kFrThreads;
+    pf.dst[k] = -1;
+    if (u < blk.n_units) {
+      int r = 0;
+      while (r + 1 < blk.n_runs && u >= blk.run[r + 1].unit0) ++r;
+      const FRun& run = blk.run[r];
+      const int local = u - run.unit0;
+      if (local < run.nu) {
+        const int orig = run.p0 - fp.pad + 4 * local;
+        pf.dst[k] = run.aud0 + 4 * local;
+        pf.orig[k] = orig;
+        pf.run[k] = r;
+        if (orig >= 0 && orig + 4 <= run.L) {
+          const long long e = run.base + orig;
+          unit_load<DT>(fp, e, pf.raw[k]);
+          if (fp.noise_mode != ASR_NOISE_NONE) unit_load_z(fp.z, e, pf.zz[k]);
+          pf.inside |= 1u << k;
+        }
+      }
+    }
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ void stage_unit_direct(const FParams& fp, const FRun& run, float* __restrict__ aud, const int local) {
+  const float scale = (DT == ASR_I16 && fp.noise_mode == ASR_NOISE_NONE) ? 32768.0f : 1.0f;
+  const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
+  const int orig = run.p0 - fp.pad + 4 * local;
+  float4 v;
+  if (orig >= 0 && orig + 4 <= run.L) {
+    const long long e = run.base + orig;
+    UnitRaw<DT> raw;
+    UnitZ zz, gg;
+    unit_load<DT>(fp, e, raw);
+    if (fp.noise_mode != ASR_NOISE_NONE) unit_load_z(fp.z, e, zz);
+    if (fp.noise_mode == ASR_NOISE_MIXTURE) unit_load_z(fp.z2, e, gg);
+    v = unit_convert<DT>(fp, raw, zz, gg, sig);
+  } else {
+    const int p = orig + fp.pad;
+    v.x = padded_at<DT>(fp, run.base, run.L, p, sig) * scale;
+    v.y = padded_at<DT>(fp, run.base, run.L, p + 1, sig) * scale;
+    v.z = padded_at<DT>(fp, run.base, run.L, p + 2, sig) * scale;
+    v.w = padded_at<DT>(fp, run.base, run.L, p + 3, sig) * scale;
+  }
+  *reinterpret_cast<float4*>(aud + run.aud0 + 4 * local) = v;
+}
+
+template <int DT>
+__device__ __forceinline__ void stage_finish(const FParams& fp, const FBlock& blk, float* __restrict__ aud, const int tid,
+                                             const StagePf<DT>& pf) {
+  // clean int16 is staged UNSCALED (the window table carries the exact 2^-15); scaling by 2^15 is exact
+  const float scale = (DT == ASR_I16 && fp.noise_mode == ASR_NOISE_NONE) ? 32768.0f : 1.0f;
+#pragma unroll
+  for (int k = 0; k < kStageBatch; ++k) {
+    if (pf.dst[k] >= 0) {
+      const FRun& run = blk.run[pf.run[k]];
+      const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
+      float4 v;
+      if ((pf.inside >> k) & 1u) {
+        UnitZ gg = pf.zz[k];
+        if (fp.noise_mode == ASR_NOISE_MIXTURE) unit_load_z(fp.z2, run.base + pf.orig[k], gg);   // carrier stream (rare path)
+        v = unit_convert<DT>(fp, pf.raw[k], pf.zz[k], gg, sig);
+      } else {
+        const int p = pf.orig[k] + fp.pad;
+        v.x = padded_at<DT>(fp, run.base, run.L, p, sig) * scale;
+        v.y = padded_at<DT>(fp, run.base, run.L, p + 1, sig) * scale;
+        v.z = padded_at<DT>(fp, run.base, run.L, p + 2, sig) * scale;
+        v.w = padded_at<DT>(fp, run.base, run.L, p + 3, sig) * scale;
+      }
+      *reinterpret_cast<float4*>(aud + pf.dst[k]) = v;
+    }
+  }
+  // units past the prefetched ones (large hops), then runs staged sample by sample
+  for (int u = tid + kStageBatch * kFrThreads; u < blk.n_units; u += kFrThreads) {
+    int r = 0;
+    while (r + 1 < blk.n_runs && u >= blk.run[r + 1].unit0) ++r;
+    if (u - blk.run[r].unit0 < blk.run[r].nu) stage_unit_direct<DT>(fp, blk.run[r], aud, u - blk.run[r].unit0);
+  }
+  for (int r = 0; r < blk.n_runs; ++r) {
+    const FRun& run = blk.run[r];
+    if (run.nu != 0) continue;
+    const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
+    for (int i = tid; i < run.count; i += kFrThreads)
+      aud[run.aud0 + i] = padded_at<DT>(fp, run.base, run.L, run.p0 + i, sig) * scale;
   }
 }
 
@@ -363,8 +468,9 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
         run.count = (n - 1) * fp.hop + 512;
         const long long e0 = run.base + static_cast<long long>(run.p0) - fp.pad;
         const bool vec = fp.vec_ok && (e0 & 3) == 0;
-        run.unit0 = vec ? n_units : -1;
-        if (vec) n_units += run.count >> 2;
+        run.unit0 = n_units;
+        run.nu = vec ? run.count >> 2 : 0;
+        n_units += run.nu;
         run.aud0 = (aud + 3) & ~3;
         aud = run.aud0 + run.count;
         // slot tables of this run are filled by the lanes of the warp afterwards: stash what they need
@@ -469,12 +575,14 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
       __syncwarp();
       fill_slots(*nb);
     }
-    // ---- stage (block it+1): samples -> shared memory, once per sample ----
-    if (b_stage->n_slots > 0) stage_block<DT>(fp, *b_stage, s_aud + (par ^ 1) * fp.aud_cap, tid, kFrThreads);
+    // ---- stage (block it+1), part 1: issue the loads of this thread's samples (consumed after the mel phase) ----
+    StagePf<DT> pf;
+    const bool do_stage = b_stage->n_slots > 0 && !(fp.dbg_skip & 1);
+    if (do_stage) stage_issue<DT>(fp, *b_stage, tid, pf);
 
     // ---- combine (block it-2): lanes <-> filters; warp w takes slots w and w+16.
     //      filter j = rising slope over segment j + falling slope over segment j+1 ----
-    if (n_comb > 0) {
+    if (n_comb > 0 && !(fp.dbg_skip & 2)) {
       const float* part = s_part + par * part_buf;
 #pragma unroll
       for (int h = 0; h < 2; ++h)
@@ -482,7 +590,7 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
     }
 
     // ---- mel (block it-1): lanes <-> frames, this warp's segments ----
-    if (n_mel > 0) {
+    if (n_mel > 0 && !(fp.dbg_skip & 4)) {
       const float* S = s_S + (par ^ 1) * s_buf + lane * fp.s_pitch;      // S buffer of block it-1
       float* part = s_part + (par ^ 1) * part_buf + lane;
 #pragma unroll 1
@@ -508,8 +616,11 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
       }
     }
 
+    // ---- stage (block it+1), part 2: convert (noise mix in float64), store to shared memory, once per sample ----
+    if (do_stage) stage_finish<DT>(fp, *b_stage, s_aud + (par ^ 1) * fp.aud_cap, tid, pf);
+
     // ---- fft (block it) ----
-    if (n_fft > 0) {
+    if (n_fft > 0 && !(fp.dbg_skip & 8)) {
       const float* xs = s_aud + par * fp.aud_cap + b_fft->slot_aud[fft_slot];
       float re[16], im[16];
       fft512_load(xs, s_win2, fft_l, re, im);

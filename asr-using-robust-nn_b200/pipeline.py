@@ -37,9 +37,9 @@ class _StepGraphs:
 
 class NoisyFeaturePipeline:
     def __init__(self, params: MfccParams, out_frames: int, device=None, distributed: bool = False, group=None,
-                 world_size: int = 1, use_graphs: bool = True):
+                 world_size: int = 1, use_graphs: bool = True, path: str = "auto"):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.plan = MfccPlan(params, self.device.index)
+        self.plan = MfccPlan(params, self.device.index, path=path)
         self.out_frames = int(out_frames)
         self.rows = self.plan.feature_rows
         self.D = self.rows * self.out_frames

@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU per step")
+    ap.add_argument("--path", default="auto", choices=["auto", "clip", "frames"], help="kernel path of the MFCC launch (asr_path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -234,7 +235,7 @@ def main():
 
     params = A.PRESETS[preset]
     T = params.num_frames(L)
-    pipe = NoisyFeaturePipeline(params, T, device=dev, distributed=world > 1, world_size=world)
+    pipe = NoisyFeaturePipeline(params, T, device=dev, distributed=world > 1, world_size=world, path=args.path)
     D = pipe.D
 
     # synthetic inputs: 256 distinct seeded clips tiled to the batch, rolled per row so no two rows are equal
