@@ -73,6 +73,9 @@ SIGNATURES = {
     "asr_cmvn_colsum_centered": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp]),
     "asr_cmvn_finalize": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "asr_cmvn_apply": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "asr_resample_out_len": (_i64, [_i64, _i32, _i32]),
+    "asr_resample_design": (C.c_int, [_i32, _i32, _f64, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "asr_resample_batch": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "asr_mfcc_batch_host": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _f32, _u64, _vp, _i32, _i32, _vp]),
 }
 

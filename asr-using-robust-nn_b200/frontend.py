@@ -344,6 +344,47 @@ def randn(seed: int, first_index: int, n: int, device="cuda", out: Optional[torc
     return out
 
 
+# ---- audio ingest: resampling on the device ---------------------------------------------------------------
+class Resampler:
+    """``scipy.signal.resample_poly(x, up, down)`` for a packed batch on the device (the resampling step of
+    ``librosa.load``; see ``asr_resample_design`` in include/asr_b200.h for what is restated)."""
+
+    def __init__(self, orig_sr: int, target_sr: int, kaiser_beta: float = 5.0, device="cuda"):
+        _require_cuda()
+        u, d, n, pre = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib.asr_resample_design(int(target_sr), int(orig_sr), float(kaiser_beta), None, 0, C.byref(u), C.byref(d),
+                                      C.byref(n), C.byref(pre)), "asr_resample_design")
+        self.up, self.down, self.n_taps, self.n_pre_remove = u.value, d.value, n.value, pre.value
+        self.taps_host = np.zeros(max(self.n_taps, 1), dtype=np.float32)
+        if self.n_taps:
+            check(lib.asr_resample_design(int(target_sr), int(orig_sr), float(kaiser_beta), self.taps_host.ctypes.data,
+                                          self.n_taps, C.byref(u), C.byref(d), C.byref(n), C.byref(pre)), "asr_resample_design")
+        self.taps = torch.from_numpy(self.taps_host).to(device)
+
+    def out_length(self, n_in: int) -> int:
+        return int(lib.asr_resample_out_len(int(n_in), self.up, self.down))
+
+    def __call__(self, batch: ClipBatch) -> ClipBatch:
+        """int16 / float32 clips -> float32 clips at the target rate (a new packed batch, same clip order)."""
+        if batch.audio.dtype not in (torch.int16, torch.float32):
+            raise TypeError("resampling takes int16 or float32 audio")
+        dev = batch.audio.device
+        if self.up == 1 and self.down == 1:
+            audio = batch.audio if batch.audio.dtype == torch.float32 else batch.audio.to(torch.float32) / 32768.0
+            return batch.like(audio)
+        out_len = np.array([self.out_length(n) for n in batch.lengths_host], dtype=np.int32)
+        offsets, total = ClipBatch.layout(out_len)
+        out = torch.zeros(total, dtype=torch.float32, device=dev)
+        off_d = torch.from_numpy(offsets).to(dev)
+        len_d = torch.from_numpy(out_len).to(dev)
+        with torch.cuda.device(dev):
+            check(lib.asr_resample_batch(batch.audio.data_ptr(), batch.dtype_code, batch.offsets.data_ptr(),
+                                         batch.lengths.data_ptr(), batch.n_clips, batch.max_length, self.up, self.down,
+                                         self.taps.data_ptr(), self.n_taps, self.n_pre_remove, out.data_ptr(),
+                                         off_d.data_ptr(), _stream()), "asr_resample_batch")
+        return ClipBatch(out, off_d, len_d, int(out_len.max()) if len(out_len) else 0, offsets, out_len)
+
+
 # ---- standardisation ---------------------------------------------------------------------------------
 class Standardizer:
     """``StandardScaler().fit_transform`` over row blocks that may live on several GPUs.

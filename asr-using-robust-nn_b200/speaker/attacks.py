@@ -26,7 +26,7 @@ def _window_sigma(sigma_file: np.ndarray, fid: np.ndarray, device) -> torch.Tens
 
 
 def black_box_attack_on_waveforms_dataset(waves, labels, sigma=0, p=0, alpha=0, params=None):
-    batch = ClipBatch.from_arrays([_as_audio(w) for w in waves])
+    batch = waves if isinstance(waves, ClipBatch) else ClipBatch.from_arrays([_as_audio(w) for w in waves])
     prm = efcd.PARAMS if params is None else params
     _, fid = efcd.windows_of(batch, prm.sr)
     noise = None
@@ -41,7 +41,7 @@ def black_box_attack_on_waveforms_dataset(waves, labels, sigma=0, p=0, alpha=0, 
 
 
 def black_box_attack_on_waveforms_snr(waves, labels, target_snr_db, params=None):
-    batch = ClipBatch.from_arrays([_as_audio(w) for w in waves])
+    batch = waves if isinstance(waves, ClipBatch) else ClipBatch.from_arrays([_as_audio(w) for w in waves])
     prm = efcd.PARAMS if params is None else params
     sigma_file = snr_sigma_host(clip_power(batch).cpu().numpy(), target_snr_db)
     (z,) = _draw_like(batch)
@@ -51,7 +51,8 @@ def black_box_attack_on_waveforms_snr(waves, labels, target_snr_db, params=None)
 
 
 def _load_all(filenames):
-    return [audio_io.load(f, sr=efcd.PARAMS.sr, mono=True)[0] for f in filenames]
+    """Decode on the host, resample on the device: one packed batch for the whole file list."""
+    return audio_io.load_batch(list(filenames), sr=efcd.PARAMS.sr)
 
 
 def black_box_attack_on_audio_dataset(filenames, labels, sigma=0, p=0, alpha=0):

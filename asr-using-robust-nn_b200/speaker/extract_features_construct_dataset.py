@@ -80,15 +80,15 @@ def mfcc_windows(batch: ClipBatch, noise=None, params: MfccParams = None):
 
 
 def load_waveforms_and_labels(waves, labels, params: MfccParams = None):
-    """``load_audio_dataset_and_labels`` on decoded waveforms."""
-    batch = ClipBatch.from_arrays([np.ascontiguousarray(w) for w in waves])
+    """``load_audio_dataset_and_labels`` on decoded waveforms (a list of arrays, or a packed ``ClipBatch``)."""
+    batch = waves if isinstance(waves, ClipBatch) else ClipBatch.from_arrays([np.ascontiguousarray(w) for w in waves])
     mfcc, fid = mfcc_windows(batch, None, params)
     return mfcc, np.asarray(labels)[fid]
 
 
 def load_audio_dataset_and_labels(filenames, labels):
-    waves = [audio_io.load(f, sr=PARAMS.sr, mono=True)[0] for f in filenames]
-    return load_waveforms_and_labels(waves, labels)
+    # decode on the host, upload the PCM once, resample to 22 050 Hz on the device; windows are index ranges
+    return load_waveforms_and_labels(audio_io.load_batch(list(filenames), sr=PARAMS.sr), labels)
 
 
 def extract_features(file_path, utterance_length):

@@ -139,7 +139,7 @@ def _draw_like(batch, n_streams=1):
 
 
 def black_box_attack_on_waveforms(waves, sigma=0, p=0, alpha=0, utterance_length=UTTERANCE_LENGTH, params=None):
-    batch = ClipBatch.from_arrays([_as_audio(w) for w in waves])
+    batch = waves if isinstance(waves, ClipBatch) else ClipBatch.from_arrays([_as_audio(w) for w in waves])
     noise = None
     if sigma != 0:
         (z,) = _draw_like(batch)
@@ -152,7 +152,7 @@ def black_box_attack_on_waveforms(waves, sigma=0, p=0, alpha=0, utterance_length
 
 
 def black_box_attack_on_waveforms_snr(waves, target_snr_db, utterance_length=UTTERANCE_LENGTH, params=None):
-    batch = ClipBatch.from_arrays([_as_audio(w) for w in waves])
+    batch = waves if isinstance(waves, ClipBatch) else ClipBatch.from_arrays([_as_audio(w) for w in waves])
     sigma = snr_sigma_host(clip_power(batch).cpu().numpy(), target_snr_db)
     (z,) = _draw_like(batch)
     return _features(batch, Noise.white(z, torch.from_numpy(sigma).to(z.device)), utterance_length, params)
@@ -160,7 +160,8 @@ def black_box_attack_on_waveforms_snr(waves, target_snr_db, utterance_length=UTT
 
 # ---- reference-named, path-based entry points ---------------------------------------------------------------
 def _load_all(filenames):
-    return [audio_io.load(f, sr=efcd.PARAMS.sr, mono=True)[0] for f in filenames]
+    """Decode on the host, resample on the device: one packed batch for the whole file list."""
+    return audio_io.load_batch(list(filenames), sr=efcd.PARAMS.sr)
 
 
 def black_box_attack_on_audio(file_path, utterance_length, sigma=0, p=0, alpha=0):

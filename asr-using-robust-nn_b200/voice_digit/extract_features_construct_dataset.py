@@ -39,11 +39,11 @@ def get_plan(params: MfccParams = None) -> MfccPlan:
 
 
 def extract_features_waveforms(waves, utterance_length, params: MfccParams = None, out_dtype=torch.float32):
-    """MFCC of a list of decoded waveforms -> CUDA tensor (N, n_mfcc, utterance_length), frames
-    truncated / zero-padded in the feature domain exactly like reference :33-37."""
+    """MFCC of a list of decoded waveforms (or of a packed ``ClipBatch`` already on the device) -> CUDA tensor
+    (N, n_mfcc, utterance_length), frames truncated / zero-padded in the feature domain exactly like reference :33-37."""
     global maxim
     plan = get_plan(params)
-    batch = ClipBatch.from_arrays(waves)
+    batch = waves if isinstance(waves, ClipBatch) else ClipBatch.from_arrays(waves)
     maxim = max(maxim, plan.num_frames(batch.max_length))
     out, status = plan.mfcc(batch, out_frames=utterance_length, out_dtype=out_dtype)
     bad = torch.nonzero(status).flatten()
@@ -68,8 +68,8 @@ def compute_mfcc_all_waveforms(waves, utterance_length=None, params: MfccParams 
 
 
 def compute_mfcc_all_files(filenames):
-    waves = [audio_io.load(f, sr=PARAMS.sr, mono=True)[0] for f in filenames]
-    return compute_mfcc_all_waveforms(waves)
+    # decode on the host, upload the PCM once, resample to 22 050 Hz and extract on the device
+    return compute_mfcc_all_waveforms(audio_io.load_batch(list(filenames), sr=PARAMS.sr))
 
 
 def get_file_names_and_labels(data_dir):

@@ -218,6 +218,23 @@ int asr_cmvn_finalize(const double* acc2_dev, const double* mean_dev, int64_t n_
 int asr_cmvn_apply(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld,
                    const double* mean_dev, const double* scale_dev, void* out_dev, int32_t out_dtype, void* stream);
 
+/* ---- audio ingest: the resampling step of librosa.load (VDR/extract...py:27, SR/extract...py:210) ----
+ * librosa resamples every file to 22 050 Hz with resampy's `kaiser_best` table, which is not available; the
+ * stand-in is scipy.signal.resample_poly semantics: Kaiser(beta)-windowed sinc of
+ * 20*max(up,down)+1 taps, unit DC gain, float32 taps scaled by up, zero-padded in front so that output sample 0
+ * aligns with input sample 0; out[m] = sum_k taps[k] * x_up[(m + n_pre_remove)*down - k]. */
+int64_t asr_resample_out_len(int64_t n_in, int32_t up, int32_t down);   /* ceil(n_in*up/down) after reducing up/down */
+/* Host-side filter design.  taps_host == NULL: only the sizes are returned.  up/down come back reduced by their gcd. */
+int asr_resample_design(int32_t up, int32_t down, double kaiser_beta /* scipy default 5.0 */, float* taps_host,
+                        int32_t capacity, int32_t* up_out, int32_t* down_out, int32_t* n_taps_out,
+                        int32_t* n_pre_remove_out);
+/* Batched resampling on the device: clip b = in[in_offsets[b] .. +in_lengths[b]) (ASR_I16: value/32768, or ASR_F32)
+ * -> out[out_offsets[b] .. + asr_resample_out_len(in_lengths[b], up, down)) float32.  up/down as returned by the design. */
+int asr_resample_batch(const void* in_dev, int32_t dtype, const int64_t* in_offsets_dev, const int32_t* in_lengths_dev,
+                       int32_t n_clips, int32_t max_in_length, int32_t up, int32_t down, const float* taps_dev,
+                       int32_t n_taps, int32_t n_pre_remove, float* out_dev, const int64_t* out_offsets_dev,
+                       void* stream);
+
 /* ---- host-buffer entry points (what a ctypes binding on the reference side calls) ----------
  * Synchronous; host<->device copies are pipelined in chunks over two streams inside. */
 

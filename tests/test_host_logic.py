@@ -131,3 +131,53 @@ def test_first_sample_index_matches_the_packed_layout():
             lo, hi = sharding.shard_bounds(len(lengths), r, world)
             want = int(off[lo]) if lo < len(lengths) else int(off[-1] + (lengths[-1] + 7) // 8 * 8)
             assert sharding.first_sample_index(lengths, r, world) == want
+
+
+@pytest.mark.parametrize("orig,target", [(16000, 22050), (44100, 22050), (8000, 22050), (48000, 22050), (22050, 16000)])
+def test_resample_filter_design_is_scipy_firwin(orig, target):
+    """asr_resample_design (host code of the library, no GPU) == the taps scipy.signal.resample_poly builds for float32."""
+    import ctypes as C
+    from math import gcd
+    import scipy.signal
+    from asr_b200._lib import lib
+    u, d, n, pre = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    assert lib.asr_resample_design(target, orig, 5.0, None, 0, C.byref(u), C.byref(d), C.byref(n), C.byref(pre)) == 0
+    g = gcd(orig, target)
+    assert (u.value, d.value) == (target // g, orig // g)
+    taps = np.zeros(n.value, np.float32)
+    assert lib.asr_resample_design(target, orig, 5.0, taps.ctypes.data, n.value, C.byref(u), C.byref(d), C.byref(n), C.byref(pre)) == 0
+    mr = max(u.value, d.value)
+    half = 10 * mr
+    h = scipy.signal.firwin(2 * half + 1, 1.0 / mr, window=("kaiser", 5.0)).astype(np.float32)
+    h *= u.value
+    n_pre_pad = d.value - half % d.value
+    ref = np.concatenate([np.zeros(n_pre_pad, np.float32), h])
+    assert n.value == len(ref) and pre.value == (half + n_pre_pad) // d.value
+    np.testing.assert_allclose(taps, ref, rtol=2e-7, atol=1e-12)
+    for n_in in (1, 2, 159, 160, 16000, 22051):
+        assert lib.asr_resample_out_len(n_in, target, orig) == len(scipy.signal.resample_poly(np.zeros(n_in, np.float32), u.value, d.value))
+
+
+def test_processed_dataset_files_round_trip(tmp_path):
+    """The six .npy files the reference's training / attack scripts load: names, dtypes, C-order float64 rows."""
+    from asr_b200 import dataset_io
+    rng = np.random.default_rng(3)
+    files = np.array([f"data\\\\seven\\\\f{i}.wav" for i in range(23)])
+    labels = np.arange(23, dtype=np.int32) % 10
+    (f_tr, f_dev, f_te), (l_tr, l_dev, l_te) = dataset_io.split_70_20_10(files, labels)
+    assert (len(f_tr), len(f_dev), len(f_te)) == (16, 4, 2)            # int(23*0.7), int(23*0.9)-16, int(23*0.1)
+    assert list(f_te) == list(files[-2:]) and list(l_te) == list(labels[-2:])
+    data = [rng.standard_normal((len(f), 880)).astype(np.float32) for f in (f_tr, f_dev, f_te)]
+    d = str(tmp_path / "processed_google_dataset")
+    dataset_io.save_processed_dataset(d, data, (l_tr, l_dev, l_te), str(tmp_path / "test_dataset_to_add_noise"), f_te)
+    got = dataset_io.load_npy_dataset(d + os.sep)
+    for name, x, y, gx, gy in zip(("train", "dev", "test"), data, (l_tr, l_dev, l_te), got[0::2], got[1::2]):
+        assert gx.dtype == np.float64 and gx.flags["C_CONTIGUOUS"] and gx.shape == x.shape
+        assert np.array_equal(gx, x.astype(np.float64)) and np.array_equal(gy, y)
+        raw = open(os.path.join(d, f"{name}_data.npy"), "rb").read()
+        assert len(raw) == 128 + 8 * x.size                              # 128-byte header + float64 payload (LFS pointer size rule)
+    assert np.array_equal(np.load(str(tmp_path / "test_dataset_to_add_noise" / "test_filenames.npy")), f_te)
+    # shard merge by index == single-process row order
+    full = rng.standard_normal((10, 7))
+    parts = [full[slice(*sharding.shard_bounds(10, r, 3))] for r in range(3)]
+    assert np.array_equal(dataset_io.merge_shards(parts), full)
