@@ -146,6 +146,22 @@ class NoisyFeaturePipeline:
             cap(lambda: (g1(), g2(), g3()))
         return sg
 
+    def run_corpus(self, batches, n_local: int, out_dtype=torch.float32):
+        """BASELINE configs[3]: this rank's shard of a corpus arrives batch by batch (``batches`` yields
+        ``(ClipBatch, z or None, snr_db or None)``); the features of all batches stay resident in one ``(n_local, D)``
+        matrix (1 M C1 clips = 5.3 GB), the column statistics are all-reduced ONCE for the whole corpus
+        (``n_total`` = sum of ``n_local`` over the ranks), then every row is standardised."""
+        feats = torch.empty((n_local, self.rows, self.out_frames), dtype=torch.float32, device=self.device)
+        done = 0
+        for batch, z, snr_db in batches:
+            self._group1(batch, z, snr_db, feats[done:done + batch.n_clips])
+            done += batch.n_clips
+        if done != n_local:
+            raise ValueError(f"the batches held {done} clips, expected {n_local}")
+        flat = feats.view(n_local, self.D)
+        self.std.fit([flat], n_total=None if self.distributed else n_local)
+        return self.std.transform(flat, out_dtype=out_dtype)
+
     def run_host(self, audio_host: torch.Tensor, snr_db: Optional[float], seed: int, out_host: torch.Tensor,
                  first_index: int = 0) -> torch.Tensor:
         """End to end from PINNED host memory: (B, L) int16/float32 host tensor in, standardised

@@ -59,3 +59,17 @@ def test_host_pipeline_slots_do_not_race():
         z = A.randn(99, 1000 * i, B * L) if snrs[i] is not None else None
         want = eager.run_device(A.ClipBatch.from_matrix(dev), z, snrs[i]).cpu()
         assert torch.equal(outs[i], want), i
+
+
+def test_corpus_in_batches_equals_one_shot():
+    """configs[3] shape: the corpus arrives in batches, statistics are taken once over all rows."""
+    import asr_b200 as A
+    from asr_b200.pipeline import NoisyFeaturePipeline
+    B, L = 40, 16000
+    clips = synth_clips(B, L, 16000, 700)
+    audio = torch.from_numpy(np.stack(clips)).cuda()
+    pipe = NoisyFeaturePipeline(A.C1, 101, use_graphs=False)
+    one = pipe.run_device(A.ClipBatch.from_matrix(audio), None, None).clone()
+    parts = [(A.ClipBatch.from_matrix(audio[i:i + 16].contiguous()), None, None) for i in range(0, B, 16)]
+    many = pipe.run_corpus(iter(parts), B)
+    assert torch.equal(one, many)
