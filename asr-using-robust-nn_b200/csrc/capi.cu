@@ -504,20 +504,39 @@ extern "C" int asr_plan_get_tables(const asr_plan* plan, float* window, float* m
 
 // ---- block-pipelined path: shared-memory layout, workspace layout, launch ----
 namespace {
-struct FrLayout { int sm_aud, sm_S, sm_xb, sm_part, aud_cap, max_runs, smem_bytes; };
-bool frames_layout(const asr_plan* plan, FrLayout* lo) {
-  const int hop = plan->prm.hop_length;
-  for (int runs = kFrMaxRuns; runs >= 1; --runs) {
-    int off = 4 * plan->fr_blob_f4;
-    lo->aud_cap = round4(kFrBlock * hop + runs * (512 - std::min(hop, 512)) + 4 * runs + 8);
-    lo->sm_aud = off; off += 2 * lo->aud_cap;
-    lo->sm_S = off; off += 2 * kFrBlock * plan->fr_s_pitch;
-    off = round4(off);
-    lo->sm_xb = off; off += kFrWarps * 2 * plan->fr_xb_stride;
-    lo->sm_part = off; off += 2 * plan->fr_n_refs * 33;
-    lo->max_runs = runs;
-    lo->smem_bytes = 4 * off;
-    if (lo->smem_bytes + 6144 <= kMaxSmemBytes) return true;     // + static shared memory (descriptor ring)
+struct FrLayout { int sm_aud, sm_S, sm_xb, sm_part, sm_raw, aud_cap, xb_stride, max_runs, smem_bytes, async_stage; };
+// Shared-memory layout of the frames kernel.  Asynchronous staging (raw bytes of the next block copied in with cp.async:
+// one sample buffer, half-size exchange buffers, a raw buffer) is taken when the alignment rules hold and it fits;
+// otherwise the synchronous layout (two sample buffers filled through registers).
+bool frames_layout(const asr_plan* plan, int dtype, int noise_mode, bool aligned, FrLayout* lo) {
+  const asr_mfcc_params& p = plan->prm;
+  const int hop = p.hop_length;
+  const int esz = dtype == ASR_I16 ? 2 : (dtype == ASR_F32 ? 4 : 8);
+  const bool can_async = aligned && noise_mode != ASR_NOISE_MIXTURE && p.preemph == 0.0f && (hop % 8) == 0 && (plan->pad % 8) == 0;
+  for (int async_stage = can_async ? 1 : 0; async_stage >= 0; --async_stage) {
+    for (int runs = kFrMaxRuns; runs >= (async_stage ? 2 : 1); --runs) {
+      int off = 4 * plan->fr_blob_f4;
+      lo->aud_cap = round4(kFrBlock * hop + runs * (512 - std::min(hop, 512)) + 4 * runs + 8);
+      lo->sm_aud = off; off += (async_stage ? 1 : 2) * lo->aud_cap;
+      lo->sm_S = off; off += 2 * kFrBlock * plan->fr_s_pitch;
+      off = round4(off);
+      lo->xb_stride = async_stage ? 272 : plan->frame_stride;      // 8 x 17 float2 (two-round exchange) : 16 x 17 float2 + bank split
+      lo->sm_xb = off; off += kFrWarps * 2 * lo->xb_stride;
+      lo->sm_part = off; off += 2 * plan->fr_n_refs * 33;
+      off = round4(off);
+      lo->sm_raw = off;
+      if (async_stage) {
+        // samples a block can need raw: 32 hops + per run the frame overlap, the reflection sources of a lone edge frame
+        // and the alignment slack
+        const long long samples = static_cast<long long>(kFrBlock) * hop + static_cast<long long>(runs) * (512 - std::min(hop, 512) + plan->pad + 1 + 16);
+        const long long bytes = samples * (esz + (noise_mode != ASR_NOISE_NONE ? 8 : 0)) + 64LL * runs;
+        off += static_cast<int>((bytes + 3) / 4);
+      }
+      lo->max_runs = runs;
+      lo->async_stage = async_stage;
+      lo->smem_bytes = 4 * off;
+      if (lo->smem_bytes + 7168 <= kMaxSmemBytes) return true;      // + static shared memory (descriptor ring, clip cache)
+    }
   }
   return false;
 }
@@ -533,17 +552,18 @@ WsLayout ws_layout(const asr_plan* plan, int n_clips, int max_length) {
   w.bytes = w.off_lm + up(sizeof(float) * frames * plan->fr_lm_pitch + 16);
   return w;
 }
-bool frames_path_usable(const asr_plan* plan, int n_clips, int max_length, FrLayout* lo) {
+bool frames_path_usable(const asr_plan* plan, int n_clips, int max_length, int dtype, int noise_mode, bool aligned,
+                        FrLayout* lo) {
   if (!plan->fr_ok || plan->path == ASR_PATH_CLIP) return false;
   const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
   if (frames >= (1ll << 31) - 64) return false;                  // flattened frame index is int32
-  return frames_layout(plan, lo);
+  return frames_layout(plan, dtype, noise_mode, aligned, lo);
 }
 }  // namespace
 
 extern "C" size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips, int32_t max_length) {
   FrLayout lo;
-  if (!plan || n_clips <= 0 || max_length < 0 || !frames_path_usable(plan, n_clips, max_length, &lo)) return 0;
+  if (!plan || n_clips <= 0 || max_length < 0 || !frames_path_usable(plan, n_clips, max_length, ASR_F64, ASR_NOISE_NONE, false, &lo)) return 0;
   return ws_layout(plan, n_clips, max_length).bytes;
 }
 
@@ -553,7 +573,8 @@ static bool frames_path_wanted(const asr_plan* plan, bool noisy) {
 
 extern "C" int32_t asr_plan_launches(const asr_plan* plan, int32_t noisy) {
   FrLayout lo;
-  return (plan && plan->fr_ok && plan->path != ASR_PATH_CLIP && frames_path_wanted(plan, noisy != 0) && frames_layout(plan, &lo)) ? 3 : 1;
+  return (plan && plan->fr_ok && plan->path != ASR_PATH_CLIP && frames_path_wanted(plan, noisy != 0) &&
+          frames_layout(plan, ASR_F64, ASR_NOISE_NONE, false, &lo)) ? 3 : 1;
 }
 
 extern "C" int asr_plan_set_path(asr_plan* plan, int32_t path) {
@@ -603,7 +624,8 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
   }
   // ---- n_fft = 512: block-pipelined path (frame prefix -> frames -> cepstra) ----
   FrLayout flo;
-  if (frames_path_wanted(plan, kp.noise_mode != ASR_NOISE_NONE) && frames_path_usable(plan, n_clips, max_length, &flo)) {
+  if (frames_path_wanted(plan, kp.noise_mode != ASR_NOISE_NONE) &&
+      frames_path_usable(plan, n_clips, max_length, dtype, kp.noise_mode, kp.vec_ok != 0, &flo)) {
     const WsLayout wl = ws_layout(plan, n_clips, max_length);
     char* ws = static_cast<char*>(workspace_dev);
     if (ws) {
@@ -634,10 +656,12 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.off_twp = plan->fr_off_twp; fp.off_twu = plan->fr_off_twu; fp.off_wtab = plan->fr_off_wtab;
     fp.off_pieces = plan->fr_off_pieces; fp.off_wrange = plan->fr_off_wrange; fp.off_frange = plan->fr_off_frange;
     fp.off_refs = plan->fr_off_refs;
-    fp.sm_aud = flo.sm_aud; fp.sm_S = flo.sm_S; fp.sm_xb = flo.sm_xb; fp.sm_part = flo.sm_part;
-    fp.aud_cap = flo.aud_cap; fp.s_pitch = plan->fr_s_pitch; fp.xb_stride = plan->fr_xb_stride;
+    fp.sm_aud = flo.sm_aud; fp.sm_S = flo.sm_S; fp.sm_xb = flo.sm_xb; fp.sm_part = flo.sm_part; fp.sm_raw = flo.sm_raw;
+    fp.async_stage = flo.async_stage;
+    fp.aud_cap = flo.aud_cap; fp.s_pitch = plan->fr_s_pitch; fp.xb_stride = flo.xb_stride;
     fp.n_refs = plan->fr_n_refs; fp.max_runs = flo.max_runs;
-    fp.vec_ok = kp.vec_ok && p.preemph == 0.0f && (p.hop_length % 4) == 0 && (plan->pad % 4) == 0;
+    fp.vec_ok = kp.vec_ok && p.preemph == 0.0f && (p.hop_length % 4) == 0 && (plan->pad % 4) == 0 &&
+                (!flo.async_stage || kp.noise_mode != ASR_NOISE_MIXTURE);
     fp.fstart = reinterpret_cast<int*>(ws + wl.off_fstart);
     fp.nframes = reinterpret_cast<int*>(ws + wl.off_nframes);
     fp.clipmax = reinterpret_cast<float*>(ws + wl.off_clipmax);

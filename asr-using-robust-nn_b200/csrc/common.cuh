@@ -106,7 +106,8 @@ struct FParams {
   int blob_f4;
   int off_window, off_twp, off_twu, off_wtab, off_pieces, off_wrange, off_frange, off_refs;
   // ---- frames kernel shared-memory layout (floats) ----
-  int sm_aud, sm_S, sm_xb, sm_part;
+  int sm_aud, sm_S, sm_xb, sm_part, sm_raw;
+  int async_stage;    // 1: samples are copied raw to shared memory with cp.async one block ahead (frames512_kernel<.., true>)
   int aud_cap, s_pitch, xb_stride, n_refs, max_runs, vec_ok;
   // ---- workspace ----
   float* lm;          // [total frames][lm_pitch] log-mel rows (unclamped)

@@ -105,7 +105,9 @@ template <> struct FftCfg<2048> { static constexpr int M = 1024, G = 32, P = 32;
 //   unpack          : X[k], X[M-k] from Z[k], conj Z[M-k] (fetched from lane G-l by shuffle)
 //                     -> |X|^2 into fbuf[0..M]
 // fbuf is the exchange buffer, srow receives the power spectrum (they may be the same buffer).
-template <int NFFT, bool ZERO_TAIL>
+// HALF_XB: the exchange goes through a buffer of G/2 rows in two rounds (lanes 0..G/2-1 write, everybody reads its
+// first G/2 operands, then the upper lanes): half the shared memory for G/2 more (half-populated) store instructions.
+template <int NFFT, bool ZERO_TAIL, bool HALF_XB = false>
 __device__ __forceinline__ void frame_power_fft(float (&re)[FftCfg<NFFT>::P], float (&im)[FftCfg<NFFT>::P],
                                                 const float* __restrict__ twp, const float2* __restrict__ twu,
                                                 float* fbuf, float* srow, const int l) {
@@ -128,18 +130,40 @@ __device__ __forceinline__ void frame_power_fft(float (&re)[FftCfg<NFFT>::P], fl
       im[k2 + 1] = fmaf(r, t.w, i * t.z);
     }
   }
-  __syncwarp();                                    // staged frames read their samples from the frame buffers
-#pragma unroll
-  for (int k2 = 0; k2 < P; ++k2) xb[l * (P + 1) + k2] = make_float2(re[k2], im[k2]);
-  __syncwarp();
   float ur[Q][G], ui[Q][G];
+  if constexpr (!HALF_XB) {
+    __syncwarp();                                  // staged frames read their samples from the frame buffers
 #pragma unroll
-  for (int q = 0; q < Q; ++q) {
+    for (int k2 = 0; k2 < P; ++k2) xb[l * (P + 1) + k2] = make_float2(re[k2], im[k2]);
+    __syncwarp();
 #pragma unroll
-    for (int n1 = 0; n1 < G; ++n1) {
-      const float2 a = xb[n1 * (P + 1) + l + G * q];
-      ur[q][brev<G>(n1)] = a.x;
-      ui[q][brev<G>(n1)] = a.y;
+    for (int q = 0; q < Q; ++q) {
+#pragma unroll
+      for (int n1 = 0; n1 < G; ++n1) {
+        const float2 a = xb[n1 * (P + 1) + l + G * q];
+        ur[q][brev<G>(n1)] = a.x;
+        ui[q][brev<G>(n1)] = a.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      __syncwarp();                                // round 0: earlier readers of the buffer; round 1: round 0's reads
+      if ((l >= G / 2) == (half == 1)) {
+        const int row = l - half * (G / 2);
+#pragma unroll
+        for (int k2 = 0; k2 < P; ++k2) xb[row * (P + 1) + k2] = make_float2(re[k2], im[k2]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+#pragma unroll
+        for (int r = 0; r < G / 2; ++r) {
+          const float2 a = xb[r * (P + 1) + l + G * q];
+          ur[q][brev<G>(half * (G / 2) + r)] = a.x;
+          ui[q][brev<G>(half * (G / 2) + r)] = a.y;
+        }
+      }
     }
   }
 #pragma unroll

@@ -218,6 +218,10 @@ struct FRun {
   int aud0;         // staged position of padded sample p0
   int unit0;        // first linear unit index of the run (runs staged by 4-sample units; the others hold 0 units)
   int nu;           // units of the run: count / 4, or 0 when the run is staged sample by sample
+  // asynchronous staging (ASYNC kernel): original samples [ra, rb) of the clip are copied raw to shared memory
+  int ra, rb;
+  int raw_a;        // byte offset of the raw audio inside the raw buffer (16-byte aligned)
+  int raw_z;        // byte offset of the raw float64 noise
 };
 struct FBlock {
   int n_runs, n_slots, fin, n_units;
@@ -389,6 +393,118 @@ __device__ __forceinline__ void stage_finish(const FParams& fp, const FBlock& bl
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Asynchronous staging (ASYNC kernel): the raw bytes of a block's samples (and of its float64 noise) are copied to
+// shared memory with cp.async while the previous block is transformed; a short conversion phase then turns them into
+// the float32 frame samples.  Nothing waits on global-memory latency any more.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, const int src_bytes) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int DT>
+__device__ __forceinline__ void raw_issue(const FParams& fp, const FBlock& blk, char* __restrict__ raw, const int tid) {
+  constexpr int esz = DT == ASR_I16 ? 2 : (DT == ASR_F32 ? 4 : 8);
+  const int n_runs = blk.n_runs;
+  for (int r = 0; r < n_runs; ++r) {
+    // descriptor fields into registers first: the copies below write shared memory, which would force re-reads
+    const int nu = blk.run[r].nu, ra = blk.run[r].ra, rb = blk.run[r].rb, raw_a = blk.run[r].raw_a, raw_z = blk.run[r].raw_z;
+    const long long first = blk.run[r].base + ra;
+    if (nu == 0) continue;
+    const int n = rb - ra;
+    {
+      const char* src = reinterpret_cast<const char*>(fp.audio) + first * esz + tid * 16;
+      char* dst = raw + raw_a + tid * 16;
+      const int bytes = n * esz;
+      for (int c = tid * 16; c < bytes; c += kFrThreads * 16, src += kFrThreads * 16, dst += kFrThreads * 16)
+        cp_async16(dst, src, min(16, bytes - c));
+    }
+    if (fp.noise_mode != ASR_NOISE_NONE) {
+      const char* src = reinterpret_cast<const char*>(fp.z + first) + tid * 16;
+      char* dst = raw + raw_z + tid * 16;
+      const int bytes = n * 8;
+      for (int c = tid * 16; c < bytes; c += kFrThreads * 16, src += kFrThreads * 16, dst += kFrThreads * 16)
+        cp_async16(dst, src, min(16, bytes - c));
+    }
+  }
+  cp_async_commit();
+}
+
+// one sample from the raw copy: original index o must lie in [ra, rb)
+template <int DT>
+__device__ __forceinline__ float raw_sample(const FParams& fp, const FRun& run, const char* __restrict__ raw, const int o,
+                                            const double sig, const float scale) {
+  const int i = o - run.ra;
+  float x;
+  double xd;
+  if constexpr (DT == ASR_I16) {
+    x = static_cast<float>(reinterpret_cast<const short*>(raw + run.raw_a)[i]) * (1.0f / 32768.0f);
+    xd = static_cast<double>(x);
+  } else if constexpr (DT == ASR_F32) {
+    x = reinterpret_cast<const float*>(raw + run.raw_a)[i];
+    xd = static_cast<double>(x);
+  } else {
+    xd = reinterpret_cast<const double*>(raw + run.raw_a)[i];
+    x = static_cast<float>(xd);
+  }
+  if (fp.noise_mode == ASR_NOISE_NONE) return x * scale;
+  const double z = reinterpret_cast<const double*>(raw + run.raw_z)[i];
+  return static_cast<float>(__dadd_rn(xd, __dmul_rn(sig, z)));
+}
+
+template <int DT>
+__device__ __forceinline__ void raw_convert(const FParams& fp, const FBlock& blk, const char* __restrict__ raw,
+                                            float* __restrict__ aud, const int tid) {
+  constexpr int esz = DT == ASR_I16 ? 2 : (DT == ASR_F32 ? 4 : 8);
+  // clean int16 is staged UNSCALED (the window table carries the exact 2^-15); scaling by 2^15 is exact
+  const float scale = (DT == ASR_I16 && fp.noise_mode == ASR_NOISE_NONE) ? 32768.0f : 1.0f;
+  const int n_runs = blk.n_runs;
+  for (int r = 0; r < n_runs; ++r) {
+    const FRun run = blk.run[r];                        // a register copy: the stores below go to shared memory too
+    const double sig = (fp.noise_mode == ASR_NOISE_WHITE) ? __ldg(fp.sigma + run.clip) : 0.0;
+    float* dst = aud + run.aud0;
+    if (run.nu == 0) {        // odd alignment / pre-emphasis / mixture noise: straight from global memory
+      for (int i = tid; i < run.count; i += kFrThreads) dst[i] = padded_at<DT>(fp, run.base, run.L, run.p0 + i, sig) * scale;
+      continue;
+    }
+    const int orig0 = run.p0 - fp.pad;
+    const char* base_a = raw + run.raw_a - run.ra * esz;       // sample o of the clip at base_a + o*esz
+    const char* base_z = raw + run.raw_z - run.ra * 8;
+    for (int u = tid; u < run.nu; u += kFrThreads) {
+      const int orig = orig0 + 4 * u;
+      float4 v;
+      if (orig >= 0 && orig + 4 <= run.L) {                          // inside the clip (hence inside [ra, rb))
+        UnitRaw<DT> ur;
+        UnitZ uz;
+        const char* pa = base_a + orig * esz;
+        if constexpr (DT == ASR_I16) ur.a = *reinterpret_cast<const int2*>(pa);
+        else if constexpr (DT == ASR_F32) ur.a = *reinterpret_cast<const float4*>(pa);
+        else { ur.a[0] = *reinterpret_cast<const double2*>(pa); ur.a[1] = *reinterpret_cast<const double2*>(pa + 16); }
+        if (fp.noise_mode != ASR_NOISE_NONE) {
+          const char* pz = base_z + orig * 8;
+          uz.z[0] = *reinterpret_cast<const double2*>(pz);
+          uz.z[1] = *reinterpret_cast<const double2*>(pz + 16);
+        }
+        v = unit_convert<DT>(fp, ur, uz, uz, sig);
+      } else {                                                       // reflect / zero padding at the clip edges
+        float e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int o = orig + j;
+          bool zero = false;
+          if (o < 0) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = -o; }
+          else if (o >= run.L) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = 2 * (run.L - 1) - o; }
+          e[j] = zero ? 0.0f : raw_sample<DT>(fp, run, raw, o, sig, scale);
+        }
+        v = make_float4(e[0], e[1], e[2], e[3]);
+      }
+      *reinterpret_cast<float4*>(dst + 4 * u) = v;
+    }
+  }
+}
+
 __device__ __forceinline__ float fast_log2(const float x) {     // x >= amin > 0: no denormal handling needed
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -396,7 +512,7 @@ __device__ __forceinline__ float fast_log2(const float x) {     // x >= amin > 0
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int DT>
+template <int DT, bool ASYNC>
 __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __grid_constant__ FParams fp) {
   extern __shared__ __align__(16) float smem[];
   __shared__ FBlock ring[kFrRing];
@@ -421,7 +537,8 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
   const float2* s_twu = reinterpret_cast<const float2*>(smem + fp.off_twu);
   const float4* s_wtab = reinterpret_cast<const float4*>(smem + fp.off_wtab);
   const int4* s_pieces = reinterpret_cast<const int4*>(smem + fp.off_pieces);
-  float* s_aud = smem + fp.sm_aud;          // [2][aud_cap]
+  float* s_aud = smem + fp.sm_aud;          // [2][aud_cap] (ASYNC: one buffer)
+  char* s_raw = reinterpret_cast<char*>(smem + fp.sm_raw);   // ASYNC: raw bytes of the block being copied in
   float* s_S = smem + fp.sm_S;              // [2][32][s_pitch]
   float* s_xb = smem + fp.sm_xb;            // [16 warps][2][xb_stride]
   float* s_part = smem + fp.sm_part;        // [2][n_refs][33]
@@ -452,7 +569,7 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
   load_meta(cache_base);
   __syncthreads();
   auto assemble_runs = [&](FBlock& blk) {              // cursor thread
-    int n_slots = 0, n_runs = 0, aud = 0, n_units = 0;
+    int n_slots = 0, n_runs = 0, aud = 0, n_units = 0, raw_off = 0;
 #pragma unroll 1
     for (int c = 0; c < kFrMaxRuns; ++c) {
       const int b = b_cur;
@@ -467,12 +584,27 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
         run.p0 = t_cur * fp.hop;
         run.count = (n - 1) * fp.hop + 512;
         const long long e0 = run.base + static_cast<long long>(run.p0) - fp.pad;
-        const bool vec = fp.vec_ok && (e0 & 3) == 0;
+        const bool vec = fp.vec_ok && (e0 & (ASYNC ? 7 : 3)) == 0;
         run.unit0 = n_units;
         run.nu = vec ? run.count >> 2 : 0;
         n_units += run.nu;
         run.aud0 = (aud + 3) & ~3;
         aud = run.aud0 + run.count;
+        if (ASYNC && vec) {
+          constexpr int esz = DT == ASR_I16 ? 2 : (DT == ASR_F32 ? 4 : 8);
+          const int o0 = run.p0 - fp.pad, o1 = o0 + run.count;
+          int ra = max(0, o0), rb = min(run.L, o1);
+          if (fp.pad_mode == ASR_PAD_REFLECT) {         // sources of the reflected samples (single-frame runs at a clip edge)
+            if (o0 < 0) rb = max(rb, min(run.L, 1 - o0));
+            if (o1 > run.L) ra = min(ra, max(0, 2 * (run.L - 1) - (o1 - 1)));
+          }
+          ra &= ~7;                                     // keeps the copy 16-byte aligned for every dtype
+          run.ra = ra; run.rb = rb;
+          run.raw_a = raw_off;
+          raw_off += ((rb - ra) * esz + 15) & ~15;
+          run.raw_z = raw_off;
+          if (fp.noise_mode != ASR_NOISE_NONE) raw_off += ((rb - ra) * 8 + 15) & ~15;
+        }
         // slot tables of this run are filled by the lanes of the warp afterwards: stash what they need
         blk.slot_g[n_runs] = g_cur; blk.slot_clip[n_runs] = n_slots;       // (temporarily: g0 and slot0 of run r)
         n_slots += n; t_cur += n; g_cur += n; ++n_runs;
@@ -510,8 +642,17 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
     __syncthreads();                                   // also: tables and the zeroed S
     if (ring[i].refill >= 0) { load_meta(ring[i].refill); __syncthreads(); }
   }
-  stage_block<DT>(fp, ring[0], s_aud, tid, kFrAllThreads);
-  __syncthreads();
+  if constexpr (ASYNC) {
+    raw_issue<DT>(fp, ring[0], s_raw, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    raw_convert<DT>(fp, ring[0], s_raw, s_aud, tid);
+    __syncthreads();
+    raw_issue<DT>(fp, ring[1], s_raw, tid);
+  } else {
+    stage_block<DT>(fp, ring[0], s_aud, tid, kFrAllThreads);
+    __syncthreads();
+  }
 
   // ---- per-thread constants of the phases ----
   const int part_buf = fp.n_refs * 33;                 // floats per partial buffer
@@ -577,7 +718,7 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
     }
     // ---- stage (block it+1), part 1: issue the loads of this thread's samples (consumed after the mel phase) ----
     StagePf<DT> pf;
-    const bool do_stage = b_stage->n_slots > 0 && !(fp.dbg_skip & 1);
+    const bool do_stage = !ASYNC && b_stage->n_slots > 0 && !(fp.dbg_skip & 1);
     if (do_stage) stage_issue<DT>(fp, *b_stage, tid, pf);
 
     // ---- combine (block it-2): lanes <-> filters; warp w takes slots w and w+16.
@@ -621,16 +762,23 @@ __global__ void __launch_bounds__(kFrAllThreads, 1) frames512_kernel(const __gri
 
     // ---- fft (block it) ----
     if (n_fft > 0 && !(fp.dbg_skip & 8)) {
-      const float* xs = s_aud + par * fp.aud_cap + b_fft->slot_aud[fft_slot];
+      const float* xs = s_aud + (ASYNC ? 0 : par * fp.aud_cap) + b_fft->slot_aud[fft_slot];
       float re[16], im[16];
       fft512_load(xs, s_win2, fft_l, re, im);
-      frame_power_fft<512, false>(re, im, s_twp, s_twu, fft_xb, s_S + par * s_buf + fft_slot * fp.s_pitch, fft_l);
+      frame_power_fft<512, false, ASYNC>(re, im, s_twp, s_twu, fft_xb, s_S + par * s_buf + fft_slot * fp.s_pitch, fft_l);
     }
 
     nb = &ring[(it + 2) % kFrRing];
     b_comb = b_mel; b_mel = b_fft; b_fft = b_stage; b_stage = nb;
+    if constexpr (ASYNC) cp_async_wait_all();          // this thread's share of the next block's raw bytes has landed
     __syncthreads();
     if (nb->refill >= 0) { load_meta(nb->refill); __syncthreads(); }   // rare: the cursor ran past the cached clips
+    if constexpr (ASYNC) {
+      // the FFTs are done with the sample buffer: convert the next block into it, then start copying the one after
+      if (b_fft->n_slots > 0 && !(fp.dbg_skip & 1)) raw_convert<DT>(fp, *b_fft, s_raw, s_aud, tid);
+      __syncthreads();
+      if (b_stage->n_slots > 0 && !(fp.dbg_skip & 1)) raw_issue<DT>(fp, *b_stage, s_raw, tid);
+    }
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) flush_max(cm_clip[h], cm_max[h]);
@@ -748,15 +896,15 @@ __global__ void __launch_bounds__(kCepThreads) cepstra_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int DT>
+template <int DT, bool ASYNC>
 static cudaError_t launch_frames_dt(const FParams& fp, int grid, int smem_bytes, cudaStream_t stream) {
   static int granted = 0;                      // the kernel also has static shared memory: ask for what is needed
   if (smem_bytes > granted) {
-    cudaError_t e = cudaFuncSetAttribute(frames512_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(frames512_kernel<DT, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     granted = smem_bytes;
   }
-  frames512_kernel<DT><<<grid, kFrAllThreads, smem_bytes, stream>>>(fp);
+  frames512_kernel<DT, ASYNC><<<grid, kFrAllThreads, smem_bytes, stream>>>(fp);
   return cudaGetLastError();
 }
 
@@ -777,10 +925,18 @@ cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_
   frame_prefix_kernel<<<1, 1024, 0, stream>>>(fp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  switch (fp.dtype) {
-    case ASR_I16: e = launch_frames_dt<ASR_I16>(fp, sm_count, frames_smem_bytes, stream); break;
-    case ASR_F32: e = launch_frames_dt<ASR_F32>(fp, sm_count, frames_smem_bytes, stream); break;
-    default: e = launch_frames_dt<ASR_F64>(fp, sm_count, frames_smem_bytes, stream); break;
+  if (fp.async_stage) {
+    switch (fp.dtype) {
+      case ASR_I16: e = launch_frames_dt<ASR_I16, true>(fp, sm_count, frames_smem_bytes, stream); break;
+      case ASR_F32: e = launch_frames_dt<ASR_F32, true>(fp, sm_count, frames_smem_bytes, stream); break;
+      default: e = launch_frames_dt<ASR_F64, true>(fp, sm_count, frames_smem_bytes, stream); break;
+    }
+  } else {
+    switch (fp.dtype) {
+      case ASR_I16: e = launch_frames_dt<ASR_I16, false>(fp, sm_count, frames_smem_bytes, stream); break;
+      case ASR_F32: e = launch_frames_dt<ASR_F32, false>(fp, sm_count, frames_smem_bytes, stream); break;
+      default: e = launch_frames_dt<ASR_F64, false>(fp, sm_count, frames_smem_bytes, stream); break;
+    }
   }
   if (e != cudaSuccess) return e;
   const int half = (fp.delta_orders > 0 && !fp.logmel_only) ? fp.delta_width / 2 : 0;
