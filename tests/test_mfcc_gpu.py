@@ -259,3 +259,38 @@ def test_many_tiny_and_empty_clips():
             r = lr.mfcc(to_f32([c])[0], lr.C1)
             _close(out[i:i + 1, :, :r.shape[1]].cpu().numpy(), r[None])
             assert (out[i, :, r.shape[1]:] == 0).all()
+
+
+@pytest.mark.parametrize("noisy", [False, True])
+def test_unaligned_packing(noisy):
+    """Clips packed back to back at odd offsets (no 8-sample alignment): the vector / asynchronous staging paths
+    must fall back to their scalar forms and still match."""
+    import asr_b200 as A
+    from oracle import noise_ref as nr
+    lr = _o()
+    lengths = [16000, 7001, 12345, 16000, 3333]
+    clips = synth_clips(len(lengths), 0, 16000, 93, lengths=lengths)
+    offsets = np.zeros(len(lengths), dtype=np.int64)
+    offsets[1:] = np.cumsum(lengths[:-1]) + 1                       # +1: first clip at 0, the others at odd / arbitrary offsets
+    total = int(offsets[-1] + lengths[-1]) + 3
+    host = np.zeros(total, dtype=np.int16)
+    zhost = np.zeros(total, dtype=np.float64)
+    rng = np.random.default_rng(6)
+    zs = [rng.standard_normal(n) for n in lengths]
+    for c, z, o in zip(clips, zs, offsets):
+        host[o:o + len(c)] = c
+        zhost[o:o + len(c)] = z
+    lens = np.asarray(lengths, dtype=np.int32)
+    batch = A.ClipBatch(torch.from_numpy(host).cuda(), torch.from_numpy(offsets).cuda(), torch.from_numpy(lens).cuda(),
+                        int(lens.max()), offsets, lens)
+    plan = A.MfccPlan(A.C1, path=PATH)
+    noise = None
+    sig = np.array([0.01, 0.0, 0.02, 0.005, 0.03])
+    if noisy:
+        noise = A.Noise.white(torch.from_numpy(zhost).cuda(), torch.from_numpy(sig).cuda())
+    out, st = plan.mfcc(batch, noise=noise)
+    assert int(st.max()) == 0
+    for i, (c, z) in enumerate(zip(to_f32(clips), zs)):
+        x = nr.add_white_noise_z(c, sig[i], z) if noisy else c
+        r = lr.mfcc(np.asarray(x), lr.C1)
+        _close(out[i:i + 1, :, :r.shape[1]].cpu().numpy(), r[None], atol=3e-3)
