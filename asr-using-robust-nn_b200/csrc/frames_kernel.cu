@@ -51,7 +51,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, const float v) {
 // ------------------------------------------------------------------------------------------------
 // T_b, status, exclusive prefix sum of T_b over the clips (single CTA; thread t owns a contiguous chunk).
 __global__ void __launch_bounds__(1024) frame_prefix_kernel(const FParams fp) {
-  __shared__ int s_sum[1024];
+  __shared__ int s_sum[64 + 1024];
   const int tid = threadIdx.x;
   const int per = (fp.n_clips + 1023) / 1024;
   const int lo = min(fp.n_clips, tid * per), hi = min(fp.n_clips, lo + per);
@@ -71,20 +71,34 @@ __global__ void __launch_bounds__(1024) frame_prefix_kernel(const FParams fp) {
     fp.nframes[b] = T;
     local += T;
   }
-  s_sum[tid] = local;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {            // Hillis-Steele inclusive scan
-    const int v = tid >= o ? s_sum[tid - o] : 0;
-    __syncthreads();
-    s_sum[tid] += v;
-    __syncthreads();
+  // inclusive scan of the 1024 chunk sums: within warps by shuffles, then over the 32 warp totals
+  const int lane = tid & 31, warp = tid >> 5;
+  int inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
   }
-  int run = s_sum[tid] - local;
+  if (lane == 31) s_sum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_sum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    s_sum[32 + lane] = w;                       // inclusive totals of the warps
+  }
+  __syncthreads();
+  inc += warp > 0 ? s_sum[32 + warp - 1] : 0;
+  s_sum[64 + tid] = inc;                        // (only the last entry is read back below)
+  int run = inc - local;
   for (int b = lo; b < hi; ++b) {
     fp.fstart[b] = run;
     run += fp.nframes[b];
   }
-  if (tid == 1023) fp.fstart[fp.n_clips] = s_sum[1023];
+  if (tid == 1023) fp.fstart[fp.n_clips] = inc;
 }
 
 // ------------------------------------------------------------------------------------------------
