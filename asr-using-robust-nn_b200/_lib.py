@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libasr_b200.so")
 ASR_I16, ASR_F32, ASR_F64 = 0, 1, 2
 ASR_NOISE_NONE, ASR_NOISE_WHITE, ASR_NOISE_MIXTURE = 0, 1, 2
 ASR_CLIP_OK, ASR_CLIP_TOO_SHORT, ASR_CLIP_TOO_FEW_FRAMES = 0, 1, 2
-ASR_PATH_AUTO, ASR_PATH_CLIP, ASR_PATH_FRAMES = 0, 1, 2
+ASR_PATH_AUTO, ASR_PATH_CLIP, ASR_PATH_FRAMES, ASR_PATH_TILES = 0, 1, 2, 3
 
 
 class AsrError(RuntimeError):
@@ -61,6 +61,7 @@ SIGNATURES = {
     "asr_mfcc_workspace_bytes": (C.c_size_t, [_vp, _i32, _i32]),
     "asr_plan_launches": (_i32, [_vp, _i32]),
     "asr_plan_set_path": (C.c_int, [_vp, _i32]),
+    "asr_plan_path_used": (_i32, [_vp, _i32, _i32]),
     "asr_clip_power": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "asr_snr_sigma": (C.c_int, [_vp, _f32, _vp, _i32, _vp]),
     "asr_mix_white": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),

@@ -230,6 +230,125 @@ static bool build_frames_tables(asr_plan* pl, const std::vector<double>& mel_f, 
   return true;
 }
 
+// ---- tables of the TMA-staged path (tile_kernel.cu), n_fft = 512 ---------------------------------------
+// The same segment form of the mel bank as above, as a flat "program": bins are taken four at a time (one float4 of the
+// spectrum row); a step belongs to one segment and carries (fall, rise) weights for its 4 bins (zero outside the segment,
+// so a float4 that straddles a boundary appears in two steps).  The steps are dealt out in order to `n_vw` "virtual warps"
+// (groups of FR lanes, FR = frames per block); where a share ends inside a segment the segment is cut into pieces, each
+// with its own pair of partial rows (row (seg * npc + piece) * 2 = fall, + 1 = rise); filter j = sum of the rise rows of
+// segment j and the fall rows of j+1.  With two virtual warps per hardware warp (FR = 16) the shares of a pair are padded
+// with empty steps to the same length.
+static bool build_tile_tables(asr_plan* pl, int cfg, int n_vw, bool pair_equal, const std::vector<double>& mel_f,
+                              const std::vector<double>& fftfreqs, const std::vector<float>& twp, const std::vector<float>& twu) {
+  const asr_mfcc_params& p = pl->prm;
+  const int fr = cfg == 1 ? 16 : 32;                       // frames per block of this kernel shape
+  const int n_bins = pl->n_bins, n_mels = p.n_mels;
+  asr_plan::TileTables& tt = pl->tl[cfg];
+  std::vector<int> seg(n_bins);
+  for (int k = 0; k < n_bins; ++k) {
+    int sg = 0;
+    while (sg < n_mels && mel_f[sg + 1] <= fftfreqs[k]) ++sg;
+    seg[k] = sg;
+  }
+  auto W = [&](int i, int k) { return (i >= 0 && i < n_mels) ? pl->h_mel_dense[static_cast<size_t>(i) * n_bins + k] : 0.0f; };
+  struct Step { int q, seg, piece, last; };
+  std::vector<Step> steps;
+  for (int sg = 0; sg <= n_mels; ++sg) {
+    int k0 = -1, k1 = -1;
+    for (int k = 0; k < n_bins; ++k)
+      if (seg[k] == sg && (W(sg - 1, k) != 0.0f || W(sg, k) != 0.0f)) { if (k0 < 0) k0 = k; k1 = k + 1; }
+    if (k0 < 0) continue;                                   // no bin of this segment carries weight: its partial rows stay 0
+    for (int q = k0 / 4; q <= (k1 - 1) / 4; ++q) steps.push_back({q, sg, 0, 0});
+  }
+  const int ns = static_cast<int>(steps.size());
+  if (ns == 0) return true;
+  std::vector<std::vector<Step>> share(16);
+  std::vector<int> n_pieces(n_mels + 1, 0);
+  for (int w = 0; w < n_vw; ++w) {
+    const int a = static_cast<int>(static_cast<long long>(w) * ns / n_vw);
+    const int b = static_cast<int>(static_cast<long long>(w + 1) * ns / n_vw);
+    for (int i = a; i < b; ++i) {
+      Step st = steps[i];
+      if (i == a || steps[i].seg != steps[i - 1].seg) ++n_pieces[st.seg];
+      st.piece = n_pieces[st.seg] - 1;
+      st.last = (i + 1 == b || steps[i + 1].seg != st.seg) ? 1 : 0;
+      share[w].push_back(st);
+    }
+  }
+  if (pair_equal)
+    for (int w = 0; w < 16; w += 2) {
+      const size_t n = std::max(share[w].size(), share[w + 1].size());
+      share[w].resize(n, Step{0, -1, 0, 0});
+      share[w + 1].resize(n, Step{0, -1, 0, 0});
+    }
+  int npc = 1;
+  for (int sg = 0; sg <= n_mels; ++sg) npc = std::max(npc, n_pieces[sg]);
+  if (npc > kTlMaxPieces) return true;
+  std::vector<float> wtab;
+  std::vector<int> stab, wrange(2 * 16, 0);
+  for (int w = 0; w < 16; ++w) {
+    wrange[2 * w] = static_cast<int>(stab.size() / 2);
+    wrange[2 * w + 1] = static_cast<int>(share[w].size());
+    for (const Step& st : share[w]) {
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * st.q + e;
+        const bool in = st.seg >= 0 && k < n_bins && seg[k] == st.seg;
+        wtab.push_back(in ? 0.25f * W(st.seg - 1, k) : 0.0f);       // the spectrum row of this path holds 4|X|^2 (exact scaling)
+        wtab.push_back(in ? 0.25f * W(st.seg, k) : 0.0f);
+      }
+      stab.push_back(16 * st.q);                                                  // byte offset inside the spectrum row
+      stab.push_back(st.last ? (st.seg * npc + st.piece) * 2 * fr * 4 : -1);      // byte offset of the (fall) partial row
+    }
+  }
+  tt.npc = npc;
+  tt.npart = (n_mels + 1) * npc * 2;
+  tt.nsteps = static_cast<int>(stab.size() / 2);
+  std::vector<float> blob;
+  auto put_f = [&](const float* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.insert(blob.end(), src, src + n);
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  auto put_i = [&](const int* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.resize(blob.size() + n);
+    if (n) std::memcpy(blob.data() + off, src, n * sizeof(int));
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  tt.off_twp = put_f(twp.data(), twp.size());
+  {
+    std::vector<float> twu2(twu);
+    for (float& v : twu2) v *= 2.0f;                       // the tile kernel unpacks 2X (exact scaling)
+    tt.off_twu = put_f(twu2.data(), twu2.size());
+  }
+  tt.off_wtab = put_f(wtab.data(), wtab.size());
+  tt.off_steps = put_i(stab.data(), stab.size());
+  tt.off_wrange = put_i(wrange.data(), wrange.size());
+  tt.blob_f4 = static_cast<int>(blob.size() / 4);           // copied to shared memory; one of the two windows follows it there
+  tt.off_window = put_f(pl->h_window.data(), pl->h_window.size());
+  {
+    std::vector<float> wi(pl->h_window);
+    for (float& v : wi) v *= (1.0f / 32768.0f);
+    tt.off_window_i16 = put_f(wi.data(), wi.size());
+  }
+  if (cudaMalloc(reinterpret_cast<void**>(&tt.blob_dev), blob.size() * sizeof(float)) != cudaSuccess) return false;
+  if (cudaMemcpy(tt.blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  return true;
+}
+
+static bool build_tile_tables_all(asr_plan* pl, const std::vector<double>& mel_f, const std::vector<double>& fftfreqs,
+                                  const std::vector<float>& twp, const std::vector<float>& twu) {
+  const asr_mfcc_params& p = pl->prm;
+  pl->tl_ok = 0;
+  if (!pl->fr_ok || (p.hop_length % 8) != 0 || (pl->pad % 8) != 0 || p.preemph != 0.0f) return true;
+  if (!build_tile_tables(pl, 0, 15, false, mel_f, fftfreqs, twp, twu)) return false;     // 16 warps, 32 frames per block
+  if (!build_tile_tables(pl, 1, 14, true, mel_f, fftfreqs, twp, twu)) return false;      // 8 warps, 16 frames per block
+  pl->tl_ok = (pl->tl[0].blob_dev && pl->tl[1].blob_dev) ? 1 : 0;
+  return true;
+}
+
 struct FftShape { int M, G, P; };
 static bool fft_shape(int n_fft, FftShape* s) {
   switch (n_fft) {
@@ -460,7 +579,7 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
     cudaDeviceProp prop;
     pl->sm_count = (cudaGetDeviceProperties(&prop, pl->device) == cudaSuccess) ? prop.multiProcessorCount : 148;
   }
-  if (!build_frames_tables(pl, mel_f, fftfreqs, twp, twu)) {
+  if (!build_frames_tables(pl, mel_f, fftfreqs, twp, twu) || !build_tile_tables_all(pl, mel_f, fftfreqs, twp, twu)) {
     const cudaError_t e2 = cudaGetLastError();
     asr_plan_destroy(pl);
     return cuda_fail(e2, "asr_plan_create (frames-path tables)");
@@ -473,6 +592,8 @@ extern "C" void asr_plan_destroy(asr_plan* plan) {
   if (!plan) return;
   if (plan->blob_dev) cudaFree(plan->blob_dev);
   if (plan->fr_blob_dev) cudaFree(plan->fr_blob_dev);
+  for (int c = 0; c < 2; ++c)
+    if (plan->tl[c].blob_dev) cudaFree(plan->tl[c].blob_dev);
   if (plan->ws_dev) cudaFree(plan->ws_dev);
   delete plan;
 }
@@ -540,6 +661,38 @@ bool frames_layout(const asr_plan* plan, int dtype, int noise_mode, bool aligned
   }
   return false;
 }
+struct TlLayout { int sm_aud, sm_S, sm_part, sm_raw, max_runs, smem_bytes, nw, cfg; };
+// Shared-memory layout of the tile kernel: tables | window | frame samples of one block | FR slots (exchange buffer /
+// spectrum row) | mel partial rows | raw bytes of the block being copied in.  The 8-warp shape (two CTAs per SM) is taken
+// when two such CTAs fit one SM, else the 16-warp shape.
+bool tiles_layout(const asr_plan* plan, int dtype, int noise_mode, TlLayout* lo) {
+  const asr_mfcc_params& p = plan->prm;
+  const int hop = p.hop_length;
+  const int esz = dtype == ASR_I16 ? 2 : (dtype == ASR_F32 ? 4 : 8);
+  const char* force = std::getenv("ASR_B200_TILE_WARPS");          // experiments: 8 or 16
+  for (int cfg = 0; cfg < 2; ++cfg) {                              // measured: the 16-warp shape is (slightly) faster when it fits
+    const int nw = cfg == 1 ? 8 : 16, fr = 2 * nw;
+    if (force && std::atoi(force) != nw) continue;
+    const asr_plan::TileTables& tt = plan->tl[cfg];
+    const long long budget = cfg == 1 ? (228 * 1024 - 2 * 1024) / 2 - 3072 : kMaxSmemBytes - 4096;   // minus static shared memory
+    for (int runs = kTlMaxRuns; runs >= 2; --runs) {
+      long long off = 4LL * tt.blob_f4 + 512;
+      const long long aud_cap = round4(fr * hop + runs * (512 - std::min(hop, 512)) + 4 * runs + 8);
+      lo->sm_aud = static_cast<int>(off); off += aud_cap;
+      lo->sm_S = static_cast<int>(off); off += fr * kTlRS;
+      lo->sm_part = static_cast<int>(off); off += tt.npart * fr;
+      lo->sm_raw = static_cast<int>(off);
+      // samples a block can need raw: FR hops + per run the frame overlap, the reflection sources of a lone edge frame
+      // and the alignment slack
+      const long long samples = static_cast<long long>(fr) * hop + static_cast<long long>(runs) * (512 - std::min(hop, 512) + plan->pad + 1 + 16);
+      const long long bytes = samples * (esz + (noise_mode != ASR_NOISE_NONE ? 8 : 0)) + 64LL * runs;
+      off += (bytes + 3) / 4;
+      lo->max_runs = runs; lo->nw = nw; lo->cfg = cfg;
+      if (4 * off <= budget) { lo->smem_bytes = static_cast<int>(4 * off); return true; }
+    }
+  }
+  return false;
+}
 struct WsLayout { size_t off_fstart, off_nframes, off_clipmax, off_lm, bytes; };
 WsLayout ws_layout(const asr_plan* plan, int n_clips, int max_length) {
   WsLayout w;
@@ -549,7 +702,7 @@ WsLayout ws_layout(const asr_plan* plan, int n_clips, int max_length) {
   w.off_nframes = up(sizeof(int) * (static_cast<size_t>(n_clips) + 1));
   w.off_clipmax = w.off_nframes + up(sizeof(int) * static_cast<size_t>(n_clips));
   w.off_lm = w.off_clipmax + up(sizeof(float) * static_cast<size_t>(n_clips));
-  w.bytes = w.off_lm + up(sizeof(float) * frames * plan->fr_lm_pitch + 16);
+  w.bytes = w.off_lm + up(sizeof(float) * (frames + 32) * plan->fr_lm_pitch + 16);   // either layout: [frames][lm_pitch] or [n_mels][frames rounded up to 32]
   return w;
 }
 bool frames_path_usable(const asr_plan* plan, int n_clips, int max_length, int dtype, int noise_mode, bool aligned,
@@ -559,26 +712,49 @@ bool frames_path_usable(const asr_plan* plan, int n_clips, int max_length, int d
   if (frames >= (1ll << 31) - 64) return false;                  // flattened frame index is int32
   return frames_layout(plan, dtype, noise_mode, aligned, lo);
 }
+// TILES: n_fft = 512, hop and pad multiples of 8, no pre-emphasis, no mixture noise, 16-byte aligned arrays
+bool tiles_path_usable(const asr_plan* plan, int n_clips, int max_length, int dtype, int noise_mode, bool aligned,
+                              TlLayout* lo) {
+  if (!plan->tl_ok || !(plan->path == ASR_PATH_AUTO || plan->path == ASR_PATH_TILES)) return false;
+  if (noise_mode == ASR_NOISE_MIXTURE || !aligned) return false;
+  const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
+  if (frames >= (1ll << 31) - 64) return false;                  // flattened frame index is int32
+  return tiles_layout(plan, dtype, noise_mode, lo);
+}
+
 }  // namespace
 
 extern "C" size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips, int32_t max_length) {
   FrLayout lo;
-  if (!plan || n_clips <= 0 || max_length < 0 || !frames_path_usable(plan, n_clips, max_length, ASR_F64, ASR_NOISE_NONE, false, &lo)) return 0;
+  if (!plan || n_clips <= 0 || max_length < 0) return 0;
+  TlLayout tlo;
+  if (!frames_path_usable(plan, n_clips, max_length, ASR_F64, ASR_NOISE_NONE, false, &lo) &&
+      !tiles_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tlo)) return 0;
   return ws_layout(plan, n_clips, max_length).bytes;
 }
 
 static bool frames_path_wanted(const asr_plan* plan, bool noisy) {
-  return plan->path == ASR_PATH_FRAMES || (plan->path == ASR_PATH_AUTO && noisy);
+  return plan->path == ASR_PATH_FRAMES || plan->path == ASR_PATH_TILES || (plan->path == ASR_PATH_AUTO && noisy);
 }
-
 extern "C" int32_t asr_plan_launches(const asr_plan* plan, int32_t noisy) {
   FrLayout lo;
+  TlLayout tlo;
+  if (plan && tiles_path_usable(plan, 1, 0, ASR_F64, noisy ? ASR_NOISE_WHITE : ASR_NOISE_NONE, true, &tlo)) return 3;
   return (plan && plan->fr_ok && plan->path != ASR_PATH_CLIP && frames_path_wanted(plan, noisy != 0) &&
           frames_layout(plan, ASR_F64, ASR_NOISE_NONE, false, &lo)) ? 3 : 1;
 }
 
+extern "C" int32_t asr_plan_path_used(const asr_plan* plan, int32_t dtype, int32_t noise_mode) {
+  if (!plan) return ASR_PATH_CLIP;
+  FrLayout lo;
+  TlLayout tlo;
+  if (tiles_path_usable(plan, 1, 0, dtype, noise_mode, true, &tlo)) return ASR_PATH_TILES;
+  if (frames_path_wanted(plan, noise_mode != ASR_NOISE_NONE) && frames_path_usable(plan, 1, 0, dtype, noise_mode, true, &lo)) return ASR_PATH_FRAMES;
+  return ASR_PATH_CLIP;
+}
+
 extern "C" int asr_plan_set_path(asr_plan* plan, int32_t path) {
-  if (!plan || path < ASR_PATH_AUTO || path > ASR_PATH_FRAMES) { set_error("asr_plan_set_path: bad argument"); return ASR_ERR_INVALID; }
+  if (!plan || path < ASR_PATH_AUTO || path > ASR_PATH_TILES) { set_error("asr_plan_set_path: bad argument"); return ASR_ERR_INVALID; }
   plan->path = path;
   return ASR_OK;
 }
@@ -621,6 +797,54 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
   {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     kp.vec_ok = al16(audio_dev) && (kp.noise_mode == ASR_NOISE_NONE || (al16(kp.z) && (kp.noise_mode != ASR_NOISE_MIXTURE || al16(kp.z2))));
+  }
+  // ---- n_fft = 512: TMA-staged block pipeline (frame prefix -> tiles -> cepstra) ----
+  TlLayout tlo;
+  if (tiles_path_usable(plan, n_clips, max_length, dtype, kp.noise_mode, kp.vec_ok != 0, &tlo)) {
+    const WsLayout wl = ws_layout(plan, n_clips, max_length);
+    char* ws = static_cast<char*>(workspace_dev);
+    if (ws) {
+      if (workspace_bytes < wl.bytes || (reinterpret_cast<uintptr_t>(ws) & 15)) return bad("workspace too small or not 16-byte aligned");
+    } else {
+      asr_plan* mp = const_cast<asr_plan*>(plan);                // plan-owned scratch (documented: no concurrent launches)
+      if (mp->ws_bytes < wl.bytes) {
+        if (mp->ws_dev) ASR_CUDA_TRY(cudaFree(mp->ws_dev));
+        mp->ws_dev = nullptr; mp->ws_bytes = 0;
+        ASR_CUDA_TRY(cudaMalloc(&mp->ws_dev, wl.bytes));
+        mp->ws_bytes = wl.bytes;
+      }
+      ws = static_cast<char*>(mp->ws_dev);
+    }
+    FParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.audio = audio_dev; fp.offsets = kp.offsets; fp.lengths = lengths_dev; fp.dtype = dtype; fp.n_clips = n_clips;
+    fp.noise_mode = kp.noise_mode; fp.z = kp.z; fp.z2 = kp.z2; fp.sigma = kp.sigma;
+    fp.out = out_dev; fp.out_f64 = out_dtype == ASR_F64; fp.out_frames = out_frames;
+    fp.out_rows = p.n_mfcc * (1 + p.delta_orders); fp.logmel_only = logmel_only; fp.status = status_dev;
+    fp.n_fft = p.n_fft; fp.hop = p.hop_length; fp.pad = plan->pad; fp.pad_mode = p.pad_mode;
+    fp.n_mels = p.n_mels; fp.n_mfcc = p.n_mfcc; fp.delta_orders = p.delta_orders; fp.delta_width = p.delta_width;
+    fp.top_db = p.top_db; fp.amin = p.amin; fp.preemph = p.preemph;
+    const asr_plan::TileTables& tt = plan->tl[tlo.cfg];
+    fp.blob = reinterpret_cast<const float4*>(tt.blob_dev); fp.blob_f4 = tt.blob_f4;
+    const bool unscaled_i16 = dtype == ASR_I16 && kp.noise_mode == ASR_NOISE_NONE;   // staged unscaled, 2^-15 in the window
+    fp.off_window = unscaled_i16 ? tt.off_window_i16 : tt.off_window;
+    fp.off_twp = tt.off_twp; fp.off_twu = tt.off_twu; fp.off_wtab = tt.off_wtab;
+    fp.off_steps = tt.off_steps; fp.off_wrange = tt.off_wrange;
+    fp.sm_aud = tlo.sm_aud; fp.sm_S = tlo.sm_S; fp.sm_part = tlo.sm_part; fp.sm_raw = tlo.sm_raw;
+    fp.max_runs = tlo.max_runs; fp.vec_ok = 1;
+    fp.t_npart = tt.npart; fp.t_npc = tt.npc; fp.t_nw = tlo.nw;
+    fp.fstart = reinterpret_cast<int*>(ws + wl.off_fstart);
+    fp.nframes = reinterpret_cast<int*>(ws + wl.off_nframes);
+    fp.clipmax = reinterpret_cast<float*>(ws + wl.off_clipmax);
+    fp.lm = reinterpret_cast<float*>(ws + wl.off_lm);
+    const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
+    fp.lm_stride = static_cast<int>((frames + 31) & ~31LL);
+    fp.cep_blob = reinterpret_cast<const float4*>(plan->fr_blob_dev) + plan->cep_blob_f4;
+    fp.cep_tab_f4 = plan->cep_tab_f4; fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
+    fp.cep_off_col = plan->cep_smem_bytes / 4;
+    ASR_CUDA_TRY(launch_tiles_path(fp, plan->sm_count, tlo.smem_bytes, plan->cep_smem_bytes + 4 * 128 * p.n_mels,
+                                   std::max(1, asr_plan_num_frames(plan, max_length)), as_stream(stream)));
+    return ASR_OK;
   }
   // ---- n_fft = 512: block-pipelined path (frame prefix -> frames -> cepstra) ----
   FrLayout flo;

@@ -81,6 +81,14 @@ constexpr int kFrAllThreads = kFrThreads;
 constexpr int kFrBlock = 32;        // frames per block
 constexpr int kFrMaxRuns = 4;       // runs of consecutive frames (of one clip) per block, at most
 
+// ---- TMA-staged block pipeline for n_fft = 512 (tile_kernel.cu) ----
+// Two shapes: 16 warps / 32 frames per block / one CTA per SM, or 8 warps / 16 frames per block / two CTAs per SM.
+// The last warp of a CTA assembles descriptors and issues the copies; the other warps share the mel steps.
+constexpr int kTlMaxRuns = 4;
+constexpr int kTlRS = 548;          // floats per frame slot: 16 x 17 float2 exchange buffer, reused as the spectrum row
+                                    // (RS/4 odd: float4 rows conflict-free over lanes; RS = 4 mod 8: slots 4 apart sit in complementary bank halves)
+constexpr int kTlMaxPieces = 4;     // a mel segment is cut into at most this many per-warp pieces
+
 struct FParams {
   // ---- batch ----
   const void* audio;
@@ -118,10 +126,21 @@ struct FParams {
   // ---- cepstra kernel tables: float4 offset inside the blob, size, shared-memory offsets (floats) ----
   int cep_blob_f4, cep_tab_f4, cep_off_cbuf, cep_off_taps;
   int dbg_skip;       // timing experiments only (ASR_B200_DBG_SKIP): bit 0 stage, 1 combine, 2 mel, 3 fft are skipped
+  // ---- tiles path (tile_kernel.cu) ----
+  int off_steps;      // int2 per mel step: (float4 index inside the spectrum row, partial row to flush into or -1)
+  int t_npart;        // rows of 32 floats in the partial buffer: (n_mels + 1) * t_npc * 2
+  int t_npc;          // pieces per mel segment
+  int t_nw;           // warps per CTA: 16 (one CTA per SM) or 8 (two CTAs per SM)
+  int lm_stride;      // tiles path: lm is [n_mels][lm_stride] (transposed), lm_stride >= total frames
+  const float4* cep_blob;   // cepstra tables (global)
+  int cep_off_col;    // cepstra_t_kernel: shared-memory offset (floats) of the [n_mels][128] log-mel column buffer
 };
 
 cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_bytes, int cep_smem_bytes, int max_frames,
                                cudaStream_t stream);
+cudaError_t launch_frame_prefix(const FParams& fp, cudaStream_t stream);          // frames_kernel.cu
+cudaError_t launch_tiles_path(const FParams& fp, int sm_count, int tile_smem_bytes, int cep_smem_bytes, int max_frames,
+                              cudaStream_t stream);                              // tile_kernel.cu
 
 // host-side launcher (mfcc_kernel.cu)
 cudaError_t launch_mfcc(const KParams& kp, int smem_bytes, cudaStream_t stream);
@@ -156,6 +175,14 @@ struct asr_plan {
       fr_off_refs;
   int fr_n_refs, fr_s_pitch, fr_xb_stride, fr_lm_pitch;
   int cep_blob_f4, cep_tab_f4, cep_off_cbuf, cep_off_taps, cep_smem_bytes;
+  // ---- tiles path (n_fft = 512, TMA staging): tables; tl_ok = 0 -> not available for this plan ----
+  int tl_ok;
+  struct TileTables {   // one set per kernel shape (index 0: 16 warps, 1: 8 warps): the mel steps are dealt out differently
+    float* blob_dev;
+    int blob_f4;        // common tables, copied to shared memory; the two windows follow in the global blob
+    int off_window, off_window_i16, off_twp, off_twu, off_wtab, off_steps, off_wrange;
+    int npc, npart, nsteps;
+  } tl[2];
   // plan-owned workspace for callers that pass none (grown on demand; not safe for concurrent launches)
   void* ws_dev;
   size_t ws_bytes;

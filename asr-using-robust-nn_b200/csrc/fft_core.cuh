@@ -60,10 +60,10 @@ __host__ __device__ constexpr int brev(int i) {
 // In-register radix-2 decimation-in-time DFT of P complex points (P <= 32).
 // Input in bit-reversed order, output in natural order.  Non-trivial butterflies use the
 // 6-FMA form  a' = a + w*b ; b' = 2a - a'.
-template <int P>
-__device__ __forceinline__ void dft_dit(float (&re)[P], float (&im)[P]) {
+template <int P, int M0 = 2>   // M0 = 4: the first stage (m = 2) has already been applied
+__device__ __forceinline__ void dft_dit_from(float (&re)[P], float (&im)[P]) {
 #pragma unroll
-  for (int m = 2; m <= P; m *= 2) {
+  for (int m = M0; m <= P; m *= 2) {
     const int h = m / 2;
 #pragma unroll
     for (int g = 0; g < P; g += m) {
@@ -92,6 +92,9 @@ __device__ __forceinline__ void dft_dit(float (&re)[P], float (&im)[P]) {
     }
   }
 }
+
+template <int P>
+__device__ __forceinline__ void dft_dit(float (&re)[P], float (&im)[P]) { dft_dit_from<P, 2>(re, im); }
 
 template <int NFFT> struct FftCfg;
 template <> struct FftCfg<512>  { static constexpr int M = 256,  G = 16, P = 16; };

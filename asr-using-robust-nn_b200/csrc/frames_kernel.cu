@@ -25,6 +25,7 @@
 #include <cstring>
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "sample_access.cuh"
 
 namespace asr {
 
@@ -49,102 +50,66 @@ __device__ __forceinline__ void atomic_max_float(float* addr, const float v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// T_b, status, exclusive prefix sum of T_b over the clips (single CTA; thread t owns a contiguous chunk).
+// T_b, status, exclusive prefix sum of T_b over the clips.  Single CTA; clips are taken in groups of 8 x 1024 with
+// coalesced, independent loads (thread t <-> clips base + 1024*c + t), one block-wide scan per 1024 clips.
 __global__ void __launch_bounds__(1024) frame_prefix_kernel(const FParams fp) {
-  __shared__ int s_sum[64 + 1024];
-  const int tid = threadIdx.x;
-  const int per = (fp.n_clips + 1023) / 1024;
-  const int lo = min(fp.n_clips, tid * per), hi = min(fp.n_clips, lo + per);
-  int local = 0;
-  for (int b = lo; b < hi; ++b) {
-    const int L = fp.lengths[b];
-    const long long padded = static_cast<long long>(L) + 2 * fp.pad;
-    int T = padded < fp.n_fft ? 0 : static_cast<int>(1 + (padded - fp.n_fft) / fp.hop);
-    int st = ASR_CLIP_OK;
-    if (T <= 0 || (fp.pad_mode == ASR_PAD_REFLECT && fp.pad > 0 && L <= fp.pad) || (fp.preemph != 0.0f && L < 2))
-      st = ASR_CLIP_TOO_SHORT;
-    else if (fp.delta_orders > 0 && !fp.logmel_only && T < fp.delta_width)
-      st = ASR_CLIP_TOO_FEW_FRAMES;
-    if (st != ASR_CLIP_OK) T = 0;
-    if (fp.status) fp.status[b] = st;
-    fp.clipmax[b] = __int_as_float(0xff800000);
-    fp.nframes[b] = T;
-    local += T;
-  }
-  // inclusive scan of the 1024 chunk sums: within warps by shuffles, then over the 32 warp totals
-  const int lane = tid & 31, warp = tid >> 5;
-  int inc = local;
+  __shared__ int s_w[8][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int carry = 0;
+  for (int base = 0; base < fp.n_clips; base += 8 * 1024) {
+    int T[8], inc[8];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
-  }
-  if (lane == 31) s_sum[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    int w = s_sum[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
+    for (int c = 0; c < 8; ++c) {
+      const int b = base + 1024 * c + tid;
+      T[c] = 0;
+      if (b < fp.n_clips) {
+        const int L = fp.lengths[b];
+        const long long padded = static_cast<long long>(L) + 2 * fp.pad;
+        int t = padded < fp.n_fft ? 0 : static_cast<int>(1 + (padded - fp.n_fft) / fp.hop);
+        int st = ASR_CLIP_OK;
+        if (t <= 0 || (fp.pad_mode == ASR_PAD_REFLECT && fp.pad > 0 && L <= fp.pad) || (fp.preemph != 0.0f && L < 2))
+          st = ASR_CLIP_TOO_SHORT;
+        else if (fp.delta_orders > 0 && !fp.logmel_only && t < fp.delta_width)
+          st = ASR_CLIP_TOO_FEW_FRAMES;
+        if (st != ASR_CLIP_OK) t = 0;
+        if (fp.status) fp.status[b] = st;
+        fp.clipmax[b] = __int_as_float(0xff800000);
+        fp.nframes[b] = t;
+        T[c] = t;
+      }
     }
-    s_sum[32 + lane] = w;                       // inclusive totals of the warps
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                // inclusive scans inside the warps
+      int v = T[c];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      inc[c] = v;
+      if (lane == 31) s_w[c][warp] = v;
+    }
+    __syncthreads();
+    if (warp < 8) {                              // warp c scans the 32 warp totals of chunk c
+      int v = s_w[warp][lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      s_w[warp][lane] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int b = base + 1024 * c + tid;
+      const int before = carry + (warp > 0 ? s_w[c][warp - 1] : 0) + inc[c] - T[c];
+      if (b < fp.n_clips) fp.fstart[b] = before;
+      carry += s_w[c][31];
+    }
+    __syncthreads();                             // s_w is rewritten by the next group
   }
-  __syncthreads();
-  inc += warp > 0 ? s_sum[32 + warp - 1] : 0;
-  s_sum[64 + tid] = inc;                        // (only the last entry is read back below)
-  int run = inc - local;
-  for (int b = lo; b < hi; ++b) {
-    fp.fstart[b] = run;
-    run += fp.nframes[b];
-  }
-  if (tid == 1023) fp.fstart[fp.n_clips] = inc;
-}
-
-// ------------------------------------------------------------------------------------------------
-// sample decode (+ additive noise, float64 with two roundings) at GLOBAL element index i
-template <int DT>
-__device__ __forceinline__ float clean_at(const FParams& fp, const long long i) {
-  if (DT == ASR_I16) return static_cast<float>(__ldg(reinterpret_cast<const short*>(fp.audio) + i)) * (1.0f / 32768.0f);
-  if (DT == ASR_F32) return __ldg(reinterpret_cast<const float*>(fp.audio) + i);
-  return static_cast<float>(__ldg(reinterpret_cast<const double*>(fp.audio) + i));
-}
-
-template <int DT>
-__device__ __forceinline__ float value_at(const FParams& fp, const long long i, const double sig) {
-  if (fp.noise_mode == ASR_NOISE_NONE) return clean_at<DT>(fp, i);
-  double xd;
-  if (DT == ASR_F64) xd = __ldg(reinterpret_cast<const double*>(fp.audio) + i);
-  else xd = static_cast<double>(clean_at<DT>(fp, i));
-  double nz;
-  if (fp.noise_mode == ASR_NOISE_WHITE) {
-    nz = __dmul_rn(sig, __ldg(fp.z + i));
-  } else {
-    const double sel = (fabs(__ldg(fp.z + i)) < fp.mix_p) ? fp.mix_s1 : fp.mix_s0;
-    nz = __dmul_rn(sel, __ldg(fp.z2 + i));
-  }
-  return static_cast<float>(__dadd_rn(xd, nz));
-}
-
-// signal at ORIGINAL index o of the clip after [noise] and [pre-emphasis]
-template <int DT>
-__device__ __forceinline__ float signal_at(const FParams& fp, const long long base, const int o, const double sig) {
-  const float x = value_at<DT>(fp, base + o, sig);
-  if (fp.preemph == 0.0f) return x;
-  if (o > 0) return __fadd_rn(x, __fmul_rn(-fp.preemph, value_at<DT>(fp, base + o - 1, sig)));
-  // librosa.effects.preemphasis: lfilter state zi = 2*y[0]-y[1]  ->  out[0] = y[0] + zi
-  const float y1 = value_at<DT>(fp, base + 1, sig);
-  return __fadd_rn(x, __fadd_rn(2.0f * x, -y1));
-}
-
-// signal at padded position p (reflect / zero padding)
-template <int DT>
-__device__ __forceinline__ float padded_at(const FParams& fp, const long long base, const int L, const int p,
-                                           const double sig) {
-  int o = p - fp.pad;
-  if (o < 0) { if (fp.pad_mode != ASR_PAD_REFLECT) return 0.0f; o = -o; }
-  else if (o >= L) { if (fp.pad_mode != ASR_PAD_REFLECT) return 0.0f; o = 2 * (L - 1) - o; }
-  return signal_at<DT>(fp, base, o, sig);
+  if (tid == 0) fp.fstart[fp.n_clips] = carry;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -934,10 +899,14 @@ static cudaError_t launch_cep_n(const FParams& fp, dim3 grid, int smem_bytes, cu
   return cudaGetLastError();
 }
 
+cudaError_t launch_frame_prefix(const FParams& fp, cudaStream_t stream) {
+  frame_prefix_kernel<<<1, 1024, 0, stream>>>(fp);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_bytes, int cep_smem_bytes, int max_frames,
                                cudaStream_t stream) {
-  frame_prefix_kernel<<<1, 1024, 0, stream>>>(fp);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_frame_prefix(fp, stream);
   if (e != cudaSuccess) return e;
   if (fp.async_stage) {
     switch (fp.dtype) {

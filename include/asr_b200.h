@@ -153,14 +153,22 @@ int asr_mfcc_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, c
 
 /* Bytes of scratch the two entry points above/below need for such a batch (0: none needed). */
 size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips, int32_t max_length);
-/* Kernel path of asr_mfcc_batch / asr_logmel_batch.  Two implementations exist for n_fft = 512 with an even hop:
+/* Kernel path of asr_mfcc_batch / asr_logmel_batch.  Three implementations exist for n_fft = 512:
  *   ASR_PATH_CLIP    one CTA (or cluster) per clip, everything in one launch (the only path for other n_fft);
- *   ASR_PATH_FRAMES  block-pipelined: frame prefix -> frames (persistent, all clips' frames as one list) -> cepstra.
- * ASR_PATH_AUTO (default) takes FRAMES when noise is fused into the launch (each sample and its noise are then
- * read and mixed once instead of once per overlapping frame) and CLIP otherwise.  Tests force either path. */
-typedef enum asr_path { ASR_PATH_AUTO = 0, ASR_PATH_CLIP = 1, ASR_PATH_FRAMES = 2 } asr_path;
+ *   ASR_PATH_FRAMES  block-pipelined: frame prefix -> frames (persistent, all clips' frames as one list) -> cepstra;
+ *                    samples staged through registers or cp.async (any even hop, pre-emphasis, mixture noise);
+ *   ASR_PATH_TILES   the same pipeline with the raw samples (and their float64 noise) brought in by TMA bulk copies
+ *                    (cp.async.bulk + mbarrier), a transposed log-mel workspace and the clip maximum taken by the
+ *                    cepstra kernel; needs hop and n_fft/2 multiples of 8, no pre-emphasis, no mixture noise and
+ *                    16-byte aligned arrays (clips that do not start on a 16-byte boundary are staged from global memory).
+ * ASR_PATH_AUTO (default) takes TILES when its conditions hold, else FRAMES when noise is fused into the launch
+ * (each sample and its noise are then read and mixed once instead of once per overlapping frame), else CLIP.
+ * Tests force every path. */
+typedef enum asr_path { ASR_PATH_AUTO = 0, ASR_PATH_CLIP = 1, ASR_PATH_FRAMES = 2, ASR_PATH_TILES = 3 } asr_path;
 int asr_plan_set_path(asr_plan* plan, int32_t path);
-/* Kernel launches one asr_mfcc_batch call makes with this plan: 1 (CLIP) or 3 (FRAMES); `noisy` as in the call. */
+/* Path a call with 16-byte aligned arrays of `dtype` and noise mode `noise_mode` takes (ASR_PATH_CLIP/FRAMES/TILES). */
+int32_t asr_plan_path_used(const asr_plan* plan, int32_t dtype, int32_t noise_mode);
+/* Kernel launches one asr_mfcc_batch call makes with this plan: 1 (CLIP) or 3 (FRAMES, TILES); `noisy` as in the call. */
 int32_t asr_plan_launches(const asr_plan* plan, int32_t noisy);
 
 /* Stage-level probe for parity tests: the clamped log-mel matrix [n_clips][n_mels][out_frames] (float32). */

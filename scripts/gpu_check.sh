@@ -24,6 +24,6 @@ if [ -z "$2" ]; then
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > $O/plain_$TAG.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?"
-$CMD > $O/plain2_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:mfcc -s 3 -c 1 -f -o $O/prof_$TAG $CMD > $O/ncu_full_$TAG.log 2>&1
+$CMD > $O/plain2_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"tile512|frames512|mfcc_kernel" -s 3 -c 1 -f -o $O/prof_$TAG $CMD > $O/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
 fi

@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: scripts/gpu_prof.sh <tag> <workload> [kernel regex]   -> launch list + one full capture
-TAG=$1; WL=$2; KR=${3:-frames512}
+TAG=$1; WL=$2; KR=${3:-tile512}
 O=gpurun_out
 CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
 $CMD > $O/plain_$TAG.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_list_$TAG.log 2>&1
