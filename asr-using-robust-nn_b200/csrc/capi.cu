@@ -275,34 +275,39 @@ static bool build_tile_tables(asr_plan* pl, int cfg, int n_vw, bool pair_equal, 
       share[w].push_back(st);
     }
   }
-  if (pair_equal)
-    for (int w = 0; w < 16; w += 2) {
-      const size_t n = std::max(share[w].size(), share[w + 1].size());
-      share[w].resize(n, Step{0, -1, 0, 0});
-      share[w + 1].resize(n, Step{0, -1, 0, 0});
-    }
+  (void)pair_equal;
   int npc = 1;
   for (int sg = 0; sg <= n_mels; ++sg) npc = std::max(npc, n_pieces[sg]);
   if (npc > kTlMaxPieces) return true;
+  // per virtual warp a list of pieces (int4: byte offset of the first float4 in the S row, steps, byte offset of the
+  // fall partial row, index of the first weight float4); the steps of a piece read consecutive float4 of the row
   std::vector<float> wtab;
   std::vector<int> stab, wrange(2 * 16, 0);
   for (int w = 0; w < 16; ++w) {
-    wrange[2 * w] = static_cast<int>(stab.size() / 2);
-    wrange[2 * w + 1] = static_cast<int>(share[w].size());
-    for (const Step& st : share[w]) {
+    wrange[2 * w] = static_cast<int>(stab.size() / 4);
+    int n_pc = 0;
+    for (size_t i = 0; i < share[w].size(); ++i) {
+      const Step& st = share[w][i];
+      if (i == 0 || share[w][i - 1].last) {               // a piece starts here
+        stab.push_back(16 * st.q);
+        stab.push_back(0);
+        stab.push_back((st.seg * npc + st.piece) * 2 * fr * 4);
+        stab.push_back(static_cast<int>(wtab.size() / 4));
+        ++n_pc;
+      }
+      stab[stab.size() - 3] += 1;
       for (int e = 0; e < 4; ++e) {
         const int k = 4 * st.q + e;
-        const bool in = st.seg >= 0 && k < n_bins && seg[k] == st.seg;
+        const bool in = k < n_bins && seg[k] == st.seg;
         wtab.push_back(in ? 0.25f * W(st.seg - 1, k) : 0.0f);       // the spectrum row of this path holds 4|X|^2 (exact scaling)
         wtab.push_back(in ? 0.25f * W(st.seg, k) : 0.0f);
       }
-      stab.push_back(16 * st.q);                                                  // byte offset inside the spectrum row
-      stab.push_back(st.last ? (st.seg * npc + st.piece) * 2 * fr * 4 : -1);      // byte offset of the (fall) partial row
     }
+    wrange[2 * w + 1] = n_pc;
   }
   tt.npc = npc;
   tt.npart = (n_mels + 1) * npc * 2;
-  tt.nsteps = static_cast<int>(stab.size() / 2);
+  tt.nsteps = static_cast<int>(stab.size() / 4);
   std::vector<float> blob;
   auto put_f = [&](const float* src, size_t n) {
     const int off = static_cast<int>(blob.size());

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
   constexpr int esz = DT == ASR_I16 ? 2 : (DT == ASR_F32 ? 4 : 8);
   constexpr int kAsmWarp = kTlWarps - 1;            // assembles descriptors and issues the copies; takes no mel steps
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // the same value, known to be warp-uniform
 
   // ---- this CTA's range of the flattened frame list ----
   const int total = __ldg(fp.fstart + fp.n_clips);
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
   const float* s_twp = smem + fp.off_twp;
   const float2* s_twu = reinterpret_cast<const float2*>(smem + fp.off_twu);
   const float4* s_wtab = reinterpret_cast<const float4*>(smem + fp.off_wtab);
-  const int2* s_steps = reinterpret_cast<const int2*>(smem + fp.off_steps);
+  const int4* s_pieces = reinterpret_cast<const int4*>(smem + fp.off_steps);
   float* s_aud = smem + fp.sm_aud;
   float* s_S = smem + fp.sm_S;                       // [32 slots][kTlRS]
   float* s_part = smem + fp.sm_part;                 // [t_npart][32]
@@ -378,28 +379,33 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
       const char* pa = s_raw + q2.w - ra * esz;          // original sample o at pa + o*esz
       const char* pz = s_raw + q3.x - ra * 8;
       // a warp takes 128 consecutive samples per round: lane l the pairs at 2l and 64 + 2l
-      for (int i0 = 128 * warp + 2 * lane; i0 < count; i0 += 128 * kTlWarps) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int i = i0 + 64 * h;
+      for (int c0 = 128 * warp_u; c0 < count; c0 += 128 * kTlWarps) {
+        const int og = o0 + c0;                         // original index of the round's first sample
+        if (og >= 0 && og + 128 <= L && c0 + 128 <= count) {       // (warp-uniform) all 128 samples inside the clip
+          const char* qa = pa + (og + 2 * lane) * esz;
+          const char* qz = pz + (og + 2 * lane) * 8;
+          const float2 v0 = convert2<DT, NOISE>(qa, qz, sig);
+          const float2 v1 = convert2<DT, NOISE>(qa + 64 * esz, qz + 512, sig);
+          float2* qd = reinterpret_cast<float2*>(dst + c0) + lane;
+          qd[0] = v0;
+          qd[32] = v1;
+          continue;
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {                   // clip edges and the last round of the run
+          const int i = c0 + 64 * h + 2 * lane;
           if (i < count) {
             const int orig = o0 + i;
-            float2 v;
-            if (orig >= 0 && orig + 2 <= L) {
-              v = convert2<DT, NOISE>(pa + orig * esz, pz + orig * 8, sig);
-            } else {                                    // reflect / zero padding at the clip edges
-              float e[2];
+            float e[2];
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                int o = orig + j;
-                bool zero = false;
-                if (o < 0) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = -o; }
-                else if (o >= L) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = 2 * (L - 1) - o; }
-                e[j] = zero ? 0.0f : convert1<DT, NOISE>(pa, pz, o, sig);
-              }
-              v = make_float2(e[0], e[1]);
+            for (int j = 0; j < 2; ++j) {
+              int o = orig + j;
+              bool zero = false;
+              if (o < 0) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = -o; }
+              else if (o >= L) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = 2 * (L - 1) - o; }
+              e[j] = zero ? 0.0f : convert1<DT, NOISE>(pa, pz, o, sig);
             }
-            *reinterpret_cast<float2*>(dst + i) = v;
+            *reinterpret_cast<float2*>(dst + i) = make_float2(e[0], e[1]);
           }
         }
       }
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
   const int fft_slot = fft_slot0 + 4 * fft_h;
   float* const fft_buf = s_S + fft_slot * kTlRS;
   const int fr = tid & (kTlBlock - 1), vw = tid / kTlBlock;      // frame slot and "virtual warp" of the mel / combine phases
-  const int2 mel_range = reinterpret_cast<const int2*>(smem + fp.off_wrange)[vw];   // (first step, steps); equal counts within a warp
+  const int2 mel_range = reinterpret_cast<const int2*>(smem + fp.off_wrange)[vw];   // (first piece, pieces)
   const float4* mel_S = reinterpret_cast<const float4*>(s_S + fr * kTlRS);
   const int npc = fp.t_npc;
   float* const lm_fr = fp.lm + fr;
@@ -463,27 +469,28 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
     if (fft_slot0 < cur.n_slots)
       tile_fft512(reinterpret_cast<const float2*>(s_aud + cur.slot_aud[fft_slot]), s_win2, s_twp, s_twu, fft_buf, fft_l);
     __syncthreads();
-    // ---- mel (block it): lanes <-> frames, this virtual warp's steps ----
+    // ---- mel (block it): lanes <-> frames, this virtual warp's pieces ----
     {
-      float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
-      const int2* sp = s_steps + mel_range.x;
-      const float4* wp = s_wtab + 2 * mel_range.x;
+      const int4* pp = s_pieces + mel_range.x;
       const char* Sb = reinterpret_cast<const char*>(mel_S);
-#pragma unroll 2
-      for (int n = mel_range.y; n > 0; --n, ++sp, wp += 2) {
-        const int2 st = *sp;                           // (byte offset of the 4 bins in the S row, byte offset of the partial row to flush into or -1)
-        const float4 sv = *reinterpret_cast<const float4*>(Sb + st.x);
-        const float4 w01 = wp[0], w23 = wp[1];         // (fall, rise) of bins 0,1 and 2,3
-        a0 = fmaf(w01.x, sv.x, a0); b0 = fmaf(w01.y, sv.x, b0);
-        a1 = fmaf(w01.z, sv.y, a1); b1 = fmaf(w01.w, sv.y, b1);
-        a0 = fmaf(w23.x, sv.z, a0); b0 = fmaf(w23.y, sv.z, b0);
-        a1 = fmaf(w23.z, sv.w, a1); b1 = fmaf(w23.w, sv.w, b1);
-        if (st.y >= 0) {
-          float* pr = reinterpret_cast<float*>(const_cast<char*>(part_fr) + st.y);
-          pr[0] = a0 + a1;                             // falling slope of filter seg-1
-          pr[kTlBlock] = b0 + b1;                      // rising slope of filter seg
-          a0 = a1 = b0 = b1 = 0.0f;
+#pragma unroll 1
+      for (int n = mel_range.y; n > 0; --n, ++pp) {
+        const int4 pc = *pp;                           // (byte offset of the first 4 bins in the S row, steps, byte offset of the fall partial row, first weight float4)
+        const float4* sq = reinterpret_cast<const float4*>(Sb + pc.x);
+        const float4* wp = s_wtab + pc.w;
+        float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+#pragma unroll 1
+        for (int k = 0; k < pc.y; ++k) {
+          const float4 sv = sq[k];
+          const float4 w01 = wp[2 * k], w23 = wp[2 * k + 1];   // (fall, rise) of bins 0,1 and 2,3
+          a0 = fmaf(w01.x, sv.x, a0); b0 = fmaf(w01.y, sv.x, b0);
+          a1 = fmaf(w01.z, sv.y, a1); b1 = fmaf(w01.w, sv.y, b1);
+          a0 = fmaf(w23.x, sv.z, a0); b0 = fmaf(w23.y, sv.z, b0);
+          a1 = fmaf(w23.z, sv.w, a1); b1 = fmaf(w23.w, sv.w, b1);
         }
+        float* pr = reinterpret_cast<float*>(const_cast<char*>(part_fr) + pc.z);
+        pr[0] = a0 + a1;                               // falling slope of filter seg-1
+        pr[kTlBlock] = b0 + b1;                        // rising slope of filter seg
       }
     }
     // ---- convert (block it+1) ----
