@@ -348,8 +348,8 @@ static bool build_tile_tables_all(asr_plan* pl, const std::vector<double>& mel_f
   const asr_mfcc_params& p = pl->prm;
   pl->tl_ok = 0;
   if (!pl->fr_ok || (p.hop_length % 8) != 0 || (pl->pad % 8) != 0 || p.preemph != 0.0f) return true;
-  if (!build_tile_tables(pl, 0, 15, false, mel_f, fftfreqs, twp, twu)) return false;     // 16 warps, 32 frames per block
-  if (!build_tile_tables(pl, 1, 14, true, mel_f, fftfreqs, twp, twu)) return false;      // 8 warps, 16 frames per block
+  if (!build_tile_tables(pl, 0, 16, false, mel_f, fftfreqs, twp, twu)) return false;     // 16 main warps, 32 frames per block
+  if (!build_tile_tables(pl, 1, 16, true, mel_f, fftfreqs, twp, twu)) return false;      // 8 main warps, 16 frames per block
   pl->tl_ok = (pl->tl[0].blob_dev && pl->tl[1].blob_dev) ? 1 : 0;
   return true;
 }
@@ -666,7 +666,7 @@ bool frames_layout(const asr_plan* plan, int dtype, int noise_mode, bool aligned
   }
   return false;
 }
-struct TlLayout { int sm_aud, sm_S, sm_part, sm_raw, max_runs, smem_bytes, nw, cfg; };
+struct TlLayout { int sm_aud, sm_S, sm_part, sm_raw, max_runs, smem_bytes, nw, cfg, aud_cap; };
 // Shared-memory layout of the tile kernel: tables | window | frame samples of one block | FR slots (exchange buffer /
 // spectrum row) | mel partial rows | raw bytes of the block being copied in.  The 8-warp shape (two CTAs per SM) is taken
 // when two such CTAs fit one SM, else the 16-warp shape.
@@ -683,7 +683,8 @@ bool tiles_layout(const asr_plan* plan, int dtype, int noise_mode, TlLayout* lo)
     for (int runs = kTlMaxRuns; runs >= 2; --runs) {
       long long off = 4LL * tt.blob_f4 + 512;
       const long long aud_cap = round4(fr * hop + runs * (512 - std::min(hop, 512)) + 4 * runs + 8);
-      lo->sm_aud = static_cast<int>(off); off += aud_cap;
+      lo->sm_aud = static_cast<int>(off); off += 2 * aud_cap;       // two sample buffers: block i is transformed while i+1 is converted
+      lo->aud_cap = static_cast<int>(aud_cap);
       lo->sm_S = static_cast<int>(off); off += fr * kTlRS;
       lo->sm_part = static_cast<int>(off); off += tt.npart * fr;
       lo->sm_raw = static_cast<int>(off);
@@ -831,12 +832,11 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.top_db = p.top_db; fp.amin = p.amin; fp.preemph = p.preemph;
     const asr_plan::TileTables& tt = plan->tl[tlo.cfg];
     fp.blob = reinterpret_cast<const float4*>(tt.blob_dev); fp.blob_f4 = tt.blob_f4;
-    const bool unscaled_i16 = dtype == ASR_I16 && kp.noise_mode == ASR_NOISE_NONE;   // staged unscaled, 2^-15 in the window
-    fp.off_window = unscaled_i16 ? tt.off_window_i16 : tt.off_window;
+    fp.off_window = dtype == ASR_I16 ? tt.off_window_i16 : tt.off_window;   // int16 is staged unscaled, 2^-15 in the window
     fp.off_twp = tt.off_twp; fp.off_twu = tt.off_twu; fp.off_wtab = tt.off_wtab;
     fp.off_steps = tt.off_steps; fp.off_wrange = tt.off_wrange;
     fp.sm_aud = tlo.sm_aud; fp.sm_S = tlo.sm_S; fp.sm_part = tlo.sm_part; fp.sm_raw = tlo.sm_raw;
-    fp.max_runs = tlo.max_runs; fp.vec_ok = 1;
+    fp.max_runs = tlo.max_runs; fp.vec_ok = 1; fp.aud_cap = tlo.aud_cap;
     fp.t_npart = tt.npart; fp.t_npc = tt.npc; fp.t_nw = tlo.nw;
     fp.fstart = reinterpret_cast<int*>(ws + wl.off_fstart);
     fp.nframes = reinterpret_cast<int*>(ws + wl.off_nframes);

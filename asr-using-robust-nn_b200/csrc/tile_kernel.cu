@@ -27,6 +27,7 @@
 
 namespace asr {
 
+constexpr int kTlHelpDiv = 16;    // helper threads per main warp: 8 -> NW/4 helper warps, 16 -> NW/2
 constexpr int kTlCache = 32;      // clips whose metadata the descriptor warp caches in shared memory
 constexpr int kTlRing = 4;        // block descriptors alive at once: i-1 (combine) .. i+2 (being assembled)
 
@@ -88,59 +89,52 @@ __device__ __forceinline__ float tl_log2(const float x) {     // x >= amin > 0
 // ------------------------------------------------------------------------------------------------
 // 2 consecutive samples from the raw copy -> float32 frame samples (lanes take consecutive pairs: every shared-memory
 // access of the conversion is a dense, conflict-free row).
-// Clean int16 stays UNSCALED (the window table carries the exact 2^-15): bits(2^23 + (s + 32768)) - (2^23 + 32768) = s.
-// Noisy int16: s -> float64 exactly through the mantissa of 2^52, then fma(s, 2^-15, sigma*z): the product s*2^-15 is
-// exact, so this is float64(x) + (sigma*z) with the reference's two roundings.
+// int16 stays UNSCALED (the window table carries the exact 2^-15): bits(2^23 + (s + 32768)) - (2^23 + 32768) = s.
+// Noise: the frame sample is float32 anyway, so int16 / float32 audio is mixed in float32 with one rounding,
+// fma(float(z), sigma, x) - within 1.5 float32 ulp of rounding the reference's float64 x + sigma*z (the standalone mix
+// kernels, whose OUTPUT is the float64 signal, keep the two float64 roundings of VDR/attacks.py:84-85,241-244 bit for bit).
+// float64 audio is mixed in float64.  `sigf` = sigma (x 2^15 for int16).
 template <int DT, bool NOISE>
-__device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const char* __restrict__ pz, const double sig) {
-  double x0, x1;
+__device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const char* __restrict__ pz, const double sig, const float sigf) {
+  float2 v;
   if constexpr (DT == ASR_I16) {
     const unsigned w = *reinterpret_cast<const unsigned*>(pa) ^ 0x80008000u;
-    if constexpr (!NOISE) {
-      return make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8421376.0f,
-                         __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8421376.0f);
-    } else {
-      x0 = __hiloint2double(0x43300000, static_cast<int>(w & 0xffffu)) - 4503599627403264.0;
-      x1 = __hiloint2double(0x43300000, static_cast<int>(w >> 16)) - 4503599627403264.0;
-      const double2 z = *reinterpret_cast<const double2*>(pz);
-      return make_float2(static_cast<float>(__fma_rn(x0, 1.0 / 32768.0, __dmul_rn(sig, z.x))),
-                         static_cast<float>(__fma_rn(x1, 1.0 / 32768.0, __dmul_rn(sig, z.y))));
-    }
+    v.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8421376.0f;
+    v.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8421376.0f;
   } else if constexpr (DT == ASR_F32) {
-    const float2 a = *reinterpret_cast<const float2*>(pa);
-    if constexpr (!NOISE) return a;
-    x0 = static_cast<double>(a.x); x1 = static_cast<double>(a.y);
+    v = *reinterpret_cast<const float2*>(pa);
   } else {
     const double2 a = *reinterpret_cast<const double2*>(pa);
-    x0 = a.x; x1 = a.y;
-    if constexpr (!NOISE) return make_float2(static_cast<float>(x0), static_cast<float>(x1));
+    if constexpr (NOISE) {
+      const double2 z = *reinterpret_cast<const double2*>(pz);
+      return make_float2(static_cast<float>(__dadd_rn(a.x, __dmul_rn(sig, z.x))), static_cast<float>(__dadd_rn(a.y, __dmul_rn(sig, z.y))));
+    }
+    return make_float2(static_cast<float>(a.x), static_cast<float>(a.y));
   }
-  if constexpr (NOISE && DT != ASR_I16) {
+  if constexpr (NOISE) {
     const double2 z = *reinterpret_cast<const double2*>(pz);
-    return make_float2(static_cast<float>(__dadd_rn(x0, __dmul_rn(sig, z.x))), static_cast<float>(__dadd_rn(x1, __dmul_rn(sig, z.y))));
+    v.x = fmaf(static_cast<float>(z.x), sigf, v.x);
+    v.y = fmaf(static_cast<float>(z.y), sigf, v.y);
   }
-  return make_float2(0.0f, 0.0f);                        // not reached
+  return v;
 }
 
 // one sample (clip edges): original index o, pa/pz point at original sample 0 of the raw copy
 template <int DT, bool NOISE>
-__device__ __forceinline__ float convert1(const char* __restrict__ pa, const char* __restrict__ pz, const int o, const double sig) {
+__device__ __forceinline__ float convert1(const char* __restrict__ pa, const char* __restrict__ pz, const int o, const double sig,
+                                          const float sigf) {
   float x;
-  double xd;
   if constexpr (DT == ASR_I16) {
-    const float s = static_cast<float>(reinterpret_cast<const short*>(pa)[o]);
-    if constexpr (!NOISE) return s;                             // unscaled
-    x = s * (1.0f / 32768.0f);
-    xd = static_cast<double>(x);
+    x = static_cast<float>(reinterpret_cast<const short*>(pa)[o]);          // unscaled
   } else if constexpr (DT == ASR_F32) {
     x = reinterpret_cast<const float*>(pa)[o];
-    xd = static_cast<double>(x);
   } else {
-    xd = reinterpret_cast<const double*>(pa)[o];
-    x = static_cast<float>(xd);
+    const double xd = reinterpret_cast<const double*>(pa)[o];
+    if constexpr (NOISE) return static_cast<float>(__dadd_rn(xd, __dmul_rn(sig, reinterpret_cast<const double*>(pz)[o])));
+    return static_cast<float>(xd);
   }
-  if constexpr (!NOISE) return x;
-  return static_cast<float>(__dadd_rn(xd, __dmul_rn(sig, reinterpret_cast<const double*>(pz)[o])));
+  if constexpr (NOISE) x = fmaf(static_cast<float>(reinterpret_cast<const double*>(pz)[o]), sigf, x);
+  return x;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -217,19 +211,23 @@ __device__ __forceinline__ void tile_fft512(const float2* __restrict__ xs2, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// NW warps per CTA, FR = 2*NW frames per block.  NW = 16: one CTA per SM; NW = 8: two CTAs per SM, whose phases drift apart
-// so that the FFT phase of one (FP32 issue slots) overlaps the mel / convert phase of the other (shared-memory pipe).
+// NW main warps per CTA (FFT, mel, combine; FR = 2*NW frames per block) + NW/4 helper warps (descriptors, TMA copies,
+// sample conversion into the other of two sample buffers), so that the conversion - shared-memory and conversion-pipe
+// work - runs beside the FFTs - FP32 issue slots - instead of between them.  NW = 16: one CTA per SM; NW = 8: two.
 template <int DT, bool NOISE, int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const __grid_constant__ FParams fp) {
+__global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) tile512_kernel(const __grid_constant__ FParams fp) {
   constexpr int kTlThreads = NW * 32, kTlBlock = 2 * NW, kTlWarps = NW;
+  constexpr int kHelpWarps = NW * kTlHelpDiv / 32, kAllThreads = kTlThreads + 32 * kHelpWarps;
   extern __shared__ __align__(16) float smem[];
   __shared__ TBlock ring[kTlRing];
   __shared__ TMeta s_meta[kTlCache];
   __shared__ __align__(8) unsigned long long s_bar;
   constexpr int esz = DT == ASR_I16 ? 2 : (DT == ASR_F32 ? 4 : 8);
-  constexpr int kAsmWarp = kTlWarps - 1;            // assembles descriptors and issues the copies; takes no mel steps
+  constexpr int kAsmWarp = kTlWarps;                // first helper warp: assembles descriptors and issues the copies
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // the same value, known to be warp-uniform
+  const bool helper = warp_u >= kTlWarps;
+  const int hw = warp_u - kTlWarps, ht = tid - kTlThreads;   // helper warp / thread index
 
   // ---- this CTA's range of the flattened frame list ----
   const int total = __ldg(fp.fstart + fp.n_clips);
@@ -243,7 +241,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
   // ---- tables: global blob -> shared (common tables, then the window that matches the staged sample scale) ----
   {
     float4* dst = reinterpret_cast<float4*>(smem);
-    for (int i = tid; i < fp.blob_f4; i += kTlThreads) dst[i] = __ldg(fp.blob + i);
+    for (int i = tid; i < fp.blob_f4; i += kAllThreads) dst[i] = __ldg(fp.blob + i);
     if (tid < 128) dst[fp.blob_f4 + tid] = __ldg(fp.blob + fp.off_window / 4 + tid);
   }
   const float2* s_win2 = reinterpret_cast<const float2*>(smem + 4 * fp.blob_f4);
@@ -251,11 +249,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
   const float2* s_twu = reinterpret_cast<const float2*>(smem + fp.off_twu);
   const float4* s_wtab = reinterpret_cast<const float4*>(smem + fp.off_wtab);
   const int4* s_pieces = reinterpret_cast<const int4*>(smem + fp.off_steps);
-  float* s_aud = smem + fp.sm_aud;
+  float* s_aud = smem + fp.sm_aud;                   // [2][aud_cap]
   float* s_S = smem + fp.sm_S;                       // [32 slots][kTlRS]
-  float* s_part = smem + fp.sm_part;                 // [t_npart][32]
+  float* s_part = smem + fp.sm_part;                 // [t_npart][FR]
   char* s_raw = reinterpret_cast<char*>(smem + fp.sm_raw);
-  for (int i = tid; i < fp.t_npart * kTlBlock; i += kTlThreads) s_part[i] = 0.0f;   // rows of pieces that do not exist stay 0
+  for (int i = tid; i < fp.t_npart * kTlBlock; i += kAllThreads) s_part[i] = 0.0f;   // rows of pieces that do not exist stay 0
   if (tid == 0) mbar_init(&s_bar, 1);
 
   // ---- block cursor (warp kAsmWarp; lane 0 holds the live copy) ----
@@ -362,30 +360,31 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
     if (lane == 0) mbar_arrive_expect_tx(&s_bar, static_cast<unsigned>(blk.tx_bytes));
   };
   // raw -> float32 frame samples of a block, once per sample
-  const float scale = (DT == ASR_I16 && !NOISE) ? 32768.0f : 1.0f;   // slow path only: clean int16 is staged unscaled
-  auto convert_block = [&](const TBlock& blk) {
+  const float scale = DT == ASR_I16 ? 32768.0f : 1.0f;   // int16 is staged unscaled (the slow path computes scaled values)
+  auto convert_block = [&](const TBlock& blk, float* aud) {       // helper warps
     const int nr = blk.n_runs;
     for (int r = 0; r < nr; ++r) {
       const int4* rq = reinterpret_cast<const int4*>(&blk.run[r]);   // the descriptor in four 16-byte loads
       const int4 q0 = rq[0], q1 = rq[1], q2 = rq[2], q3 = rq[3];
       const long long base = (static_cast<long long>(q0.y) << 32) | static_cast<unsigned>(q0.x);
       const double sig = __hiloint2double(q0.w, q0.z);
+      const float sigf = static_cast<float>(sig * scale);
       const int L = q1.x, o0 = q1.y, count = q1.z, nu = q2.x, ra = q2.y;
-      float* dst = s_aud + q1.w;
+      float* dst = aud + q1.w;
       if (nu == 0) {                                    // clip not on a 16-byte boundary: sample by sample from global memory
-        for (int i = tid; i < count; i += kTlThreads) dst[i] = padded_at<DT>(fp, base, L, o0 + fp.pad + i, sig) * scale;
+        for (int i = ht; i < count; i += 32 * kHelpWarps) dst[i] = padded_at<DT>(fp, base, L, o0 + fp.pad + i, sig) * scale;
         continue;
       }
       const char* pa = s_raw + q2.w - ra * esz;          // original sample o at pa + o*esz
       const char* pz = s_raw + q3.x - ra * 8;
       // a warp takes 128 consecutive samples per round: lane l the pairs at 2l and 64 + 2l
-      for (int c0 = 128 * warp_u; c0 < count; c0 += 128 * kTlWarps) {
+      for (int c0 = 128 * hw; c0 < count; c0 += 128 * kHelpWarps) {
         const int og = o0 + c0;                         // original index of the round's first sample
         if (og >= 0 && og + 128 <= L && c0 + 128 <= count) {       // (warp-uniform) all 128 samples inside the clip
           const char* qa = pa + (og + 2 * lane) * esz;
           const char* qz = pz + (og + 2 * lane) * 8;
-          const float2 v0 = convert2<DT, NOISE>(qa, qz, sig);
-          const float2 v1 = convert2<DT, NOISE>(qa + 64 * esz, qz + 512, sig);
+          const float2 v0 = convert2<DT, NOISE>(qa, qz, sig, sigf);
+          const float2 v1 = convert2<DT, NOISE>(qa + 64 * esz, qz + 512, sig, sigf);
           float2* qd = reinterpret_cast<float2*>(dst + c0) + lane;
           qd[0] = v0;
           qd[32] = v1;
@@ -403,7 +402,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
               bool zero = false;
               if (o < 0) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = -o; }
               else if (o >= L) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = 2 * (L - 1) - o; }
-              e[j] = zero ? 0.0f : convert1<DT, NOISE>(pa, pz, o, sig);
+              e[j] = zero ? 0.0f : convert1<DT, NOISE>(pa, pz, o, sig, sigf);
             }
             *reinterpret_cast<float2*>(dst + i) = make_float2(e[0], e[1]);
           }
@@ -412,8 +411,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
     }
   };
 
+  // named barriers: 1 = main warps (between FFT and mel), 2 = helper warps; __syncthreads = everybody, once per block
+  auto bar_main = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kTlThreads) : "memory"); };
+  auto bar_help = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kHelpWarps) : "memory"); };
+
   // ---- prologue: descriptors of blocks 0 and 1, samples of block 0 ----
-  if (warp == kAsmWarp) {
+  if (warp_u == kAsmWarp) {
     int lo = 0, hi = fp.n_clips;                       // largest b with fstart[b] <= g_begin
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -428,13 +431,35 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
     assemble(ring[1]);
   }
   __syncthreads();                                     // tables, zeroed partials, mbarrier, descriptors 0 and 1
-  if (warp == kAsmWarp) issue_copies(ring[0]);
-  mbar_wait(&s_bar, 0);
-  convert_block(ring[0]);
+  if (helper) {
+    if (warp_u == kAsmWarp) issue_copies(ring[0]);
+    mbar_wait(&s_bar, 0);
+    convert_block(ring[0], s_aud);
+    bar_help();
+    if (warp_u == kAsmWarp && ring[1].n_slots > 0) issue_copies(ring[1]);
+  }
   __syncthreads();
-  if (warp == kAsmWarp && ring[1].n_slots > 0) issue_copies(ring[1]);
 
-  // ---- per-thread constants of the phases ----
+  if (helper) {
+    // ---- helper warps: block it+1 raw -> sample buffer (it+1)&1 while the main warps transform block it;
+    //      descriptor of block it+2, then its copies as soon as the raw buffer is free again ----
+    for (int it = 0;; ++it) {
+      if (ring[it & (kTlRing - 1)].n_slots == 0) break;
+      const TBlock& nxt = ring[(it + 1) & (kTlRing - 1)];
+      TBlock& nn = ring[(it + 2) & (kTlRing - 1)];
+      if (warp_u == kAsmWarp) assemble(nn);
+      if (nxt.n_slots > 0) {
+        mbar_wait(&s_bar, static_cast<unsigned>((it + 1) & 1));
+        convert_block(nxt, s_aud + ((it + 1) & 1) * fp.aud_cap);
+      }
+      bar_help();                                      // every helper is done with the raw buffer
+      if (warp_u == kAsmWarp && nn.n_slots > 0) issue_copies(nn);
+      __syncthreads();
+    }
+    return;
+  }
+
+  // ---- main warps: per-thread constants of the phases ----
   const int fft_h = lane >> 4, fft_l = lane & 15;
   const int fft_slot0 = 8 * (warp >> 2) + (warp & 3);            // half-warps 4 slots apart: complementary bank halves of S
   const int fft_slot = fft_slot0 + 4 * fft_h;
@@ -444,11 +469,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
   const float4* mel_S = reinterpret_cast<const float4*>(s_S + fr * kTlRS);
   const int npc = fp.t_npc;
   float* const lm_fr = fp.lm + fr;
-  const char* const part_fr = reinterpret_cast<const char*>(s_part + fr);
+  char* const part_fr = reinterpret_cast<char*>(s_part + fr);
 
   for (int it = 0;; ++it) {
     const TBlock& cur = ring[it & (kTlRing - 1)];
-    // ---- combine (block it-1): lanes <-> frames, warps <-> filters ----
+    // ---- combine (block it-1): lanes <-> frames, virtual warps <-> filters ----
     if (it > 0) {
       const TBlock& prv = ring[(it - 1) & (kTlRing - 1)];
       const int ns = prv.n_slots, g0 = prv.g0;
@@ -467,8 +492,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
     if (cur.n_slots == 0) break;                       // uniform over the CTA
     // ---- fft (block it) ----
     if (fft_slot0 < cur.n_slots)
-      tile_fft512(reinterpret_cast<const float2*>(s_aud + cur.slot_aud[fft_slot]), s_win2, s_twp, s_twu, fft_buf, fft_l);
-    __syncthreads();
+      tile_fft512(reinterpret_cast<const float2*>(s_aud + (it & 1) * fp.aud_cap + cur.slot_aud[fft_slot]), s_win2, s_twp, s_twu,
+                  fft_buf, fft_l);
+    bar_main();
     // ---- mel (block it): lanes <-> frames, this virtual warp's pieces ----
     {
       const int4* pp = s_pieces + mel_range.x;
@@ -488,22 +514,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) tile512_kernel(const
           a0 = fmaf(w23.x, sv.z, a0); b0 = fmaf(w23.y, sv.z, b0);
           a1 = fmaf(w23.z, sv.w, a1); b1 = fmaf(w23.w, sv.w, b1);
         }
-        float* pr = reinterpret_cast<float*>(const_cast<char*>(part_fr) + pc.z);
+        float* pr = reinterpret_cast<float*>(part_fr + pc.z);
         pr[0] = a0 + a1;                               // falling slope of filter seg-1
         pr[kTlBlock] = b0 + b1;                        // rising slope of filter seg
       }
     }
-    // ---- convert (block it+1) ----
-    const TBlock& nxt = ring[(it + 1) & (kTlRing - 1)];
-    if (nxt.n_slots > 0) {
-      mbar_wait(&s_bar, static_cast<unsigned>((it + 1) & 1));
-      convert_block(nxt);
-    }
-    // ---- descriptor of block it+2 ----
-    TBlock& nn = ring[(it + 2) & (kTlRing - 1)];
-    if (warp == kAsmWarp) assemble(nn);
     __syncthreads();
-    if (warp == kAsmWarp && nn.n_slots > 0) issue_copies(nn);
   }
 }
 
@@ -653,7 +669,7 @@ static cudaError_t launch_tile_nw(const FParams& fp, int sm_count, int smem_byte
     if (e != cudaSuccess) return e;
     granted = smem_bytes;
   }
-  tile512_kernel<DT, NOISE, NW><<<(NW == 8 ? 2 : 1) * sm_count, NW * 32, smem_bytes, stream>>>(fp);
+  tile512_kernel<DT, NOISE, NW><<<(NW == 8 ? 2 : 1) * sm_count, NW * 32 + NW * kTlHelpDiv, smem_bytes, stream>>>(fp);
   return cudaGetLastError();
 }
 template <int DT, bool NOISE>
