@@ -33,23 +33,7 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) colsum_partial_kernel(
   double a0 = 0.0, a1 = 0.0;
   if (c < n_cols) {
     const double m = CENTERED ? mean[c] : 0.0;
-    long long r = r0 + rl;
-    for (; r + 7 * kRowLanes < r1; r += 8 * kRowLanes) {     // eight loads in flight, added in the same (ascending) order
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = load_x(x, dtype, (r + u * kRowLanes) * ld + c);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (CENTERED) {
-          const double t = __dsub_rn(v[u], m);
-          a0 = __dadd_rn(a0, t);
-          a1 = __dadd_rn(a1, __dmul_rn(t, t));
-        } else {
-          a0 = __dadd_rn(a0, v[u]);
-        }
-      }
-    }
-    for (; r < r1; r += kRowLanes) {
+    for (long long r = r0 + rl; r < r1; r += kRowLanes) {
       const double v = load_x(x, dtype, r * ld + c);
       if (CENTERED) {
         const double t = __dsub_rn(v, m);

@@ -1,20 +1,24 @@
 // TMA-staged block pipeline for n_fft = 512 on sm_100a ("tiles" path): frame prefix -> tile512_kernel -> cepstra_t_kernel.
 //
-//   tile512_kernel   persistent, one 512-thread CTA per SM.  The frames of ALL clips form one flat list; a CTA owns a
-//                    contiguous range of it and walks it in blocks of 32 frames.  Per block:
-//                      copy     one thread issues cp.async.bulk (TMA) copies of the block's raw samples and of their
-//                               float64 noise into shared memory, two blocks ahead of the FFT; completion is an
-//                               mbarrier transaction count, nobody spends issue slots or registers on the loads
-//                      convert  raw -> float32 frame samples, ONCE per sample: dtype decode, [noise mix: x + sigma*z in
-//                               float64, two roundings, VDR/attacks.py:84-85,241-244], reflect / zero padding
-//                      fft      2 frames per warp: window, 256-point complex FFT in registers, unpack, |X|^2 -> S[slot][bin]
-//                               (the exchange buffer of a slot is reused as its spectrum row)
-//                      mel      lanes <-> frames, warps <-> bin ranges: a flat list of 4-bin steps, every bin feeds the
-//                               falling slope of one Slaney triangle and the rising slope of the next; partial sums per
-//                               (segment, piece) go to shared memory
-//                      combine  lanes <-> frames, warps <-> filters: partials -> 10*log10 -> lm[filter][flat frame]
-//                               (transposed: stores and the cepstra kernel's loads are coalesced along time)
-//                    Two __syncthreads per block: {fft(i), combine(i-1)} | {mel(i), convert(i+1), descriptors(i+2)}.
+//   tile512_kernel   persistent, one 768-thread CTA per SM.  The frames of ALL clips form one flat list; a CTA owns a
+//                    contiguous range of it and walks it in blocks of 32 frames.  Two kinds of warps:
+//                    8 HELPER warps (producer side, two blocks ahead of the FFT)
+//                      descriptors  which clips / frames make up block i+2, where their samples go
+//                      copy         one lane per run issues cp.async.bulk (TMA) copies of the block's raw samples and of
+//                                   their float64 noise into shared memory; completion is an mbarrier transaction count
+//                      convert      raw -> float32 frame samples of block i+1, ONCE per sample, into the other of two
+//                                   sample buffers: dtype decode, [noise mix], reflect / zero padding
+//                    16 MAIN warps
+//                      fft          2 frames per warp: window, 256-point complex FFT in registers, unpack, |X|^2 ->
+//                                   S[slot][bin] (the exchange buffer of a slot is reused as its spectrum row)
+//                      mel          lanes <-> frames, warps <-> bin ranges: pieces of mel segments, every bin feeds the
+//                                   falling slope of one Slaney triangle and the rising slope of the next; partial sums
+//                                   per (segment, piece) go to shared memory
+//                      combine      lanes <-> frames, warps <-> filters: partials -> 10*log10 -> lm[filter][flat frame]
+//                                   (transposed: stores and the cepstra kernel's loads are coalesced along time)
+//                    Per block: main {combine(i-1), fft(i)} | named barrier | {mel(i)} ; helpers {descriptors(i+2),
+//                    convert(i+1), copies(i+2)} ; one __syncthreads of all 24 warps.  The conversion (shared-memory and
+//                    conversion-pipe work) runs beside the FFTs (FP32 issue slots) instead of between them.
 //   cepstra_t_kernel per clip tile: clip maximum of the log-mel matrix (power_to_db's top_db clamp is clip-wide),
 //                    clamp, DCT-II (ortho) x lifter, [delta, delta-delta], truncate / zero-pad to out_frames.
 //

@@ -87,8 +87,11 @@ typedef struct asr_mfcc_params {
  *                                    (add_white_noise_with_snr, sigma[b] from the SNR chain)
  *   MIXTURE  x + (|q|<p ? s1:s0)*g   VDR/attacks.py:145-183 (mixtgauss / add_noise)
  * z / q / g are float64 standard-normal streams laid out like the audio (same offsets).
- * The mix is done in float64 with two separately rounded operations (no FMA), then
- * rounded once to float32 for the MFCC arithmetic.
+ * The MFCC arithmetic is float32, so the fused mix only has to deliver the float32 rounding of
+ * the reference's float64 signal: CLIP and FRAMES mix in float64 with two separately rounded
+ * operations (no FMA) and round once; TILES mixes int16 / float32 audio directly in float32,
+ * fma(float(z), sigma, x), within 1.5 float32 ulp of that.  The standalone asr_mix_* kernels,
+ * whose OUTPUT is the float64 noisy signal, are bit-exact.
  */
 typedef enum asr_noise_mode { ASR_NOISE_NONE = 0, ASR_NOISE_WHITE = 1, ASR_NOISE_MIXTURE = 2 } asr_noise_mode;
 
