@@ -15,15 +15,16 @@ constexpr int kColTile = 32;    // columns per block (one per lane: coalesced ro
 constexpr int kRowLanes = 8;    // row-parallel warps per block
 constexpr int kMaxSlabs = 512;
 
-__device__ __forceinline__ double load_x(const void* __restrict__ x, const int dtype, const long long i) {
-  if (dtype == ASR_F32) return static_cast<double>(__ldg(reinterpret_cast<const float*>(x) + i));
-  return __ldg(reinterpret_cast<const double*>(x) + i);
+template <int DT>   // ASR_F32 or ASR_F64, a template parameter so that batched loads are not separated by a dtype branch
+__device__ __forceinline__ double load_x(const void* __restrict__ x, const long long i) {
+  if constexpr (DT == ASR_F32) return static_cast<double>(__ldg(reinterpret_cast<const float*>(x) + i));
+  else return __ldg(reinterpret_cast<const double*>(x) + i);
 }
 
 // partial[(slab*2 + j)*n_cols + c] ; CENTERED: j=0 sum(x-mean), j=1 sum((x-mean)^2) ; else j=0 sum(x)
-template <bool CENTERED>
+template <bool CENTERED, int DT>
 __global__ void __launch_bounds__(kColTile * kRowLanes) colsum_partial_kernel(
-    const void* __restrict__ x, const int dtype, const long long n_rows, const int n_cols, const long long ld,
+    const void* __restrict__ x, const long long n_rows, const int n_cols, const long long ld,
     const double* __restrict__ mean, const long long rows_per_slab, double* __restrict__ partial) {
   __shared__ double s0[kRowLanes][kColTile], s1[kRowLanes][kColTile];
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -33,8 +34,24 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) colsum_partial_kernel(
   double a0 = 0.0, a1 = 0.0;
   if (c < n_cols) {
     const double m = CENTERED ? mean[c] : 0.0;
-    for (long long r = r0 + rl; r < r1; r += kRowLanes) {
-      const double v = load_x(x, dtype, r * ld + c);
+    long long r = r0 + rl;
+    for (; r + 7 * kRowLanes < r1; r += 8 * kRowLanes) {     // eight loads in flight, added in the same (ascending) order
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = load_x<DT>(x, (r + u * kRowLanes) * ld + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (CENTERED) {
+          const double t = __dsub_rn(v[u], m);
+          a0 = __dadd_rn(a0, t);
+          a1 = __dadd_rn(a1, __dmul_rn(t, t));
+        } else {
+          a0 = __dadd_rn(a0, v[u]);
+        }
+      }
+    }
+    for (; r < r1; r += kRowLanes) {
+      const double v = load_x<DT>(x, r * ld + c);
       if (CENTERED) {
         const double t = __dsub_rn(v, m);
         a0 = __dadd_rn(a0, t);
@@ -92,8 +109,9 @@ __global__ void cmvn_finalize_kernel(const double* __restrict__ acc2, const doub
 }
 
 // out[r][c] = (x[r][c] - mean[c]) / scale[c] in float64 (sklearn: X -= mean_; X /= scale_), thread <-> column.
+template <int DT>
 __global__ void __launch_bounds__(kColTile * kRowLanes) cmvn_apply_kernel(
-    const void* __restrict__ x, const int dtype, const long long n_rows, const int n_cols, const long long ld,
+    const void* __restrict__ x, const long long n_rows, const int n_cols, const long long ld,
     const double* __restrict__ mean, const double* __restrict__ scale, void* __restrict__ out, const int out_f64,
     const long long rows_per_slab) {
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -106,7 +124,7 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) cmvn_apply_kernel(
   for (; r + 3 * kRowLanes < r1; r += 4 * kRowLanes) {
     double v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = load_x(x, dtype, (r + u * kRowLanes) * ld + c);
+    for (int u = 0; u < 4; ++u) v[u] = load_x<DT>(x, (r + u * kRowLanes) * ld + c);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const double y = __ddiv_rn(__dsub_rn(v[u], m), sc);
@@ -116,7 +134,7 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) cmvn_apply_kernel(
     }
   }
   for (; r < r1; r += kRowLanes) {
-    const double y = __ddiv_rn(__dsub_rn(load_x(x, dtype, r * ld + c), m), sc);
+    const double y = __ddiv_rn(__dsub_rn(load_x<DT>(x, r * ld + c), m), sc);
     if (out_f64) reinterpret_cast<double*>(out)[r * n_cols + c] = y;
     else reinterpret_cast<float*>(out)[r * n_cols + c] = static_cast<float>(y);
   }
@@ -133,8 +151,11 @@ static int run_colsum(const void* x, int dtype, int64_t n_rows, int n_cols, int6
   slabs = (n_rows + rows_per_slab - 1) / rows_per_slab;
   double* partial = nullptr;
   ASR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * 2 * slabs * n_cols, st));
-  colsum_partial_kernel<CENTERED><<<dim3(col_blocks, static_cast<unsigned>(slabs)), kColTile * kRowLanes, 0, st>>>(
-      x, dtype, n_rows, n_cols, ld, mean, rows_per_slab, partial);
+  const dim3 grid(col_blocks, static_cast<unsigned>(slabs));
+  if (dtype == ASR_F32)
+    colsum_partial_kernel<CENTERED, ASR_F32><<<grid, kColTile * kRowLanes, 0, st>>>(x, n_rows, n_cols, ld, mean, rows_per_slab, partial);
+  else
+    colsum_partial_kernel<CENTERED, ASR_F64><<<grid, kColTile * kRowLanes, 0, st>>>(x, n_rows, n_cols, ld, mean, rows_per_slab, partial);
   ASR_CUDA_TRY(cudaGetLastError());
   colsum_final_kernel<<<(n_cols + 127) / 128, 128, 0, st>>>(partial, static_cast<int>(slabs), n_cols,
                                                            CENTERED ? 2 : 1, acc);
@@ -212,8 +233,13 @@ extern "C" int asr_cmvn_apply(const void* x_dev, int32_t dtype, int64_t n_rows, 
   int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((148 * 16 + col_blocks - 1) / col_blocks, (n_rows + 31) / 32));
   const int64_t rows_per_slab = (n_rows + slabs - 1) / slabs;
   slabs = (n_rows + rows_per_slab - 1) / rows_per_slab;
-  cmvn_apply_kernel<<<dim3(col_blocks, static_cast<unsigned>(slabs)), kColTile * kRowLanes, 0, as_stream(stream)>>>(
-      x_dev, dtype, n_rows, n_cols, ld, mean_dev, scale_dev, out_dev, out_dtype == ASR_F64, rows_per_slab);
+  const dim3 grid(col_blocks, static_cast<unsigned>(slabs));
+  if (dtype == ASR_F32)
+    cmvn_apply_kernel<ASR_F32><<<grid, kColTile * kRowLanes, 0, as_stream(stream)>>>(
+        x_dev, n_rows, n_cols, ld, mean_dev, scale_dev, out_dev, out_dtype == ASR_F64, rows_per_slab);
+  else
+    cmvn_apply_kernel<ASR_F64><<<grid, kColTile * kRowLanes, 0, as_stream(stream)>>>(
+        x_dev, n_rows, n_cols, ld, mean_dev, scale_dev, out_dev, out_dtype == ASR_F64, rows_per_slab);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }
