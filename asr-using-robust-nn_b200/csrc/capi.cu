@@ -218,6 +218,7 @@ static bool build_frames_tables(asr_plan* pl, const std::vector<double>& mel_f, 
   for (int c = 0; c < p.n_mfcc; ++c)
     for (int j = 0; j < n_mels; ++j) dct_t[static_cast<size_t>(j) * 4 * nc4 + c] = pl->h_dct[static_cast<size_t>(c) * n_mels + j];
   pl->cep_blob_f4 = pl->fr_blob_f4;
+  pl->h_dct_t = dct_t;
   const int dct_off = put_f(dct_t.data(), dct_t.size());
   const int taps_off = put_f(pl->h_taps.data(), pl->h_taps.size());
   pl->cep_tab_f4 = static_cast<int>(blob.size() / 4) - pl->cep_blob_f4;
@@ -847,6 +848,8 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.cep_blob = reinterpret_cast<const float4*>(plan->fr_blob_dev) + plan->cep_blob_f4;
     fp.cep_tab_f4 = plan->cep_tab_f4; fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
     fp.cep_off_col = plan->cep_smem_bytes / 4;
+    fp.cep_small = (p.n_mels <= 32 && plan->h_dct_t.size() <= static_cast<size_t>(kCepSmallTab) && p.delta_orders == 0 && !logmel_only) ? 1 : 0;
+    if (fp.cep_small) std::memcpy(fp.cep_dct, plan->h_dct_t.data(), plan->h_dct_t.size() * sizeof(float));
     ASR_CUDA_TRY(launch_tiles_path(fp, plan->sm_count, tlo.smem_bytes, plan->cep_smem_bytes + 4 * 128 * p.n_mels,
                                    std::max(1, asr_plan_num_frames(plan, max_length)), as_stream(stream)));
     return ASR_OK;

@@ -89,6 +89,8 @@ constexpr int kTlRS = 548;          // floats per frame slot: 16 x 17 float2 exc
                                     // (RS/4 odd: float4 rows conflict-free over lanes; RS = 4 mod 8: slots 4 apart sit in complementary bank halves)
 constexpr int kTlMaxPieces = 4;     // a mel segment is cut into at most this many per-warp pieces
 
+constexpr int kCepSmallTab = 512;   // floats of DCT table carried in the kernel parameters (constant bank)
+
 struct FParams {
   // ---- batch ----
   const void* audio;
@@ -134,6 +136,8 @@ struct FParams {
   int lm_stride;      // tiles path: lm is [n_mels][lm_stride] (transposed), lm_stride >= total frames
   const float4* cep_blob;   // cepstra tables (global)
   int cep_off_col;    // cepstra_t_kernel: shared-memory offset (floats) of the [n_mels][128] log-mel column buffer
+  int cep_small;      // 1: n_mels <= 32 and the transposed DCT table fits cep_dct: columns in registers, table from the constant bank
+  float cep_dct[kCepSmallTab];   // [n_mels][4*NC4] transposed DCT x lifter (cep_small only)
 };
 
 cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_bytes, int cep_smem_bytes, int max_frames,
@@ -175,6 +179,7 @@ struct asr_plan {
       fr_off_refs;
   int fr_n_refs, fr_s_pitch, fr_xb_stride, fr_lm_pitch;
   int cep_blob_f4, cep_tab_f4, cep_off_cbuf, cep_off_taps, cep_smem_bytes;
+  std::vector<float> h_dct_t;   // transposed DCT x lifter [lm_pitch][4*NC4], as in the blob
   // ---- tiles path (n_fft = 512, TMA staging): tables; tl_ok = 0 -> not available for this plan ----
   int tl_ok;
   struct TileTables {   // one set per kernel shape (index 0: 16 warps, 1: 8 warps): the mel steps are dealt out differently

@@ -663,6 +663,72 @@ __global__ void __launch_bounds__(kCepTThreads) cepstra_t_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same for n_mels <= 32 without deltas (BASELINE C1/C2/C4): the frame's log-mel column stays in registers and the
+// DCT table comes from the kernel parameters, i.e. as constant-bank operands of the FMAs - no shared memory, no table loads.
+template <int NC4>
+__global__ void __launch_bounds__(kCepTThreads) cepstra_small_kernel(const __grid_constant__ FParams fp) {
+  __shared__ float s_red[kCepTThreads / 32];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int T = __ldg(fp.nframes + b);
+  const long long out_base = static_cast<long long>(b) * fp.out_rows * fp.out_frames;
+  const int t_lo = blockIdx.y * kCepTThreads;           // first output frame of this tile
+  auto store = [&](const long long idx, const float v) {
+    if (fp.out_f64) reinterpret_cast<double*>(fp.out)[idx] = static_cast<double>(v);
+    else reinterpret_cast<float*>(fp.out)[idx] = v;
+  };
+  const int t_out = min(T, fp.out_frames);              // frames carrying data; the rest is zero padding
+  {                                                     // zero padding in the feature domain (VDR/extract...py:36-37)
+    const int z_lo = max(t_out, t_lo), z_hi = min(fp.out_frames, t_lo + kCepTThreads);
+    const int w = z_hi - z_lo;
+    for (int e = tid; w > 0 && e < fp.out_rows * w; e += kCepTThreads)
+      store(out_base + static_cast<long long>(e / w) * fp.out_frames + z_lo + e % w, 0.0f);
+  }
+  if (t_lo >= t_out) return;
+  const int g0 = __ldg(fp.fstart + b);
+  const float* lm0 = fp.lm + g0;
+  const int t = t_lo + tid;
+  const bool live = t < T;
+  float v[32];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = (live && j < fp.n_mels) ? __ldcg(lm0 + static_cast<long long>(j) * fp.lm_stride + t) : -3.0e38f;
+    mx = fmaxf(mx, v[j]);
+  }
+  float thr = -3.0e38f;
+  if (fp.top_db >= 0.0f) {
+    for (int t2 = tid; t2 < T; t2 += kCepTThreads) {   // frames of the clip outside this CTA's tile (clips longer than one tile)
+      if (t2 >= t_lo && t2 < t_lo + kCepTThreads) continue;
+      for (int j = 0; j < fp.n_mels; ++j) mx = fmaxf(mx, __ldcg(lm0 + static_cast<long long>(j) * fp.lm_stride + t2));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    mx = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kCepTThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
+    thr = mx - fp.top_db;
+  }
+  if (!live || t >= t_out) return;
+  float acc[4 * NC4];
+#pragma unroll
+  for (int c = 0; c < 4 * NC4; ++c) acc[c] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < fp.n_mels) {
+      const float x = fmaxf(v[j], thr);
+#pragma unroll
+      for (int c = 0; c < 4 * NC4; ++c) acc[c] = fmaf(x, fp.cep_dct[j * 4 * NC4 + c], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4 * NC4; ++c)
+    if (c < fp.n_mfcc) store(out_base + static_cast<long long>(c) * fp.out_frames + t, acc[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
 template <int DT, bool NOISE, int NW>
 static cudaError_t launch_tile_nw(const FParams& fp, int sm_count, int smem_bytes, cudaStream_t stream) {
   static int granted = 0;                      // the kernel also has static shared memory: ask for what is needed
@@ -712,6 +778,19 @@ cudaError_t launch_tiles_path(const FParams& fp, int sm_count, int tile_smem_byt
   const int tile = kCepTThreads - 2 * half;
   const int span = max(max_frames, fp.out_frames);
   const dim3 grid(fp.n_clips, (span + tile - 1) / tile);
+  if (fp.cep_small) {
+    switch ((fp.n_mfcc + 3) / 4) {
+      case 1: cepstra_small_kernel<1><<<grid, kCepTThreads, 0, stream>>>(fp); return cudaGetLastError();
+      case 2: cepstra_small_kernel<2><<<grid, kCepTThreads, 0, stream>>>(fp); return cudaGetLastError();
+      case 3: cepstra_small_kernel<3><<<grid, kCepTThreads, 0, stream>>>(fp); return cudaGetLastError();
+      case 4: cepstra_small_kernel<4><<<grid, kCepTThreads, 0, stream>>>(fp); return cudaGetLastError();
+      case 5: cepstra_small_kernel<5><<<grid, kCepTThreads, 0, stream>>>(fp); return cudaGetLastError();
+      case 6: cepstra_small_kernel<6><<<grid, kCepTThreads, 0, stream>>>(fp); return cudaGetLastError();
+      case 7: cepstra_small_kernel<7><<<grid, kCepTThreads, 0, stream>>>(fp); return cudaGetLastError();
+      case 8: cepstra_small_kernel<8><<<grid, kCepTThreads, 0, stream>>>(fp); return cudaGetLastError();
+      default: break;                                   // wider tables take the general kernel
+    }
+  }
   switch ((fp.n_mfcc + 3) / 4) {
     case 1: return launch_cep_t<1>(fp, grid, cep_smem_bytes, stream);
     case 2: return launch_cep_t<2>(fp, grid, cep_smem_bytes, stream);
