@@ -3,8 +3,10 @@
 The reference ships no tests, golden vectors or feature matrices and its MFCC arithmetic lives in
 librosa, which is not in the image - PARITY UNPINNED.  What can be pinned is done here:
 
-* the restatement against an INDEPENDENT implementation that is in the image
-  (``torchaudio.transforms.MFCC`` with librosa-compatible settings; fp32 FFT, so a tolerance);
+* the restatement against two INDEPENDENT implementations that are in the image
+  (``torchaudio.transforms.MFCC`` with librosa-compatible settings - fp32 FFT, so a tolerance of 1e-3 - and the numpy
+  ``transformers.audio_utils`` spectrogram / Slaney bank / power_to_db, written after librosa - float64, agreeing to
+  1e-5 dB on the log-mel matrix);
 * the reference's own pure-numpy code (noise mixers, StandardScaler standardisation) restated verbatim
   in behaviour, against numpy / sklearn run directly;
 * the structural pins the reference text holds (880 = 20 x 44, 2020 = 20 x 101, T = 1 + L // hop,
@@ -226,3 +228,25 @@ def test_sr_trim_split():
     w = pr.sr_trim_split(y, sr)
     assert len(w) == 3 and all(len(v) == sr for v in w)
     assert w[0][0] == 100 and w[-1][-1] == 399
+
+
+# ---- second independent implementation: transformers.audio_utils (numpy, float64 FFT, written after librosa) ----
+@pytest.mark.parametrize("name", ["ref_vdr", "c1", "c3", "c5"])
+def test_log_mel_vs_transformers_audio_utils(name):
+    """``transformers.audio_utils.spectrogram`` + ``mel_filter_bank(norm='slaney', mel_scale='slaney')`` restate the same
+    librosa stages (reflect-padded centred frames, periodic window, |rfft|^2, Slaney bank, power_to_db with an 80 dB
+    range over the whole call) in plain numpy: a witness that shares no code with the oracle or with torchaudio."""
+    au = pytest.importorskip("transformers.audio_utils")
+    p = lr.PRESETS[name]
+    win_length = p.win_length if p.win_length > 0 else p.n_fft
+    window = scipy.signal.get_window(p.window, win_length, fftbins=True)
+    bank = au.mel_filter_bank(1 + p.n_fft // 2, p.n_mels, p.fmin, p.fmax if p.fmax > 0 else p.sr / 2, p.sr,
+                              norm="slaney", mel_scale="slaney")
+    np.testing.assert_allclose(bank.T, lr.mel_filterbank(p), rtol=0, atol=1e-7)      # float32 storage of the oracle's bank
+    for x in to_f32(synth_clips(2, p.sr, p.sr, 31)):
+        want = au.spectrogram(x.astype(np.float64), window, frame_length=win_length, hop_length=p.hop_length, fft_length=p.n_fft,
+                              power=2.0, center=True, pad_mode="reflect", mel_filters=bank, mel_floor=p.amin, log_mel="dB",
+                              reference=1.0, min_value=p.amin, db_range=p.top_db, dtype=np.float64)
+        got = lr.log_mel(x, p)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-4)    # measured 9e-6 dB: float32 storage of |D|^2 in the oracle (librosa's dtype flow)
