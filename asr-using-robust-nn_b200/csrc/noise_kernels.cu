@@ -73,6 +73,7 @@ constexpr int kPowMaxLeaves = 640;       // covers lengths up to ~80 000 samples
 
 struct PowTable {
   int n_leaves, length;
+  int perfect;                           // 1: 2^k >= 32 leaves, all at the same depth, all of whole rows of 8 (the tree is a perfect binary tree)
   unsigned short off8[kPowMaxLeaves];    // leaf offset / 8 (every leaf starts on a multiple of 8)
   unsigned char len[kPowMaxLeaves];      // leaf length, 1..128 -> stored minus 1... (0 marks an empty clip)
   unsigned char merges[kPowMaxLeaves];
@@ -129,18 +130,22 @@ __device__ void pow_table_build(PowTable& tb, const int L, int* __restrict__ buf
     if (lane == 0) {
       // merges after each leaf: the depths on the value stack are strictly increasing -> a bit mask is the stack
       unsigned stack = 0;
+      bool perfect = n >= 32 && (n & (n - 1)) == 0;
       for (int i = 0; i < n; ++i) {
         int d = A[2 * cap + i], k = 0;
+        perfect = perfect && d == A[2 * cap] && (A[cap + i] & 7) == 0;
         while (stack & (1u << d)) { stack &= ~(1u << d); --d; ++k; }
         stack |= 1u << d;
         tb.merges[i] = static_cast<unsigned char>(k);
       }
       tb.n_leaves = n;
       tb.length = L;
+      tb.perfect = perfect ? 1 : 0;
     }
   } else if (lane == 0) {
     tb.n_leaves = 0;
     tb.length = -1;
+    tb.perfect = 0;
   }
 }
 
@@ -369,6 +374,79 @@ __device__ void clip_power_replay_vec(const void* __restrict__ audio, const long
   if (lane == 0) *out = static_cast<float>(static_cast<double>(sc.v_val[0]) / static_cast<double>(L));
 }
 
+// Perfect trees (e.g. 16 000 samples: 128 leaves of 120 / 128 at depth 7), int16, 16-byte aligned clips: lanes <-> LEAVES.
+// A round takes 32 consecutive leaves: their samples (one contiguous range, <= 8 KB) are copied to shared memory with
+// coalesced 16-byte loads (a 16-byte pad after every 16 rows spreads the lanes' rows over the banks), then every lane sums
+// ITS leaf exactly as numpy does - eight accumulators r[j] += a[8i + j] over the rows i in order, then
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) - and the 32 leaf sums fold by xor-shuffles: neighbours are siblings at every level of
+// a perfect tree (float addition is commutative, so both partners hold the parent).  Rounds fold through a small stack
+// the same way.  The samples stay UNSCALED integers in float32: scaling every operand by 2^-30 commutes with every
+// rounding of the sum (no underflow: a nonzero square is >= 1), so one exact multiply at the end replaces 16 000.
+constexpr int kPowPerfTile = 2176;        // floats per warp: 512 rows of 16 bytes + 32 pads
+template <int DT>
+__device__ void clip_power_perfect(const void* __restrict__ audio, const long long base, const int L, const PowTable& tb,
+                                   PowScratch& sc, float* __restrict__ tile, const int lane, float* __restrict__ out) {
+  static_assert(DT == ASR_I16, "int16 only");
+  const int nl = tb.n_leaves;
+  const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const short*>(audio) + base);   // rows of 8 samples
+  char* tb8 = reinterpret_cast<char*>(tile);
+  int sp = 0;                                       // round stack (uniform over the warp)
+  for (int l0 = 0, round = 0; l0 < nl; l0 += 32, ++round) {
+    const int q0 = tb.off8[l0];                                             // first row of the round
+    const int q1 = tb.off8[l0 + 31] + ((tb.len[l0 + 31] + 1) >> 3);         // one past its last row
+    const int nq = q1 - q0;                                                 // <= 512
+    __syncwarp();                                   // the tile is rewritten
+#pragma unroll 1
+    for (int c = 0; c < nq; c += 8 * 32) {
+      int4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = c + 32 * u + lane;
+        if (q < nq) v[u] = __ldg(src + q0 + q);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = c + 32 * u + lane;
+        if (q < nq) *reinterpret_cast<int4*>(tb8 + 16 * (q + (q >> 4))) = v[u];
+      }
+    }
+    __syncwarp();
+    const int leaf = l0 + lane;
+    const int qs = tb.off8[leaf] - q0, rows = (tb.len[leaf] + 1) >> 3;      // 1..16 whole rows
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < rows) {
+        const int q = qs + i;
+        const int4 w4 = *reinterpret_cast<const int4*>(tb8 + 16 * (q + (q >> 4)));
+        const unsigned w[4] = {static_cast<unsigned>(w4.x), static_cast<unsigned>(w4.y), static_cast<unsigned>(w4.z),
+                               static_cast<unsigned>(w4.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned x = w[k] ^ 0x80008000u;    // exact int16 -> float: bits(2^23 + (s + 32768)) - (2^23 + 32768)
+          const float s0 = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7410)) - 8421376.0f;
+          const float s1 = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7432)) - 8421376.0f;
+          const float p0 = __fmul_rn(s0, s0), p1 = __fmul_rn(s1, s1);
+          r[2 * k] = i == 0 ? p0 : __fadd_rn(r[2 * k], p0);
+          r[2 * k + 1] = i == 0 ? p1 : __fadd_rn(r[2 * k + 1], p1);
+        }
+      }
+    }
+    float v = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    // fold the rounds: round k merges with the stack while the low bits of k are ones (left + right)
+    for (int k = round; k & 1; k >>= 1) v = __fadd_rn(sc.v_val[--sp], v);
+    __syncwarp();
+    if (lane == 0) sc.v_val[sp] = v;
+    ++sp;
+    __syncwarp();
+  }
+  if (lane == 0)
+    *out = static_cast<float>(static_cast<double>(__fmul_rn(sc.v_val[0], 9.313225746154785e-10f)) / static_cast<double>(L));
+}
+
 // Persistent CTAs: the leaf table is built once per CTA, every warp then takes clips b0 + warp, b0 + 8 * gridDim.x ...
 template <int DT>
 __global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* __restrict__ audio,
@@ -378,9 +456,10 @@ __global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* 
                                                                      const int aligned) {
   __shared__ PowScratch scratch[kPowWarps];
   __shared__ PowTable table;
-  __shared__ __align__(16) float tiles[kPowWarps][4 * kPowTileGroup];
+  extern __shared__ __align__(16) float pow_tiles[];     // [kPowWarps][kPowPerfTile]
+  float (*tiles)[kPowPerfTile] = reinterpret_cast<float (*)[kPowPerfTile]>(pow_tiles);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  static_assert(kPowWarps * 4 * kPowTileGroup >= 6 * kPowMaxLeaves, "the tiles double as the build buffer");
+  static_assert(kPowPerfTile >= 4 * kPowTileGroup && kPowWarps * kPowPerfTile >= 6 * kPowMaxLeaves, "the tiles double as the build buffer");
   if (warp == 0) pow_table_build(table, lengths[min(n_clips - 1, blockIdx.x * kPowWarps)], reinterpret_cast<int*>(&tiles[0][0]), lane);
   __syncthreads();
   for (int b = blockIdx.x * kPowWarps + warp; b < n_clips; b += gridDim.x * kPowWarps) {
@@ -391,6 +470,13 @@ __global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* 
       continue;
     }
     if (table.n_leaves > 0 && table.length == L) {
+      if constexpr (DT == ASR_I16) {
+        if (table.perfect && aligned && (base & 7) == 0) {
+          clip_power_perfect<DT>(audio, base, L, table, scratch[warp], tiles[warp], lane, power + b);
+          __syncwarp();
+          continue;
+        }
+      }
       if (aligned && (base & 7) == 0) clip_power_replay_vec<DT>(audio, base, L, table, scratch[warp], tiles[warp], lane, power + b);
       else clip_power_replay<DT>(audio, base, L, table, scratch[warp], lane, power + b);
     } else {
@@ -519,13 +605,20 @@ extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_
     return ASR_ERR_INVALID;
   }
   if (n_clips == 0) return ASR_OK;
-  const int blocks = std::min((n_clips + kPowWarps - 1) / kPowWarps, 148 * 4);
+  const int blocks = std::min((n_clips + kPowWarps - 1) / kPowWarps, 148 * 2);      // persistent: two CTAs fit one SM
   const long long* off = reinterpret_cast<const long long*>(offsets_dev);
   const int aligned = (reinterpret_cast<uintptr_t>(audio_dev) & 15) == 0 ? 1 : 0;
+  constexpr int smem = kPowWarps * kPowPerfTile * static_cast<int>(sizeof(float));
+  static bool granted = false;
+  if (!granted) {
+    ASR_CUDA_TRY(cudaFuncSetAttribute(clip_power_kernel<ASR_I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(clip_power_kernel<ASR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    granted = true;
+  }
   if (dtype == ASR_I16)
-    clip_power_kernel<ASR_I16><<<blocks, kPowWarps * 32, 0, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
+    clip_power_kernel<ASR_I16><<<blocks, kPowWarps * 32, smem, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
   else
-    clip_power_kernel<ASR_F32><<<blocks, kPowWarps * 32, 0, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
+    clip_power_kernel<ASR_F32><<<blocks, kPowWarps * 32, smem, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }
