@@ -19,7 +19,7 @@ namespace asr {
 // lanes, lane j of a group owning numpy's accumulator r[j] - and folds the leaf sums with a
 // (value, depth) stack: two entries of equal depth are siblings and merge into their parent, which is
 // exactly the order numpy adds them in.  No shared-memory staging, no CTA barriers.
-constexpr int kPowWarps = 8;
+constexpr int kPowWarps = 12;
 constexpr int kPowStack = 40;     // > depth of the tree for any int32 length
 
 struct PowScratch {               // per warp
@@ -382,37 +382,38 @@ __device__ void clip_power_replay_vec(const void* __restrict__ audio, const long
 // a perfect tree (float addition is commutative, so both partners hold the parent).  Rounds fold through a small stack
 // the same way.  The samples stay UNSCALED integers in float32: scaling every operand by 2^-30 commutes with every
 // rounding of the sum (no underflow: a nonzero square is >= 1), so one exact multiply at the end replaces 16 000.
-constexpr int kPowPerfTile = 2176;        // floats per warp: 512 rows of 16 bytes + 32 pads
+constexpr int kPowPerfTile = 2176;        // floats per tile: 512 rows of 16 bytes + 32 pads; two tiles per warp
+__device__ __forceinline__ void pow_cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 template <int DT>
 __device__ void clip_power_perfect(const void* __restrict__ audio, const long long base, const int L, const PowTable& tb,
                                    PowScratch& sc, float* __restrict__ tile, const int lane, float* __restrict__ out) {
   static_assert(DT == ASR_I16, "int16 only");
   const int nl = tb.n_leaves;
   const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const short*>(audio) + base);   // rows of 8 samples
-  char* tb8 = reinterpret_cast<char*>(tile);
-  int sp = 0;                                       // round stack (uniform over the warp)
-  for (int l0 = 0, round = 0; l0 < nl; l0 += 32, ++round) {
+  // rows of a round -> its tile, asynchronously (cp.async: no registers, the copy of round r+1 runs under the sums of round r)
+  auto issue = [&](const int l0, char* dst) {
     const int q0 = tb.off8[l0];                                             // first row of the round
-    const int q1 = tb.off8[l0 + 31] + ((tb.len[l0 + 31] + 1) >> 3);         // one past its last row
-    const int nq = q1 - q0;                                                 // <= 512
-    __syncwarp();                                   // the tile is rewritten
-#pragma unroll 1
-    for (int c = 0; c < nq; c += 8 * 32) {
-      int4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int q = c + 32 * u + lane;
-        if (q < nq) v[u] = __ldg(src + q0 + q);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int q = c + 32 * u + lane;
-        if (q < nq) *reinterpret_cast<int4*>(tb8 + 16 * (q + (q >> 4))) = v[u];
-      }
+    const int nq = tb.off8[l0 + 31] + ((tb.len[l0 + 31] + 1) >> 3) - q0;    // rows of the round, <= 512
+    for (int q = lane; q < nq; q += 32) pow_cp_async16(dst + 16 * (q + (q >> 4)), src + q0 + q);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int sp = 0;                                       // round stack (uniform over the warp)
+  __syncwarp();                                     // the tiles are rewritten
+  issue(0, reinterpret_cast<char*>(tile));
+  for (int l0 = 0, round = 0; l0 < nl; l0 += 32, ++round) {
+    const char* tb8 = reinterpret_cast<const char*>(tile + (round & 1) * kPowPerfTile);
+    if (l0 + 32 < nl) {
+      issue(l0 + 32, reinterpret_cast<char*>(tile + ((round + 1) & 1) * kPowPerfTile));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncwarp();
     const int leaf = l0 + lane;
-    const int qs = tb.off8[leaf] - q0, rows = (tb.len[leaf] + 1) >> 3;      // 1..16 whole rows
+    const int qs = tb.off8[leaf] - tb.off8[l0], rows = (tb.len[leaf] + 1) >> 3;      // 1..16 whole rows
     float r[8];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -438,7 +439,7 @@ __device__ void clip_power_perfect(const void* __restrict__ audio, const long lo
     for (int o = 1; o < 32; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
     // fold the rounds: round k merges with the stack while the low bits of k are ones (left + right)
     for (int k = round; k & 1; k >>= 1) v = __fadd_rn(sc.v_val[--sp], v);
-    __syncwarp();
+    __syncwarp();                                   // also: every lane is done with this round's tile
     if (lane == 0) sc.v_val[sp] = v;
     ++sp;
     __syncwarp();
@@ -456,8 +457,8 @@ __global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* 
                                                                      const int aligned) {
   __shared__ PowScratch scratch[kPowWarps];
   __shared__ PowTable table;
-  extern __shared__ __align__(16) float pow_tiles[];     // [kPowWarps][kPowPerfTile]
-  float (*tiles)[kPowPerfTile] = reinterpret_cast<float (*)[kPowPerfTile]>(pow_tiles);
+  extern __shared__ __align__(16) float pow_tiles[];     // [kPowWarps][2 * kPowPerfTile]
+  float (*tiles)[2 * kPowPerfTile] = reinterpret_cast<float (*)[2 * kPowPerfTile]>(pow_tiles);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   static_assert(kPowPerfTile >= 4 * kPowTileGroup && kPowWarps * kPowPerfTile >= 6 * kPowMaxLeaves, "the tiles double as the build buffer");
   if (warp == 0) pow_table_build(table, lengths[min(n_clips - 1, blockIdx.x * kPowWarps)], reinterpret_cast<int*>(&tiles[0][0]), lane);
@@ -605,10 +606,10 @@ extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_
     return ASR_ERR_INVALID;
   }
   if (n_clips == 0) return ASR_OK;
-  const int blocks = std::min((n_clips + kPowWarps - 1) / kPowWarps, 148 * 2);      // persistent: two CTAs fit one SM
+  const int blocks = std::min((n_clips + kPowWarps - 1) / kPowWarps, 148);          // persistent: one CTA per SM
   const long long* off = reinterpret_cast<const long long*>(offsets_dev);
   const int aligned = (reinterpret_cast<uintptr_t>(audio_dev) & 15) == 0 ? 1 : 0;
-  constexpr int smem = kPowWarps * kPowPerfTile * static_cast<int>(sizeof(float));
+  constexpr int smem = kPowWarps * 2 * kPowPerfTile * static_cast<int>(sizeof(float));
   static bool granted = false;
   if (!granted) {
     ASR_CUDA_TRY(cudaFuncSetAttribute(clip_power_kernel<ASR_I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
