@@ -126,17 +126,23 @@ __device__ void pow_table_build(PowTable& tb, const int L, int* __restrict__ buf
       tb.off8[i] = static_cast<unsigned short>(A[i] >> 3);
       tb.len[i] = static_cast<unsigned char>(A[cap + i] - 1);
     }
+    // perfect tree: 2^k >= 32 leaves, all at the same depth, whole rows of 8 (checked by all lanes)
+    bool perfect = n >= 32 && (n & (n - 1)) == 0;
+    for (int i = lane; i < n; i += 32) perfect = perfect && A[2 * cap + i] == A[2 * cap] && (A[cap + i] & 7) == 0;
+    perfect = __all_sync(0xffffffffu, perfect);
+    if (perfect)                                       // a perfect tree merges like a binary counter: trailing ones of the leaf index
+      for (int i = lane; i < n; i += 32) tb.merges[i] = static_cast<unsigned char>(__ffs(~i) - 1);
     __syncwarp();
     if (lane == 0) {
-      // merges after each leaf: the depths on the value stack are strictly increasing -> a bit mask is the stack
-      unsigned stack = 0;
-      bool perfect = n >= 32 && (n & (n - 1)) == 0;
-      for (int i = 0; i < n; ++i) {
-        int d = A[2 * cap + i], k = 0;
-        perfect = perfect && d == A[2 * cap] && (A[cap + i] & 7) == 0;
-        while (stack & (1u << d)) { stack &= ~(1u << d); --d; ++k; }
-        stack |= 1u << d;
-        tb.merges[i] = static_cast<unsigned char>(k);
+      if (!perfect) {
+        // merges after each leaf: the depths on the value stack are strictly increasing -> a bit mask is the stack
+        unsigned stack = 0;
+        for (int i = 0; i < n; ++i) {
+          int d = A[2 * cap + i], k = 0;
+          while (stack & (1u << d)) { stack &= ~(1u << d); --d; ++k; }
+          stack |= 1u << d;
+          tb.merges[i] = static_cast<unsigned char>(k);
+        }
       }
       tb.n_leaves = n;
       tb.length = L;
