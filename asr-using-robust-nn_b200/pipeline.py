@@ -13,6 +13,8 @@ several GPUs (a single graph for the whole step on one GPU).
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional
 
 import torch
@@ -47,6 +49,7 @@ class NoisyFeaturePipeline:
         self.distributed = distributed
         self.std = Standardizer(self.D, device=self.device, group=group, distributed=distributed)
         self.use_graphs = use_graphs
+        self.capture_collectives = os.environ.get("ASR_B200_CAPTURE_COLLECTIVES", "1") != "0"
         self._feats = None
         self._cache: dict = {}
         self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch (eager steps only)
@@ -141,7 +144,17 @@ class NoisyFeaturePipeline:
         if not standardize:
             cap(lambda: self._group1(batch, z, snr_db, feats))
         elif self.distributed:
-            cap(g1); cap(g2); cap(g3)
+            # one graph for the whole step with the two NCCL all-reduces captured inside it; if this build of
+            # torch / NCCL cannot capture collectives, three graphs with the all-reduces launched between them
+            if self.capture_collectives:
+                try:
+                    cap(lambda: (g1(), self.std._allreduce(self.std.acc1), g2(), self.std._allreduce(self.std.acc2), g3()))
+                except Exception:                       # noqa: BLE001  (capture errors surface as RuntimeError subclasses)
+                    sg.graphs.clear()
+                    self.capture_collectives = False
+                    torch.cuda.synchronize(self.device)
+            if not sg.graphs:
+                cap(g1); cap(g2); cap(g3)
         else:
             cap(lambda: (g1(), g2(), g3()))
         return sg
