@@ -6,11 +6,15 @@ Drop-in for the data-parallel hot path of fmazilu/ASR-using-robust-NN:
   ``Voice digit recogniton/extract_features_construct_dataset.py`` / ``attacks.py``;
 * ``asr_b200.speaker.*`` mirror ``Speaker recognition/*``;
 * ``asr_b200.frontend`` is the batched array-in API they delegate to;
-* all arithmetic runs in ``libasr_b200.so`` (hand-written CUDA, C-ABI in ``include/asr_b200.h``).
+* all arithmetic of the hot path runs in ``libasr_b200.so`` (hand-written CUDA, C-ABI in ``include/asr_b200.h``);
+* ``asr_b200.mlp`` is the classifier's forward pass for the accuracy-vs-SNR sweep (plain
+  library GEMMs, BatchNorm folded).
 """
 from ._lib import AsrError, LIB_PATH  # noqa: F401
 from .params import MfccParams, REF_VDR, REF_SR, C1, C3, C5, PRESETS  # noqa: F401
 from .frontend import (ClipBatch, Noise, MfccPlan, Standardizer, Resampler, clip_power, snr_sigma_host,  # noqa: F401
                        snr_sigma_device, mix_white, mix_mixture, mix_rows_white, mix_rows_mixture, randn)
+
+from .mlp import DenseStack, accuracy_vs_snr  # noqa: F401
 
 __version__ = "0.1.0"
