@@ -49,7 +49,9 @@ class NoisyFeaturePipeline:
         self.distributed = distributed
         self.std = Standardizer(self.D, device=self.device, group=group, distributed=distributed)
         self.use_graphs = use_graphs
-        self.capture_collectives = os.environ.get("ASR_B200_CAPTURE_COLLECTIVES", "1") != "0"
+        # opt-in (ASR_B200_CAPTURE_COLLECTIVES=1): capture the NCCL all-reduces inside the step's graph.  Measured: identical
+        # rows, no gain at 8 GPUs (0.891 vs 0.888 ms per step) and the process group then takes minutes to tear down at exit.
+        self.capture_collectives = os.environ.get("ASR_B200_CAPTURE_COLLECTIVES", "0") == "1"
         self._feats = None
         self._cache: dict = {}
         self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch (eager steps only)
@@ -144,8 +146,8 @@ class NoisyFeaturePipeline:
         if not standardize:
             cap(lambda: self._group1(batch, z, snr_db, feats))
         elif self.distributed:
-            # one graph for the whole step with the two NCCL all-reduces captured inside it; if this build of
-            # torch / NCCL cannot capture collectives, three graphs with the all-reduces launched between them
+            # default: three graphs with the two NCCL all-reduces launched between them; opt-in: one graph for the whole
+            # step with the all-reduces captured inside it
             if self.capture_collectives:
                 try:
                     cap(lambda: (g1(), self.std._allreduce(self.std.acc1), g2(), self.std._allreduce(self.std.acc2), g3()))
