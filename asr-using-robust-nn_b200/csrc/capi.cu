@@ -325,37 +325,18 @@ static bool build_tile_tables(asr_plan* pl, int cfg, int n_vw, bool pair_equal, 
   };
   tt.off_twp = put_f(twp.data(), twp.size());
   {
-    // the tile kernel unpacks 2X (exact scaling); float4 [k1 / 2][lane] = twiddles of bins lane + 16 k1 and lane + 16 (k1 + 1)
-    std::vector<float> twu4(4 * 16 * 4, 0.0f);
-    for (int kp = 0; kp < 4; ++kp)
-      for (int l = 0; l < 16; ++l)
-        for (int e = 0; e < 2; ++e) {
-          const int k = l + 16 * (2 * kp + e);
-          twu4[(kp * 16 + l) * 4 + 2 * e] = 2.0f * twu[2 * k];
-          twu4[(kp * 16 + l) * 4 + 2 * e + 1] = 2.0f * twu[2 * k + 1];
-        }
-    tt.off_twu = put_f(twu4.data(), twu4.size());
+    std::vector<float> twu2(twu);
+    for (float& v : twu2) v *= 2.0f;                       // the tile kernel unpacks 2X (exact scaling)
+    tt.off_twu = put_f(twu2.data(), twu2.size());
   }
   tt.off_wtab = put_f(wtab.data(), wtab.size());
   tt.off_steps = put_i(stab.data(), stab.size());
   tt.off_wrange = put_i(wrange.data(), wrange.size());
   tt.blob_f4 = static_cast<int>(blob.size() / 4);           // copied to shared memory; one of the two windows follows it there
-  // window as float4 [j][lane] = (w[2 na], w[2 na + 1], w[2 nb], w[2 nb + 1]) with na = lane + 16 j, nb = na + 128:
-  // the operand pairs of the FFT's first radix-2 stage
-  auto win4 = [&](float scale) {
-    std::vector<float> w4(512);
-    for (int j = 0; j < 8; ++j)
-      for (int l = 0; l < 16; ++l) {
-        const int na = l + 16 * j, nb = na + 128;
-        float* q = w4.data() + (j * 16 + l) * 4;
-        q[0] = pl->h_window[2 * na] * scale; q[1] = pl->h_window[2 * na + 1] * scale;
-        q[2] = pl->h_window[2 * nb] * scale; q[3] = pl->h_window[2 * nb + 1] * scale;
-      }
-    return w4;
-  };
+  tt.off_window = put_f(pl->h_window.data(), pl->h_window.size());
   {
-    const std::vector<float> w = win4(1.0f), wi = win4(1.0f / 32768.0f);   // exact: int16 samples are scaled through the window
-    tt.off_window = put_f(w.data(), w.size());
+    std::vector<float> wi(pl->h_window);
+    for (float& v : wi) v *= (1.0f / 32768.0f);
     tt.off_window_i16 = put_f(wi.data(), wi.size());
   }
   if (cudaMalloc(reinterpret_cast<void**>(&tt.blob_dev), blob.size() * sizeof(float)) != cudaSuccess) return false;

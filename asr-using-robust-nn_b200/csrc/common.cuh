@@ -85,7 +85,7 @@ constexpr int kFrMaxRuns = 4;       // runs of consecutive frames (of one clip) 
 // Two shapes: 16 warps / 32 frames per block / one CTA per SM, or 8 warps / 16 frames per block / two CTAs per SM.
 // The last warp of a CTA assembles descriptors and issues the copies; the other warps share the mel steps.
 constexpr int kTlMaxRuns = 4;
-constexpr int kTlRS = 580;          // floats per frame slot: 16 x 18 float2 exchange buffer, reused as the spectrum row
+constexpr int kTlRS = 548;          // floats per frame slot: 16 x 17 float2 exchange buffer, reused as the spectrum row
                                     // (RS/4 odd: float4 rows conflict-free over lanes; RS = 4 mod 8: slots 4 apart sit in complementary bank halves)
 constexpr int kTlMaxPieces = 4;     // a mel segment is cut into at most this many per-warp pieces
 

@@ -147,20 +147,19 @@ __device__ __forceinline__ float convert1(const char* __restrict__ pa, const cha
 // unpack.  Differences from frame_power_fft<512> (fft_core.cuh): the window multiply is fused into the first
 // radix-2 stage (p = xa*wa; p +- xb*wb), and the unpack works on 2X: X' = (A + conj B) + w'(A - conj B),
 // Y' = 2(A + conj B) - X', with w' = 2w; the spectrum row holds 4|X|^2 and the mel weights of this path carry the 1/4.
-__device__ __forceinline__ void tile_fft512(const float2* __restrict__ xs2, const float4* __restrict__ win4,
-                                            const float* __restrict__ twp, const float4* __restrict__ twu4,
+__device__ __forceinline__ void tile_fft512(const float2* __restrict__ xs2, const float2* __restrict__ win2,
+                                            const float* __restrict__ twp, const float2* __restrict__ twu2,
                                             float* buf, const int l) {
-  constexpr int M = 256, G = 16, P = 16, XP = 18;  // XP: exchange row pitch in float2 (144 bytes: 16-byte stores, conflict-free)
+  constexpr int M = 256, G = 16, P = 16;
   float re[P], im[P];
 #pragma unroll
   for (int g = 0; g < P; g += 2) {                  // first stage: bit-reversed inputs g, g+1 <-> n2 = brev(g), brev(g) + 8
-    const int j = brev<16>(g);                      // 0..7
-    const int na = l + 16 * j, nb = na + 128;
+    const int na = l + 16 * brev<16>(g), nb = na + 128;
     const float2 xa = xs2[na], xb = xs2[nb];
-    const float4 w = win4[16 * j + l];              // (window[2 na], [2 na + 1], [2 nb], [2 nb + 1])
-    const float pr = xa.x * w.x, pi = xa.y * w.y;
-    re[g] = fmaf(xb.x, w.z, pr); re[g + 1] = fmaf(-xb.x, w.z, pr);
-    im[g] = fmaf(xb.y, w.w, pi); im[g + 1] = fmaf(-xb.y, w.w, pi);
+    const float2 wa = win2[na], wb = win2[nb];
+    const float pr = xa.x * wa.x, pi = xa.y * wa.y;
+    re[g] = fmaf(xb.x, wb.x, pr); re[g + 1] = fmaf(-xb.x, wb.x, pr);
+    im[g] = fmaf(xb.y, wb.y, pi); im[g + 1] = fmaf(-xb.y, wb.y, pi);
   }
   dft_dit_from<P, 4>(re, im);
   {
@@ -178,16 +177,15 @@ __device__ __forceinline__ void tile_fft512(const float2* __restrict__ xs2, cons
       im[k2 + 1] = fmaf(r, t.w, i * t.z);
     }
   }
-  float4* xb4 = reinterpret_cast<float4*>(buf);
-  const float2* xb2 = reinterpret_cast<const float2*>(buf);
+  float2* xb2 = reinterpret_cast<float2*>(buf);
   float ur[G], ui[G];
   __syncwarp();
 #pragma unroll
-  for (int k2 = 0; k2 < P; k2 += 2) xb4[l * (XP / 2) + k2 / 2] = make_float4(re[k2], im[k2], re[k2 + 1], im[k2 + 1]);
+  for (int k2 = 0; k2 < P; ++k2) xb2[l * (P + 1) + k2] = make_float2(re[k2], im[k2]);
   __syncwarp();
 #pragma unroll
   for (int n1 = 0; n1 < G; ++n1) {
-    const float2 a = xb2[n1 * XP + l];
+    const float2 a = xb2[n1 * (P + 1) + l];
     ur[brev<G>(n1)] = a.x;
     ui[brev<G>(n1)] = a.y;
   }
@@ -203,13 +201,12 @@ __device__ __forceinline__ void tile_fft512(const float2* __restrict__ xs2, cons
     const float give_i = (l == 0) ? ui[j0] : ui[G - 1 - k1];
     const float br = __shfl_sync(0xffffffffu, give_r, partner, G);
     const float bi = __shfl_sync(0xffffffffu, give_i, partner, G);
-    const float4 w2 = twu4[16 * (k1 / 2) + l];     // unpack twiddles of k1 (xy) and k1 + 1 (zw): (-sin(2 pi k/N), -cos(2 pi k/N))
-    const float wx = (k1 & 1) ? w2.z : w2.x, wy = (k1 & 1) ? w2.w : w2.y;
+    const float2 w = twu2[k];                      // (-sin(2 pi k/N), -cos(2 pi k/N))
     const float ar = ur[k1], ai = ui[k1];
     const float sr = ar + br, si = ai - bi;        // A + conj(B)
     const float dr = ar - br, di = ai + bi;        // A - conj(B)
-    const float xr = fmaf(-wy, di, fmaf(wx, dr, sr));
-    const float xi = fmaf(wy, dr, fmaf(wx, di, si));
+    const float xr = fmaf(-w.y, di, fmaf(w.x, dr, sr));
+    const float xi = fmaf(w.y, dr, fmaf(w.x, di, si));
     const float yr = fmaf(2.0f, sr, -xr), yi = fmaf(2.0f, si, -xi);
     buf[k] = fmaf(xr, xr, xi * xi);
     buf[M - k] = fmaf(yr, yr, yi * yi);
@@ -251,9 +248,9 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
     for (int i = tid; i < fp.blob_f4; i += kAllThreads) dst[i] = __ldg(fp.blob + i);
     if (tid < 128) dst[fp.blob_f4 + tid] = __ldg(fp.blob + fp.off_window / 4 + tid);
   }
-  const float4* s_win4 = reinterpret_cast<const float4*>(smem + 4 * fp.blob_f4);   // [8][16] (window of sample pairs n, n + 128)
+  const float2* s_win2 = reinterpret_cast<const float2*>(smem + 4 * fp.blob_f4);
   const float* s_twp = smem + fp.off_twp;
-  const float4* s_twu4 = reinterpret_cast<const float4*>(smem + fp.off_twu);        // [4][16] unpack twiddles of bins k, k + 16
+  const float2* s_twu = reinterpret_cast<const float2*>(smem + fp.off_twu);
   const float4* s_wtab = reinterpret_cast<const float4*>(smem + fp.off_wtab);
   const int4* s_pieces = reinterpret_cast<const int4*>(smem + fp.off_steps);
   float* s_aud = smem + fp.sm_aud;                   // [2][aud_cap]
@@ -499,7 +496,7 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
     if (cur.n_slots == 0) break;                       // uniform over the CTA
     // ---- fft (block it) ----
     if (fft_slot0 < cur.n_slots)
-      tile_fft512(reinterpret_cast<const float2*>(s_aud + (it & 1) * fp.aud_cap + cur.slot_aud[fft_slot]), s_win4, s_twp, s_twu4,
+      tile_fft512(reinterpret_cast<const float2*>(s_aud + (it & 1) * fp.aud_cap + cur.slot_aud[fft_slot]), s_win2, s_twp, s_twu,
                   fft_buf, fft_l);
     bar_main();
     // ---- mel (block it): lanes <-> frames, this virtual warp's pieces ----
