@@ -16,6 +16,25 @@ constexpr int kMaxSmemBytes = 227 * 1024;   // opt-in dynamic shared memory per 
 constexpr int kMelChunkQuads = 4;           // a mel task covers at most 4 float4 = 16 bins
 
 void set_error(const std::string& msg);
+
+// Opt-in dynamic shared memory above `floor_bytes`, remembered per device: cudaFuncSetAttribute applies to the current
+// device only, and one process may drive several.
+constexpr int kMaxDevices = 64;
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, int bytes, int floor_bytes, int (&granted)[kMaxDevices], bool max_carveout = false) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (bytes > floor_bytes && bytes > granted[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && max_carveout)
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    granted[dev] = bytes;
+  }
+  return cudaSuccess;
+}
 int cuda_fail(cudaError_t e, const char* what);
 #define ASR_CUDA_TRY(expr)                                   \
   do {                                                       \

@@ -877,24 +877,18 @@ __global__ void __launch_bounds__(kCepThreads) cepstra_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 template <int DT, bool ASYNC>
 static cudaError_t launch_frames_dt(const FParams& fp, int grid, int smem_bytes, cudaStream_t stream) {
-  static int granted = 0;                      // the kernel also has static shared memory: ask for what is needed
-  if (smem_bytes > granted) {
-    cudaError_t e = cudaFuncSetAttribute(frames512_kernel<DT, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    granted = smem_bytes;
-  }
+  static int granted[kMaxDevices] = {0};       // the kernel also has static shared memory: always ask for what is needed
+  const cudaError_t eg = ensure_dyn_smem(frames512_kernel<DT, ASYNC>, smem_bytes, 0, granted);
+  if (eg != cudaSuccess) return eg;
   frames512_kernel<DT, ASYNC><<<grid, kFrAllThreads, smem_bytes, stream>>>(fp);
   return cudaGetLastError();
 }
 
 template <int NC4>
 static cudaError_t launch_cep_n(const FParams& fp, dim3 grid, int smem_bytes, cudaStream_t stream) {
-  static int granted = 48 * 1024;
-  if (smem_bytes > granted) {
-    cudaError_t e = cudaFuncSetAttribute(cepstra_kernel<NC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    granted = smem_bytes;
-  }
+  static int granted[kMaxDevices] = {0};
+  const cudaError_t eg = ensure_dyn_smem(cepstra_kernel<NC4>, smem_bytes, 48 * 1024, granted);
+  if (eg != cudaSuccess) return eg;
   cepstra_kernel<NC4><<<grid, kCepThreads, smem_bytes, stream>>>(fp);
   return cudaGetLastError();
 }

@@ -616,12 +616,9 @@ extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_
   const long long* off = reinterpret_cast<const long long*>(offsets_dev);
   const int aligned = (reinterpret_cast<uintptr_t>(audio_dev) & 15) == 0 ? 1 : 0;
   constexpr int smem = kPowWarps * 2 * kPowPerfTile * static_cast<int>(sizeof(float));
-  static bool granted = false;
-  if (!granted) {
-    ASR_CUDA_TRY(cudaFuncSetAttribute(clip_power_kernel<ASR_I16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(clip_power_kernel<ASR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    granted = true;
-  }
+  static int granted_i16[kMaxDevices] = {0}, granted_f32[kMaxDevices] = {0};
+  ASR_CUDA_TRY(ensure_dyn_smem(clip_power_kernel<ASR_I16>, smem, 0, granted_i16));
+  ASR_CUDA_TRY(ensure_dyn_smem(clip_power_kernel<ASR_F32>, smem, 0, granted_f32));
   if (dtype == ASR_I16)
     clip_power_kernel<ASR_I16><<<blocks, kPowWarps * 32, smem, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
   else

@@ -731,14 +731,9 @@ __global__ void __launch_bounds__(kCepTThreads) cepstra_small_kernel(const __gri
 // ------------------------------------------------------------------------------------------------
 template <int DT, bool NOISE, int NW>
 static cudaError_t launch_tile_nw(const FParams& fp, int sm_count, int smem_bytes, cudaStream_t stream) {
-  static int granted = 0;                      // the kernel also has static shared memory: ask for what is needed
-  if (smem_bytes > granted) {
-    cudaError_t e = cudaFuncSetAttribute(tile512_kernel<DT, NOISE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tile512_kernel<DT, NOISE, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    granted = smem_bytes;
-  }
+  static int granted[kMaxDevices] = {0};       // the kernel also has static shared memory: always ask for what is needed
+  const cudaError_t eg = ensure_dyn_smem(tile512_kernel<DT, NOISE, NW>, smem_bytes, 0, granted, true);
+  if (eg != cudaSuccess) return eg;
   tile512_kernel<DT, NOISE, NW><<<(NW == 8 ? 2 : 1) * sm_count, NW * 32 + NW * kTlHelpDiv, smem_bytes, stream>>>(fp);
   return cudaGetLastError();
 }
@@ -750,12 +745,9 @@ static cudaError_t launch_tile_dt(const FParams& fp, int sm_count, int smem_byte
 
 template <int NC4>
 static cudaError_t launch_cep_t(const FParams& fp, dim3 grid, int smem_bytes, cudaStream_t stream) {
-  static int granted = 48 * 1024;
-  if (smem_bytes > granted) {
-    cudaError_t e = cudaFuncSetAttribute(cepstra_t_kernel<NC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    granted = smem_bytes;
-  }
+  static int granted[kMaxDevices] = {0};
+  const cudaError_t eg = ensure_dyn_smem(cepstra_t_kernel<NC4>, smem_bytes, 48 * 1024, granted);
+  if (eg != cudaSuccess) return eg;
   cepstra_t_kernel<NC4><<<grid, kCepTThreads, smem_bytes, stream>>>(fp);
   return cudaGetLastError();
 }
