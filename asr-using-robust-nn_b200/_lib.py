@@ -54,6 +54,8 @@ SIGNATURES = {
     "asr_plan_feature_rows": (_i32, [_vp]),
     "asr_plan_uses_fft": (_i32, [_vp]),
     "asr_plan_get_tables": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "asr_plan_set_stage_probe": (C.c_int, [_vp, _vp]),
+    "asr_tc_selftest": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "asr_mfcc_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(NoiseC), _vp, _i32, _i32, _vp,
                                  _vp, C.c_size_t, _vp]),
     "asr_logmel_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(NoiseC), _vp, _i32, _vp,
@@ -64,6 +66,7 @@ SIGNATURES = {
     "asr_plan_path_used": (_i32, [_vp, _i32, _i32]),
     "asr_clip_power": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "asr_snr_sigma": (C.c_int, [_vp, _f32, _vp, _i32, _vp]),
+    "asr_snr_sigma_host": (C.c_int, [_vp, _vp, _f32, _vp, _i32]),
     "asr_mix_white": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "asr_mix_mixture": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _f64, _f64, _f64, _vp, _vp]),
     "asr_mix_rows_white": (C.c_int, [_vp, _i64, _vp, _f64, _vp, _vp]),

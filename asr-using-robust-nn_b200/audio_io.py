@@ -64,6 +64,9 @@ def load_batch(paths, sr: int = 22050):
     resampled on the device, one launch per distinct source rate."""
     import torch
     from .frontend import ClipBatch
+    paths = list(paths)
+    if not paths:
+        return ClipBatch.from_arrays([], dtype=np.float32)
     decoded = [_decode(p) for p in paths]
     dev = torch.cuda.current_device()
     groups = {}

@@ -760,6 +760,12 @@ extern "C" int32_t asr_plan_path_used(const asr_plan* plan, int32_t dtype, int32
   return ASR_PATH_CLIP;
 }
 
+extern "C" int asr_plan_set_stage_probe(asr_plan* plan, float* staged_dev) {
+  if (!plan) { set_error("asr_plan_set_stage_probe: null plan"); return ASR_ERR_INVALID; }
+  plan->stage_probe = staged_dev;
+  return ASR_OK;
+}
+
 extern "C" int asr_plan_set_path(asr_plan* plan, int32_t path) {
   if (!plan || path < ASR_PATH_AUTO || path > ASR_PATH_TILES) { set_error("asr_plan_set_path: bad argument"); return ASR_ERR_INVALID; }
   plan->path = path;
@@ -850,6 +856,8 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.cep_off_col = plan->cep_smem_bytes / 4;
     fp.cep_small = (p.n_mels <= 32 && plan->h_dct_t.size() <= static_cast<size_t>(kCepSmallTab) && p.delta_orders == 0 && !logmel_only) ? 1 : 0;
     if (fp.cep_small) std::memcpy(fp.cep_dct, plan->h_dct_t.data(), plan->h_dct_t.size() * sizeof(float));
+    { const char* mf = std::getenv("ASR_B200_MIX_F32"); fp.mix_f32 = (mf && std::atoi(mf) != 0) ? 1 : 0; }
+    fp.stage_probe = plan->stage_probe;
     ASR_CUDA_TRY(launch_tiles_path(fp, plan->sm_count, tlo.smem_bytes, plan->cep_smem_bytes + 4 * 128 * p.n_mels,
                                    std::max(1, asr_plan_num_frames(plan, max_length)), as_stream(stream)));
     return ASR_OK;

@@ -157,6 +157,8 @@ struct FParams {
   int cep_off_col;    // cepstra_t_kernel: shared-memory offset (floats) of the [n_mels][128] log-mel column buffer
   int cep_small;      // 1: n_mels <= 32 and the transposed DCT table fits cep_dct: columns in registers, table from the constant bank
   float cep_dct[kCepSmallTab];   // [n_mels][4*NC4] transposed DCT x lifter (cep_small only)
+  int mix_f32;        // 1: fused white-noise mix in float32 with one rounding (timing experiments, ASR_B200_MIX_F32=1); 0: exact
+  float* stage_probe; // parity probe (asr_plan_set_stage_probe): staged samples written back, packed like the audio; or null
 };
 
 cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_bytes, int cep_smem_bytes, int max_frames,
@@ -210,4 +212,5 @@ struct asr_plan {
   // plan-owned workspace for callers that pass none (grown on demand; not safe for concurrent launches)
   void* ws_dev;
   size_t ws_bytes;
+  float* stage_probe;   // asr_plan_set_stage_probe
 };

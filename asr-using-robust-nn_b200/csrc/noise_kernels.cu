@@ -639,6 +639,30 @@ extern "C" int asr_snr_sigma(const float* power_dev, float target_snr_db, double
   return ASR_OK;
 }
 
+// Host side of the SNR chain (VDR/attacks.py:235-241 executed under numpy >= 2 scalar rules, every step float32):
+//   db = 10 * log10(P) ; ndb = db - snr ; w = 10 ** (ndb / 10) ; sigma = sqrt(w)
+// numpy evaluates the scalar `10 ** x` with libm's powf and the other steps with correctly rounded float32 arithmetic,
+// so those are restated here against the same libm.  np.log10 is NOT libm on every host (numpy dispatches to its own
+// SIMD kernels on AVX-512 machines; about half of all inputs then differ from glibc's log10f in the last bit), which is
+// why the caller may hand in log10(P) as numpy computed it (`log10_power_host`); NULL = glibc's log10f.
+// Pure host code: no CUDA call, no device memory.  Built with -ffp-contract=off (no fused multiply-subtract).
+extern "C" int asr_snr_sigma_host(const float* power_host, const float* log10_power_host, float target_snr_db,
+                                  double* sigma_host, int32_t n_clips) {
+  if (!power_host || !sigma_host || n_clips < 0) {
+    set_error("asr_snr_sigma_host: null pointer or negative count");
+    return ASR_ERR_INVALID;
+  }
+  for (int32_t i = 0; i < n_clips; ++i) {
+    const volatile float lg = log10_power_host ? log10_power_host[i] : log10f(power_host[i]);
+    const volatile float db = 10.0f * lg;
+    const volatile float ndb = db - target_snr_db;
+    const volatile float q = ndb / 10.0f;
+    const volatile float w = powf(10.0f, q);
+    sigma_host[i] = static_cast<double>(sqrtf(w));
+  }
+  return ASR_OK;
+}
+
 extern "C" int asr_mix_white(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
                              const int32_t* lengths_dev, int32_t n_clips, const double* z_dev,
                              const double* sigma_dev, double* out_dev, void* stream) {

@@ -94,12 +94,15 @@ __device__ __forceinline__ float tl_log2(const float x) {     // x >= amin > 0
 // 2 consecutive samples from the raw copy -> float32 frame samples (lanes take consecutive pairs: every shared-memory
 // access of the conversion is a dense, conflict-free row).
 // int16 stays UNSCALED (the window table carries the exact 2^-15): bits(2^23 + (s + 32768)) - (2^23 + 32768) = s.
-// Noise: the frame sample is float32 anyway, so int16 / float32 audio is mixed in float32 with one rounding,
-// fma(float(z), sigma, x) - within 1.5 float32 ulp of rounding the reference's float64 x + sigma*z (the standalone mix
-// kernels, whose OUTPUT is the float64 signal, keep the two float64 roundings of VDR/attacks.py:84-85,241-244 bit for bit).
-// float64 audio is mixed in float64.  `sigf` = sigma (x 2^15 for int16).
+// Noise (VDR/attacks.py:241-244): the reference forms float64(x) + sigma*z with two float64 roundings and hands that
+// signal to librosa; the frame sample is its float32 rounding.  EXACT (default): the same two float64 operations
+// (__dmul_rn, __dadd_rn: no FMA contraction) and one conversion, so the staged sample equals float32(reference signal)
+// bit for bit (asr_plan_set_stage_probe reads them back; tests/test_tiles_gpu.py).  `fast` (ASR_B200_MIX_F32=1, timing
+// experiments only): int16 / float32 audio mixed in float32 with one rounding, fma(float(z), sigma, x).
+// `sigf` = float(sigma) (x 2^15 for int16).
 template <int DT, bool NOISE>
-__device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const char* __restrict__ pz, const double sig, const float sigf) {
+__device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const char* __restrict__ pz, const double sig, const float sigf,
+                                           const bool fast) {
   float2 v;
   if constexpr (DT == ASR_I16) {
     const unsigned w = *reinterpret_cast<const unsigned*>(pa) ^ 0x80008000u;
@@ -117,8 +120,19 @@ __device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const ch
   }
   if constexpr (NOISE) {
     const double2 z = *reinterpret_cast<const double2*>(pz);
-    v.x = fmaf(static_cast<float>(z.x), sigf, v.x);
-    v.y = fmaf(static_cast<float>(z.y), sigf, v.y);
+    if (fast) {
+      v.x = fmaf(static_cast<float>(z.x), sigf, v.x);
+      v.y = fmaf(static_cast<float>(z.y), sigf, v.y);
+    } else if constexpr (DT == ASR_I16) {
+      // x = s / 32768 exactly; the staged value is the float32 signal x 32768 (both scalings are exact)
+      const float rx = static_cast<float>(__dadd_rn(static_cast<double>(v.x) * 0.000030517578125, __dmul_rn(sig, z.x)));
+      const float ry = static_cast<float>(__dadd_rn(static_cast<double>(v.y) * 0.000030517578125, __dmul_rn(sig, z.y)));
+      v.x = rx * 32768.0f;
+      v.y = ry * 32768.0f;
+    } else {
+      v.x = static_cast<float>(__dadd_rn(static_cast<double>(v.x), __dmul_rn(sig, z.x)));
+      v.y = static_cast<float>(__dadd_rn(static_cast<double>(v.y), __dmul_rn(sig, z.y)));
+    }
   }
   return v;
 }
@@ -126,7 +140,7 @@ __device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const ch
 // one sample (clip edges): original index o, pa/pz point at original sample 0 of the raw copy
 template <int DT, bool NOISE>
 __device__ __forceinline__ float convert1(const char* __restrict__ pa, const char* __restrict__ pz, const int o, const double sig,
-                                          const float sigf) {
+                                          const float sigf, const bool fast) {
   float x;
   if constexpr (DT == ASR_I16) {
     x = static_cast<float>(reinterpret_cast<const short*>(pa)[o]);          // unscaled
@@ -137,7 +151,13 @@ __device__ __forceinline__ float convert1(const char* __restrict__ pa, const cha
     if constexpr (NOISE) return static_cast<float>(__dadd_rn(xd, __dmul_rn(sig, reinterpret_cast<const double*>(pz)[o])));
     return static_cast<float>(xd);
   }
-  if constexpr (NOISE) x = fmaf(static_cast<float>(reinterpret_cast<const double*>(pz)[o]), sigf, x);
+  if constexpr (NOISE) {
+    const double z = reinterpret_cast<const double*>(pz)[o];
+    if (fast) x = fmaf(static_cast<float>(z), sigf, x);
+    else if constexpr (DT == ASR_I16)
+      x = static_cast<float>(__dadd_rn(static_cast<double>(x) * 0.000030517578125, __dmul_rn(sig, z))) * 32768.0f;
+    else x = static_cast<float>(__dadd_rn(static_cast<double>(x), __dmul_rn(sig, z)));
+  }
   return x;
 }
 
@@ -365,6 +385,9 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
   };
   // raw -> float32 frame samples of a block, once per sample
   const float scale = DT == ASR_I16 ? 32768.0f : 1.0f;   // int16 is staged unscaled (the slow path computes scaled values)
+  const float inv_scale = DT == ASR_I16 ? (1.0f / 32768.0f) : 1.0f;
+  const bool fast_mix = fp.mix_f32 != 0;
+  float* const probe = fp.stage_probe;                   // parity probe: staged samples back to global memory, packed like the audio
   auto convert_block = [&](const TBlock& blk, float* aud) {       // helper warps
     const int nr = blk.n_runs;
     for (int r = 0; r < nr; ++r) {
@@ -376,7 +399,11 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
       const int L = q1.x, o0 = q1.y, count = q1.z, nu = q2.x, ra = q2.y;
       float* dst = aud + q1.w;
       if (nu == 0) {                                    // clip not on a 16-byte boundary: sample by sample from global memory
-        for (int i = ht; i < count; i += 32 * kHelpWarps) dst[i] = padded_at<DT>(fp, base, L, o0 + fp.pad + i, sig) * scale;
+        for (int i = ht; i < count; i += 32 * kHelpWarps) {
+          const float v = padded_at<DT>(fp, base, L, o0 + fp.pad + i, sig);
+          dst[i] = v * scale;
+          if (probe && o0 + i >= 0 && o0 + i < L) probe[base + o0 + i] = v;
+        }
         continue;
       }
       const char* pa = s_raw + q2.w - ra * esz;          // original sample o at pa + o*esz
@@ -387,11 +414,16 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
         if (og >= 0 && og + 128 <= L && c0 + 128 <= count) {       // (warp-uniform) all 128 samples inside the clip
           const char* qa = pa + (og + 2 * lane) * esz;
           const char* qz = pz + (og + 2 * lane) * 8;
-          const float2 v0 = convert2<DT, NOISE>(qa, qz, sig, sigf);
-          const float2 v1 = convert2<DT, NOISE>(qa + 64 * esz, qz + 512, sig, sigf);
+          const float2 v0 = convert2<DT, NOISE>(qa, qz, sig, sigf, fast_mix);
+          const float2 v1 = convert2<DT, NOISE>(qa + 64 * esz, qz + 512, sig, sigf, fast_mix);
           float2* qd = reinterpret_cast<float2*>(dst + c0) + lane;
           qd[0] = v0;
           qd[32] = v1;
+          if (probe) {
+            float* pp = probe + base + og + 2 * lane;
+            pp[0] = v0.x * inv_scale; pp[1] = v0.y * inv_scale;
+            pp[64] = v1.x * inv_scale; pp[65] = v1.y * inv_scale;
+          }
           continue;
         }
 #pragma unroll 1
@@ -406,7 +438,8 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
               bool zero = false;
               if (o < 0) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = -o; }
               else if (o >= L) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = 2 * (L - 1) - o; }
-              e[j] = zero ? 0.0f : convert1<DT, NOISE>(pa, pz, o, sig, sigf);
+              e[j] = zero ? 0.0f : convert1<DT, NOISE>(pa, pz, o, sig, sigf, fast_mix);
+              if (probe && o == orig + j) probe[base + o] = e[j] * inv_scale;     // samples of the clip itself (not their reflections)
             }
             *reinterpret_cast<float2*>(dst + i) = make_float2(e[0], e[1]);
           }

@@ -171,6 +171,14 @@ class MfccPlan:
     def feature_rows(self) -> int:
         return lib.asr_plan_feature_rows(self._h)
 
+    def set_stage_probe(self, staged: Optional[torch.Tensor]) -> None:
+        """Parity probe (asr_plan_set_stage_probe): a float32 CUDA tensor shaped like the batch's audio receives the
+        frame samples the TILES path stages (audio + fused noise, before the window); ``None`` switches it off."""
+        if staged is not None and (staged.dtype != torch.float32 or not staged.is_cuda or not staged.is_contiguous()):
+            raise ValueError("staged must be a contiguous float32 CUDA tensor")
+        self._probe = staged
+        check(lib.asr_plan_set_stage_probe(self._h, 0 if staged is None else staged.data_ptr()), "asr_plan_set_stage_probe")
+
     def launches(self, noisy: bool = False) -> int:
         """Kernels one `mfcc` call launches (1, or 3 on the block-pipelined n_fft = 512 path)."""
         return lib.asr_plan_launches(self._h, int(noisy))
@@ -268,21 +276,21 @@ class MfccPlan:
 
 
 # ---- noise path --------------------------------------------------------------------------------------
-def clip_power(batch: ClipBatch) -> torch.Tensor:
+def clip_power(batch: ClipBatch, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``np.mean(sample**2)`` per clip in float32, numpy's pairwise order (bit-exact)."""
-    out = torch.empty(batch.n_clips, dtype=torch.float32, device=batch.audio.device)
+    if out is None:
+        out = torch.empty(batch.n_clips, dtype=torch.float32, device=batch.audio.device)
+    elif out.dtype != torch.float32 or out.numel() < batch.n_clips or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError("out must be a contiguous float32 CUDA tensor of at least n_clips elements")
     with torch.cuda.device(batch.audio.device):
         check(lib.asr_clip_power(batch.audio.data_ptr(), batch.dtype_code, batch.offsets.data_ptr(),
                                  batch.lengths.data_ptr(), batch.n_clips, out.data_ptr(), _stream()), "asr_clip_power")
     return out
 
 
-def snr_sigma_host(power: np.ndarray, target_snr_db) -> np.ndarray:
-    """The reference's own scalar lines (VDR/attacks.py:235-241) run on ``P``: bit-exact sigma.
-
-    ``power`` is the float32 vector from :func:`clip_power`; numpy scalar semantics keep every step in
-    float32 exactly as ``add_white_noise_with_snr`` does for float32 audio.
-    """
+def snr_sigma_host_scalar(power: np.ndarray, target_snr_db) -> np.ndarray:
+    """The reference's own scalar lines (VDR/attacks.py:235-241) run clip by clip on ``P`` - the definition of the
+    bit-exact sigma (numpy scalar semantics keep every step in float32 for float32 audio).  Slow: a Python loop."""
     out = np.empty(power.shape[0], dtype=np.float64)
     for i in range(power.shape[0]):
         signal_avg_watts = power[i]                       # np.float32 scalar
@@ -290,6 +298,27 @@ def snr_sigma_host(power: np.ndarray, target_snr_db) -> np.ndarray:
         noise_avg_db = signal_avg_db - target_snr_db
         noise_avg_watts = 10 ** (noise_avg_db / 10)
         out[i] = float(np.sqrt(noise_avg_watts))
+    return out
+
+
+def snr_sigma_host(power: np.ndarray, target_snr_db, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Bit-exact sigma for a whole batch in microseconds: the same chain as :func:`snr_sigma_host_scalar`.
+
+    ``np.log10`` is evaluated by numpy itself, vectorised - the ufunc loop a float32 scalar goes through is the same
+    SIMD kernel, so the values are those of the scalar chain on THIS host (numpy does not call libm's log10f on
+    AVX-512 machines).  The scalar ``10 ** x`` of the reference is libm's powf, which numpy's *vectorised* power is
+    not: that step, the float32 multiply / subtract / divide and the square root run in ``asr_snr_sigma_host``
+    (C, same libm).  ``tests/test_host_logic.py`` asserts equality with the scalar chain over a million powers."""
+    P = np.ascontiguousarray(power, dtype=np.float32)
+    if isinstance(target_snr_db, np.floating) and target_snr_db.dtype.itemsize > 4:
+        return snr_sigma_host_scalar(P, target_snr_db)     # a float64 numpy scalar promotes the chain: keep the literal text
+    n = P.shape[0]
+    if out is None:
+        out = np.empty(n, dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        lg = np.log10(P)
+    check(lib.asr_snr_sigma_host(P.ctypes.data, lg.ctypes.data, float(np.float32(target_snr_db)), out.ctypes.data, n),
+          "asr_snr_sigma_host")
     return out
 
 

@@ -93,13 +93,13 @@ def accuracy_vs_snr(models: Sequence[DenseStack], batch, labels: torch.Tensor, s
     mixed with seeded white noise at that SNR inside the MFCC launch, the (N, n_mfcc*T) rows are standardised with the
     statistics `standardizer` was fitted with (train + dev + test rows, VDR/attacks.py:48-69), every model predicts.
     Returns ``{snr: [accuracy per model]}``."""
-    from .frontend import Noise, clip_power, snr_sigma_device, randn
+    from .frontend import Noise, clip_power, snr_sigma_host, randn
     out = {}
-    power = clip_power(batch)
+    power = clip_power(batch).cpu().numpy()               # bit-exact P; the sigma chain is the reference's own (host)
     n = batch.audio.shape[0]
     for i, snr in enumerate(snrs):
         z = randn(seed + i, 0, n, device=batch.audio.device)
-        noise = Noise.white(z, snr_sigma_device(power, float(snr)))
+        noise = Noise.white(z, torch.from_numpy(snr_sigma_host(power, snr)).to(z.device))
         feats, _ = plan.mfcc(batch, out_frames=out_frames, noise=noise)
         rows = standardizer.transform(feats.reshape(feats.shape[0], -1), out_dtype=torch.float32)
         out[snr] = [m.accuracy(rows, labels) for m in models]

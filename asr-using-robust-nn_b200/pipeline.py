@@ -6,6 +6,14 @@ all-reduced over NCCL when sharded) -> standardised ``(B, n_mfcc*T)`` rows.  Mir
 of ``Voice digit recogniton/attacks.py:402-407`` (``black_box_attack_on_audio_dataset_snr`` then
 ``standardize_dataset``).
 
+Sigma is the reference's own chain (``sigma_mode="host"``, the default): the device computes ``P = mean(x**2)`` bit
+for bit, its 4*B bytes go to pinned host memory, ``frontend.snr_sigma_host`` runs the four lines of
+``attacks.py:235-241`` on it (numpy's log10, libm's powf) and sigma goes back - np.log10 / powf are not correctly
+rounded and differ between hosts, so only the host can reproduce them.  To keep that round trip off the critical
+path a caller that knows its next batch passes ``prefetch=``: the power launch and read-back of the NEXT step are
+enqueued in front of THIS step's MFCC launch, so the host chain of step i+1 runs while the GPU is busy with step i.
+``sigma_mode="device"`` evaluates the chain in float64 on the device (within 1 ulp of the host chain, not equal).
+
 The launches of one step are short (tens of microseconds each) and their number is fixed, so the step is
 captured once per (batch buffers, SNR) in CUDA graphs and replayed: one graph per launch group, the
 groups being separated by the two NCCL all-reduces of the standardisation when clips are sharded over
@@ -19,13 +27,14 @@ from typing import Optional
 
 import torch
 
-from .frontend import ClipBatch, MfccPlan, Noise, Standardizer, clip_power, snr_sigma_device, randn
+from .frontend import ClipBatch, MfccPlan, Noise, Standardizer, clip_power, snr_sigma_device, snr_sigma_host, randn
 from .params import MfccParams
 
 # kernels of libasr_b200 launched by one `run_device` step besides the MFCC launches (`plan.launches`):
-# 2x colsum (partial + final), mean, finalize, apply; + power and sigma when noisy; the e2e step adds randn
+# 2x colsum (partial + final), mean, finalize, apply; + power (and the sigma kernel in device mode) when noisy; the
+# e2e step adds randn
 LAUNCHES_CMVN = 7
-LAUNCHES_NOISE = 2
+LAUNCHES_NOISE = 1
 
 
 class _StepGraphs:
@@ -39,7 +48,7 @@ class _StepGraphs:
 
 class NoisyFeaturePipeline:
     def __init__(self, params: MfccParams, out_frames: int, device=None, distributed: bool = False, group=None,
-                 world_size: int = 1, use_graphs: bool = True, path: str = "auto"):
+                 world_size: int = 1, use_graphs: bool = True, path: str = "auto", sigma_mode: str = "host"):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.plan = MfccPlan(params, self.device.index, path=path)
         self.out_frames = int(out_frames)
@@ -52,12 +61,73 @@ class NoisyFeaturePipeline:
         # opt-in (ASR_B200_CAPTURE_COLLECTIVES=1): capture the NCCL all-reduces inside the step's graph.  Measured: identical
         # rows, no gain at 8 GPUs (0.891 vs 0.888 ms per step) and the process group then takes minutes to tear down at exit.
         self.capture_collectives = os.environ.get("ASR_B200_CAPTURE_COLLECTIVES", "0") == "1"
+        if sigma_mode not in ("host", "device"):
+            raise ValueError("sigma_mode must be 'host' (the reference's chain, bit-exact) or 'device'")
+        self.sigma_mode = sigma_mode
+        self._sig = None             # host-sigma state: two pinned slots, one device sigma vector
         self._feats = None
         self._cache: dict = {}
         self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch (eager steps only)
 
     def launches_per_step(self, noisy: bool, standardize: bool = True) -> int:
-        return self.plan.launches(noisy) + (LAUNCHES_NOISE if noisy else 0) + (LAUNCHES_CMVN if standardize else 0)
+        noise = (LAUNCHES_NOISE + (1 if self.sigma_mode == "device" else 0)) if noisy else 0
+        return self.plan.launches(noisy) + noise + (LAUNCHES_CMVN if standardize else 0)
+
+    # ---- sigma: device power -> host chain -> device sigma, one step ahead when the caller prefetches -----------
+    @staticmethod
+    def _bkey(batch):
+        return (batch.audio.data_ptr(), batch.n_clips, batch.max_length)
+
+    def _sig_state(self, B: int):
+        st = self._sig
+        if st is None or st["cap"] < B:
+            st = {"cap": B, "turn": 0, "pending": {},
+                  "sigma_dev": torch.empty(B, dtype=torch.float64, device=self.device),
+                  "slots": [{"P_dev": torch.empty(B, dtype=torch.float32, device=self.device),
+                             "P_host": torch.empty(B, dtype=torch.float32).pin_memory(),
+                             "sig_host": torch.empty(B, dtype=torch.float64).pin_memory(),
+                             "event": torch.cuda.Event()} for _ in range(2)]}
+            self._sig = st
+            self._cache.clear()                            # captured graphs reference the old sigma vector
+        return st
+
+    def _submit_power(self, batch) -> int:
+        """Enqueue power + read-back of `batch` on the current stream; returns the slot."""
+        st = self._sig_state(batch.n_clips)
+        k = st["turn"]
+        st["turn"] ^= 1
+        for key in [key for key, v in st["pending"].items() if v == k]:
+            del st["pending"][key]                         # a prefetch that was never consumed loses its slot
+        sl = st["slots"][k]
+        B = batch.n_clips
+        clip_power(batch, out=sl["P_dev"])
+        sl["P_host"][:B].copy_(sl["P_dev"][:B], non_blocking=True)
+        sl["event"].record()
+        return k
+
+    def prefetch_power(self, batch) -> None:
+        """Enqueue the power pass of a batch a later `run_device(..., snr_db)` will use (host sigma mode)."""
+        if self.sigma_mode == "host":
+            self._sig_state(batch.n_clips)
+            self._sig["pending"][self._bkey(batch)] = self._submit_power(batch)
+
+    def _sigma_for(self, batch, snr_db, prefetch) -> torch.Tensor:
+        """Device sigma vector for this step (valid in stream order until the next call)."""
+        if self.sigma_mode == "device":
+            return snr_sigma_device(clip_power(batch), snr_db)
+        st = self._sig_state(batch.n_clips)
+        k = st["pending"].pop(self._bkey(batch), None)
+        if k is None:
+            k = self._submit_power(batch)
+        if prefetch is not None:
+            self.prefetch_power(prefetch)                   # in front of this step's MFCC launch
+            st = self._sig
+        sl = st["slots"][k]
+        B = batch.n_clips
+        sl["event"].synchronize()
+        snr_sigma_host(sl["P_host"].numpy()[:B], snr_db, out=sl["sig_host"].numpy()[:B])
+        st["sigma_dev"][:B].copy_(sl["sig_host"][:B], non_blocking=True)
+        return st["sigma_dev"][:B]
 
     def _feat_buffer(self, B: int) -> torch.Tensor:
         if self._feats is None or self._feats.shape[0] != B:
@@ -65,10 +135,11 @@ class NoisyFeaturePipeline:
         return self._feats
 
     # ---- the three launch groups of a step ----------------------------------------------------------
-    def _group1(self, batch, z, snr_db, feats):
+    def _group1(self, batch, z, snr_db, feats, sigma=None):
         noise = None
         if snr_db is not None:
-            sigma = snr_sigma_device(clip_power(batch), snr_db)
+            if sigma is None:
+                sigma = snr_sigma_device(clip_power(batch), snr_db)
             noise = Noise.white(z, sigma)
         if self.ev_mfcc is not None:
             self.ev_mfcc[0].record()
@@ -78,26 +149,32 @@ class NoisyFeaturePipeline:
         return noise
 
     def run_device(self, batch: ClipBatch, z: Optional[torch.Tensor], snr_db: Optional[float],
-                   standardize: bool = True, out_dtype=torch.float32) -> torch.Tensor:
-        """Inputs resident in HBM; everything is asynchronous on the current stream."""
+                   standardize: bool = True, out_dtype=torch.float32, prefetch: Optional[ClipBatch] = None) -> torch.Tensor:
+        """Inputs resident in HBM; the launches are asynchronous on the current stream (in host sigma mode the call
+        waits for the 4*B-byte power read-back of THIS batch, which a previous call's ``prefetch=`` has usually
+        already enqueued).  ``prefetch``: the batch of the next noisy call."""
+        sigma = None
+        if snr_db is not None and self.sigma_mode == "host":
+            sigma = self._sigma_for(batch, snr_db, prefetch)
         if self.use_graphs and self.ev_mfcc is None:
-            return self._run_graphed(batch, z, snr_db, standardize, out_dtype)
+            return self._run_graphed(batch, z, snr_db, standardize, out_dtype, sigma)
         feats = self._feat_buffer(batch.n_clips)
-        self._group1(batch, z, snr_db, feats)
+        self._group1(batch, z, snr_db, feats, sigma)
         flat = feats.view(batch.n_clips, self.D)
         if not standardize:
             return flat
         self.std.fit([flat], n_total=batch.n_clips * self.world_size)
         return self.std.transform(flat, out_dtype=out_dtype)
 
-    def _run_graphed(self, batch, z, snr_db, standardize, out_dtype):
-        key = (batch.audio.data_ptr(), batch.n_clips, batch.max_length, None if z is None else z.data_ptr(), snr_db,
-               standardize, out_dtype)
+    def _run_graphed(self, batch, z, snr_db, standardize, out_dtype, sigma=None):
+        # host sigma mode: the graph reads the (fixed) device sigma vector, so one capture serves every SNR
+        key = (batch.audio.data_ptr(), batch.n_clips, batch.max_length, None if z is None else z.data_ptr(),
+               snr_db if sigma is None else (snr_db is not None), standardize, out_dtype)
         sg = self._cache.get(key)
         if sg is None:
             if len(self._cache) > 32:
                 self._cache.clear()
-            sg = self._capture(batch, z, snr_db, standardize, out_dtype)
+            sg = self._capture(batch, z, snr_db, standardize, out_dtype, sigma)
             self._cache[key] = sg
         if len(sg.graphs) == 1:
             sg.graphs[0].replay()
@@ -109,7 +186,7 @@ class NoisyFeaturePipeline:
             sg.graphs[2].replay()
         return sg.out
 
-    def _capture(self, batch, z, snr_db, standardize, out_dtype) -> _StepGraphs:
+    def _capture(self, batch, z, snr_db, standardize, out_dtype, sigma=None) -> _StepGraphs:
         B = batch.n_clips
         n_total = B * self.world_size
         sg = _StepGraphs()
@@ -118,7 +195,7 @@ class NoisyFeaturePipeline:
         out = torch.empty((B, self.D), dtype=out_dtype, device=self.device) if standardize else flat
         sg.out, sg.keep = out, (batch, z, feats)
         # warm the kernels once outside capture (lazy module loading is not capturable)
-        self._group1(batch, z, snr_db, feats)
+        self._group1(batch, z, snr_db, feats, sigma)
         if standardize:
             self.std.fit([flat], n_total=n_total)
             self.std.transform(flat, out=out)
@@ -132,7 +209,7 @@ class NoisyFeaturePipeline:
             sg.graphs.append(g)
 
         def g1():
-            self._group1(batch, z, snr_db, feats)
+            self._group1(batch, z, snr_db, feats, sigma)
             if standardize:
                 self.std.pass1_local([flat])
 
@@ -144,7 +221,7 @@ class NoisyFeaturePipeline:
             self.std.transform(flat, out=out)
 
         if not standardize:
-            cap(lambda: self._group1(batch, z, snr_db, feats))
+            cap(lambda: self._group1(batch, z, snr_db, feats, sigma))
         elif self.distributed:
             # default: three graphs with the two NCCL all-reduces launched between them; opt-in: one graph for the whole
             # step with the all-reduces captured inside it
@@ -168,9 +245,19 @@ class NoisyFeaturePipeline:
         (``n_total`` = sum of ``n_local`` over the ranks), then every row is standardised."""
         feats = torch.empty((n_local, self.rows, self.out_frames), dtype=torch.float32, device=self.device)
         done = 0
-        for batch, z, snr_db in batches:
-            self._group1(batch, z, snr_db, feats[done:done + batch.n_clips])
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is not None and cur[2] is not None:
+            self.prefetch_power(cur[0])
+        while cur is not None:
+            nxt = next(it, None)                             # one batch of look-ahead: its power pass goes in front
+            batch, z, snr_db = cur
+            sigma = None
+            if snr_db is not None and self.sigma_mode == "host":
+                sigma = self._sigma_for(batch, snr_db, nxt[0] if nxt is not None and nxt[2] is not None else None)
+            self._group1(batch, z, snr_db, feats[done:done + batch.n_clips], sigma)
             done += batch.n_clips
+            cur = nxt
         if done != n_local:
             raise ValueError(f"the batches held {done} clips, expected {n_local}")
         flat = feats.view(n_local, self.D)

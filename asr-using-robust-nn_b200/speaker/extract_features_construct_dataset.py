@@ -112,12 +112,12 @@ def compute_mfcc_all_files(filenames):
     return out.reshape(out.shape[0], -1).cpu().numpy()
 
 
+# the 20 RoDigits speaker folders the reference keeps, in label order (SR reference :116-117)
+SPEAKERS = ('006', '041', '043', '044', '045', '046', '047', '048', '049', '105', '117', '118', '211', '212',
+            '213', '214', '215', '260', '261', '420')
+
+
 def get_file_names_and_labels(data_dir):
-    speakers = sorted(d for d in os.listdir(data_dir) if os.path.isdir(os.path.join(data_dir, d)))
-    filenames, labels = [], []
-    for index, spk in enumerate(speakers):
-        for f in sorted(os.listdir(os.path.join(data_dir, spk))):
-            if f.lower().endswith(".wav"):
-                filenames.append(os.path.join(data_dir, spk, f))
-                labels.append(index)
-    return np.array(filenames), np.array(labels, dtype=np.int32)
+    """SR reference :113-137: the same whitelist-in-list-order rule as the digit corpus."""
+    from ..voice_digit.extract_features_construct_dataset import _listed_classes
+    return _listed_classes(data_dir, SPEAKERS)

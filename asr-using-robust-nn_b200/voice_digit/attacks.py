@@ -130,12 +130,15 @@ def _features(batch, noise, utterance_length, params=None):
 
 
 def _draw_like(batch, n_streams=1):
-    """Per clip, in order, `n_streams` standard-normal draws of the clip's length (the reference's order)."""
-    streams = [[] for _ in range(n_streams)]
-    for n in batch.lengths_host:
-        for s in streams:
-            s.append(np.random.standard_normal(int(n)))
-    return [ClipBatch.from_arrays(s).audio for s in streams]
+    """Per clip, in order, `n_streams` standard-normal draws of the clip's length (the reference's order), written at
+    the AUDIO batch's own offsets: the kernels index the noise streams exactly like the audio, whatever its packing."""
+    total = int(batch.audio.shape[0])
+    hosts = [torch.zeros(total, dtype=torch.float64).pin_memory() for _ in range(n_streams)]
+    views = [h.numpy() for h in hosts]
+    for o, n in zip(batch.offsets_host, batch.lengths_host):
+        for v in views:
+            v[int(o):int(o) + int(n)] = np.random.standard_normal(int(n))
+    return [h.to(batch.audio.device, non_blocking=True) for h in hosts]
 
 
 def black_box_attack_on_waveforms(waves, sigma=0, p=0, alpha=0, utterance_length=UTTERANCE_LENGTH, params=None):

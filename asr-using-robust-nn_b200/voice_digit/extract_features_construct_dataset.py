@@ -72,13 +72,27 @@ def compute_mfcc_all_files(filenames):
     return compute_mfcc_all_waveforms(audio_io.load_batch(list(filenames), sr=PARAMS.sr))
 
 
-def get_file_names_and_labels(data_dir):
-    """Folders under ``data_dir`` are the classes, label = folder index (reference :118-140)."""
-    commands = sorted(d for d in os.listdir(data_dir) if os.path.isdir(os.path.join(data_dir, d)))
+# class folders of the Speech Commands corpus that the reference keeps, in label order (reference :120)
+DIGITS = ('zero', 'one', 'two', 'three', 'four', 'five', 'six', 'seven', 'eight', 'nine')
+
+
+def _listed_classes(data_dir, classes):
+    """Reference :118-140: only the folders named in the fixed class list are taken, in the order of that list;
+    label = position among the folders that are present (0..9 when all ten exist); every entry of a class folder is
+    a file of that class, in sorted (glob) order."""
+    present = set(os.listdir(data_dir))
     filenames, labels = [], []
-    for index, command in enumerate(commands):
-        for f in sorted(os.listdir(os.path.join(data_dir, command))):
-            if f.lower().endswith(".wav"):
-                filenames.append(os.path.join(data_dir, command, f))
-                labels.append(index)
+    i = 0
+    for name in classes:
+        if name not in present:
+            continue
+        folder = os.path.join(data_dir, name)
+        entries = sorted(os.listdir(folder))
+        filenames += [os.path.join(folder, f) for f in entries]
+        labels += [i] * len(entries)
+        i += 1
     return np.array(filenames), np.array(labels, dtype=np.int32)
+
+
+def get_file_names_and_labels(data_dir):
+    return _listed_classes(data_dir, DIGITS)

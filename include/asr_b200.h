@@ -87,11 +87,10 @@ typedef struct asr_mfcc_params {
  *                                    (add_white_noise_with_snr, sigma[b] from the SNR chain)
  *   MIXTURE  x + (|q|<p ? s1:s0)*g   VDR/attacks.py:145-183 (mixtgauss / add_noise)
  * z / q / g are float64 standard-normal streams laid out like the audio (same offsets).
- * The MFCC arithmetic is float32, so the fused mix only has to deliver the float32 rounding of
- * the reference's float64 signal: CLIP and FRAMES mix in float64 with two separately rounded
- * operations (no FMA) and round once; TILES mixes int16 / float32 audio directly in float32,
- * fma(float(z), sigma, x), within 1.5 float32 ulp of that.  The standalone asr_mix_* kernels,
- * whose OUTPUT is the float64 noisy signal, are bit-exact.
+ * The MFCC arithmetic is float32, so the fused mix delivers the float32 rounding of the reference's float64
+ * signal: every path (CLIP, FRAMES, TILES) mixes in float64 with two separately rounded operations (no FMA) and
+ * rounds once - bit-equal to float32(reference signal) (asr_plan_set_stage_probe reads the staged samples back).
+ * The standalone asr_mix_* kernels, whose OUTPUT is the float64 noisy signal, are bit-exact as well.
  */
 typedef enum asr_noise_mode { ASR_NOISE_NONE = 0, ASR_NOISE_WHITE = 1, ASR_NOISE_MIXTURE = 2 } asr_noise_mode;
 
@@ -174,6 +173,12 @@ int32_t asr_plan_path_used(const asr_plan* plan, int32_t dtype, int32_t noise_mo
 /* Kernel launches one asr_mfcc_batch call makes with this plan: 1 (CLIP) or 3 (FRAMES, TILES); `noisy` as in the call. */
 int32_t asr_plan_launches(const asr_plan* plan, int32_t noisy);
 
+/* Parity probe of the fused noise mix (TILES path): while `staged_dev` is non-NULL, every launch of this plan on the
+ * TILES path also writes the float32 frame samples it staged - decoded audio with the noise mixed in, BEFORE the window -
+ * to staged_dev[offsets[b] + i] (float32, packed exactly like the audio; int16 audio is reported in [-1, 1) units).
+ * With white noise these equal float32(add_white_noise_with_snr(...)) of VDR/attacks.py:222-245 bit for bit.  NULL = off. */
+int asr_plan_set_stage_probe(asr_plan* plan, float* staged_dev);
+
 /* Stage-level probe for parity tests: the clamped log-mel matrix [n_clips][n_mels][out_frames] (float32). */
 int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
                      const int32_t* lengths_dev, int32_t n_clips, int32_t max_length, const asr_noise* noise,
@@ -191,6 +196,14 @@ int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_t* offsets_
  * (VDR/attacks.py:235-241 under numpy >= 2 scalar rules), evaluated on the device in float64
  * and rounded; the host-exact alternative is to run those four numpy lines on P. */
 int asr_snr_sigma(const float* power_dev, float target_snr_db, double* sigma_dev, int32_t n_clips, void* stream);
+
+/* The same chain on the HOST, bit-exact with the reference text under numpy >= 2 (every step float32; `10 ** x` is
+ * libm powf there).  HOST pointers, no CUDA call.  `log10_power_host` (may be NULL = glibc log10f) carries log10(P) as
+ * the caller's numpy computed it: np.log10 is not glibc's log10f on AVX-512 hosts (numpy's own SIMD kernel), so a
+ * Python caller passes np.log10(P) to stay bit-equal with the reference on ITS host.  This is the default of the
+ * Python pipeline (asr_b200.pipeline): power on the device -> 4*B bytes to the host -> this call -> sigma back. */
+int asr_snr_sigma_host(const float* power_host, const float* log10_power_host, float target_snr_db,
+                       double* sigma_host, int32_t n_clips);
 
 /* out = float64(x) + sigma[b]*z   (two roundings, no FMA) - VDR/attacks.py:84-85, :241-244 */
 int asr_mix_white(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
@@ -245,6 +258,13 @@ int asr_resample_batch(const void* in_dev, int32_t dtype, const int64_t* in_offs
                        int32_t n_clips, int32_t max_in_length, int32_t up, int32_t down, const float* taps_dev,
                        int32_t n_taps, int32_t n_pre_remove, float* out_dev, const int64_t* out_offsets_dev,
                        void* stream);
+
+/* ---- diagnostics ----
+ * Self-test of the tcgen05 / TMEM plumbing the tensor-core path of asr_mfcc_batch relies on:
+ * D[128][32] = A1[128][32] * B1[32][32]^T + A2 * B2^T with float16 operands (row-major, K contiguous) and float32
+ * accumulation; d_dev receives D twice (2 x 128 x 32 floats: block loads, then strided two-column loads). */
+int asr_tc_selftest(const void* a1_dev, const void* b1_dev, const void* a2_dev, const void* b2_dev, float* d_dev,
+                    void* stream);
 
 /* ---- host-buffer entry points (what a ctypes binding on the reference side calls) ----------
  * Synchronous; host<->device copies are pipelined in chunks over two streams inside. */

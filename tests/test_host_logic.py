@@ -60,6 +60,28 @@ def test_snr_sigma_host_is_the_reference_chain():
         assert got.dtype == np.float64 and np.array_equal(got, want)
 
 
+def test_snr_sigma_host_vectorised_equals_scalar_chain_on_a_million_powers():
+    """The batch form used by the benchmarked pipeline (numpy log10 vectorised + libm powf chain in C) against the
+    reference's scalar lines: zero mismatches over >= 10^6 float32 powers spanning 1e-8 .. 1 (and the edge values)."""
+    rng = np.random.default_rng(11)
+    mism = 0
+    total = 0
+    for snr in (0, 5, 10, 20):
+        P = (10.0 ** rng.uniform(-8.0, 0.0, 262144)).astype(np.float32)
+        P[:6] = np.array([0.0, 1.0, 1e-8, np.float32(2.0) ** -126, 3.0517578e-05, 0.99999994], dtype=np.float32)
+        with np.errstate(divide="ignore"):
+            want = A.snr_sigma_host_scalar(P, snr)
+        got = A.snr_sigma_host(P, snr)
+        mism += int((got.view(np.uint64) != want.view(np.uint64)).sum())
+        total += P.shape[0]
+    assert total >= 10 ** 6 and mism == 0
+    # python-float and float32 targets keep the chain in float32; a float64 numpy scalar promotes it (literal text)
+    P = (10.0 ** rng.uniform(-6.0, 0.0, 512)).astype(np.float32)
+    assert np.array_equal(A.snr_sigma_host(P, 7.5), A.snr_sigma_host_scalar(P, 7.5))
+    assert np.array_equal(A.snr_sigma_host(P, np.float32(7.3)), A.snr_sigma_host_scalar(P, np.float32(7.3)))
+    assert np.array_equal(A.snr_sigma_host(P, np.float64(7.3)), A.snr_sigma_host_scalar(P, np.float64(7.3)))
+
+
 def test_sr_window_index_matches_reference_trim_split():
     """SR/extract...py:211-222 via index arithmetic == slicing the waveform."""
     sr = 50
@@ -75,19 +97,31 @@ def test_sr_window_index_matches_reference_trim_split():
 
 
 def test_file_listing_and_labels(tmp_path):
-    """Folders are classes, label = folder index (VDR/extract...py:118-140)."""
-    for d, n in (("zero", 2), ("one", 1), ("two", 3)):
+    """The reference's fixed class list, in list order, other folders ignored (VDR/extract...py:118-140, SR :113-137)."""
+    for d, n in (("zero", 2), ("one", 1), ("two", 3), ("bed", 2), ("nine", 1)):
         os.makedirs(tmp_path / d)
         for i in range(n):
             (tmp_path / d / f"a{i}.wav").write_bytes(b"")
-        (tmp_path / d / "notes.txt").write_text("x")
     files, labels = vdr_efcd.get_file_names_and_labels(str(tmp_path))
-    assert labels.dtype == np.int32 and len(files) == 6
-    assert sorted(set(labels)) == [0, 1, 2]
+    assert labels.dtype == np.int32 and len(files) == 7          # "bed" is not a digit: ignored
     by = {os.path.basename(os.path.dirname(f)): l for f, l in zip(files, labels)}
-    assert by == {"one": 0, "two": 1, "zero": 2}            # sorted folder order
-    files2, labels2 = sr_efcd.get_file_names_and_labels(str(tmp_path))
-    assert list(files2) == list(files) and np.array_equal(labels, labels2)
+    assert by == {"zero": 0, "one": 1, "two": 2, "nine": 3}       # position among the PRESENT classes, list order
+    assert list(labels) == sorted(labels)
+    # all ten present -> label = digit value
+    for d in vdr_efcd.DIGITS:
+        os.makedirs(tmp_path / d, exist_ok=True)
+        (tmp_path / d / "z.wav").write_bytes(b"")
+    files, labels = vdr_efcd.get_file_names_and_labels(str(tmp_path))
+    by = {os.path.basename(os.path.dirname(f)): l for f, l in zip(files, labels)}
+    assert by == {d: i for i, d in enumerate(vdr_efcd.DIGITS)}
+    # speaker corpus: 20 listed IDs, in list order
+    sp = tmp_path / "spk"
+    for d in ("420", "006", "999", "105"):
+        os.makedirs(sp / d)
+        (sp / d / "u.wav").write_bytes(b"")
+    files2, labels2 = sr_efcd.get_file_names_and_labels(str(sp))
+    by2 = {os.path.basename(os.path.dirname(f)): l for f, l in zip(files2, labels2)}
+    assert by2 == {"006": 0, "105": 1, "420": 2} and labels2.dtype == np.int32
 
 
 def test_wav_decode_and_resample(tmp_path):

@@ -73,3 +73,31 @@ def test_corpus_in_batches_equals_one_shot():
     parts = [(A.ClipBatch.from_matrix(audio[i:i + 16].contiguous()), None, None) for i in range(0, B, 16)]
     many = pipe.run_corpus(iter(parts), B)
     assert torch.equal(one, many)
+
+
+def test_benchmarked_step_uses_the_reference_sigma_chain():
+    """The pipeline bench.py times (graph replay, prefetch of the next step's power) mixes with the reference's own
+    sigma: its rows equal an eager step fed with the scalar host chain, bit for bit, at every SNR."""
+    import asr_b200 as A
+    from asr_b200.pipeline import NoisyFeaturePipeline
+    B, L = 96, 16000
+    clips = synth_clips(B, L, 16000, 808)
+    audio = torch.from_numpy(np.stack(clips)).cuda()
+    batch = A.ClipBatch.from_matrix(audio)
+    z = A.randn(3, 0, B * L)
+    pipe = NoisyFeaturePipeline(A.C1, 101)
+    assert pipe.sigma_mode == "host"
+    plan = A.MfccPlan(A.C1)
+    std = A.Standardizer(pipe.D)
+    P = A.clip_power(batch).cpu().numpy()
+    for snr in (0, 5, 10, 20, 0, 5):
+        got = pipe.run_device(batch, z, snr, prefetch=batch).clone()
+        sigma = torch.from_numpy(A.snr_sigma_host_scalar(P, snr)).cuda()
+        feats, _ = plan.mfcc(batch, out_frames=101, noise=A.Noise.white(z, sigma))
+        flat = feats.reshape(B, -1)
+        std.fit([flat])
+        want = std.transform(flat, out_dtype=torch.float32)
+        assert torch.equal(got, want), snr
+    dev = NoisyFeaturePipeline(A.C1, 101, sigma_mode="device")
+    out = dev.run_device(batch, z, 10)
+    assert torch.isfinite(out).all()

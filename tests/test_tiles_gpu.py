@@ -77,3 +77,38 @@ def test_rows_do_not_depend_on_batch_composition():
     for i in (0, 3, 350, 699):
         one, _ = plan.mfcc(A.ClipBatch.from_arrays([clips[i]]))
         assert torch.equal(one[0], full[i])
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.float32])
+def test_fused_mix_staged_samples_are_bit_exact(dtype):
+    """The samples the TILES kernel stages with noise fused - what its FFT sees - equal float32(reference signal) bit
+    for bit: float32(add_white_noise_with_snr(x, snr)) of VDR/attacks.py:222-245 given the same z, with sigma from the
+    reference's own chain.  Ragged lengths: clip edges, element tails, blocks holding pieces of several clips."""
+    import asr_b200 as A
+    from oracle import noise_ref as nr
+    rng = np.random.default_rng(3)
+    lengths = [16000, 16000, 4001, 9999, 12345, 16000, 257, 15992] + rng.integers(3000, 17000, size=56).tolist()
+    base = synth_clips(len(lengths), 17000, 16000, 77)
+    clips = [b[:n] for b, n in zip(base, lengths)]
+    if dtype == np.float32:
+        clips = to_f32(clips)
+    batch = A.ClipBatch.from_arrays(clips)
+    plan = A.MfccPlan(A.C1, path="tiles")
+    assert plan.path_used(dtype, noisy=True) == "tiles"
+    xs = clips if dtype == np.float32 else to_f32(clips)
+    for snr in (0, 10, 20):
+        z = A.randn(40 + snr, 0, batch.audio.shape[0])
+        sigma = A.snr_sigma_host(A.clip_power(batch).cpu().numpy(), snr)
+        staged = torch.full((batch.audio.shape[0],), float("nan"), dtype=torch.float32, device="cuda")
+        plan.set_stage_probe(staged)
+        out, status = plan.mfcc(batch, noise=A.Noise.white(z, torch.from_numpy(sigma).cuda()))
+        torch.cuda.synchronize()
+        plan.set_stage_probe(None)
+        assert int(status.max()) == 0
+        got = batch.unpack(staged)
+        zs = batch.unpack(z)
+        bad = 0
+        for i, (x, zz) in enumerate(zip(xs, zs)):
+            want = nr.add_white_noise_with_snr_z(x, snr, zz).astype(np.float32)   # float64 reference signal, rounded once
+            bad += int((got[i].view(np.uint32) != want.view(np.uint32)).sum())
+        assert bad == 0, (snr, bad)
