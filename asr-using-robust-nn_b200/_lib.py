@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libasr_b200.so")
 ASR_I16, ASR_F32, ASR_F64 = 0, 1, 2
 ASR_NOISE_NONE, ASR_NOISE_WHITE, ASR_NOISE_MIXTURE = 0, 1, 2
 ASR_CLIP_OK, ASR_CLIP_TOO_SHORT, ASR_CLIP_TOO_FEW_FRAMES = 0, 1, 2
-ASR_PATH_AUTO, ASR_PATH_CLIP, ASR_PATH_FRAMES, ASR_PATH_TILES = 0, 1, 2, 3
+ASR_PATH_AUTO, ASR_PATH_CLIP, ASR_PATH_FRAMES, ASR_PATH_TILES, ASR_PATH_TC = 0, 1, 2, 3, 4
 
 
 class AsrError(RuntimeError):
@@ -55,6 +55,7 @@ SIGNATURES = {
     "asr_plan_uses_fft": (_i32, [_vp]),
     "asr_plan_get_tables": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "asr_plan_set_stage_probe": (C.c_int, [_vp, _vp]),
+    "asr_plan_debug_word": (_i32, [_vp, _i32]),
     "asr_tc_selftest": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "asr_mfcc_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(NoiseC), _vp, _i32, _i32, _vp,
                                  _vp, C.c_size_t, _vp]),

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace asr {
@@ -355,6 +356,146 @@ static bool build_tile_tables_all(asr_plan* pl, const std::vector<double>& mel_f
   return true;
 }
 
+// ---- tables of the tensor-core path (tc_kernel.cu), n_fft = 512, int16 audio ---------------------------------
+// Pass 1 of the 16 x 16 decomposition of the 256-point complex FFT behind the real 512-point FFT, per residue b:
+//   Y_b[c] = W256^(b c) * sum_a W16^(a c) * (w[2n] x[2n] + i w[2n+1] x[2n+1]),  n = b + 16 a
+// as a real 32 x 32 matrix M_b (rows 2c + re/im, columns 2a + even/odd sample) in float64, stored as float16 pairs:
+// 16 M = MH1 + MH2 (value + residual), M / 128 = ML; see the head of tc_kernel.cu for the operand split they multiply.
+// The mel bank in segment form (as for the tiles path), dealt out to the 4 warps of a TMEM lane quarter; a filter whose
+// terms all lie in one share is finished in registers ("direct"), the others go through boundary slots.
+static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, const std::vector<double>& fftfreqs) {
+  const asr_mfcc_params& p = pl->prm;
+  pl->tc_ok = 0;
+  if (!pl->tl_ok || (p.hop_length % 32) != 0 || p.n_mels > 254) return true;
+  const int n_bins = pl->n_bins, n_mels = p.n_mels, wl = pl->win_length, lpad = (p.n_fft - wl) / 2;
+  auto wind = [&](int i) -> double {            // the float64 window librosa multiplies the frames with
+    const int n = i - lpad;
+    if (n < 0 || n >= wl) return 0.0;
+    const double a0 = p.window == ASR_WIN_HANN ? 0.5 : 0.54, a1 = 1.0 - a0;
+    return wl == 1 ? 1.0 : a0 - a1 * std::cos(2.0 * kPi * n / wl);
+  };
+  std::vector<__half> mats(static_cast<size_t>(16) * 3 * 32 * 32);
+  auto put = [&](int b, int mat, int n, int k, double v) {
+    mats[(((static_cast<size_t>(b) * 3 + mat) * 4 + k / 8) * 32 + n) * 8 + k % 8] = __float2half_rn(static_cast<float>(v));
+  };
+  for (int b = 0; b < 16; ++b)
+    for (int c = 0; c < 16; ++c)
+      for (int a = 0; a < 16; ++a) {
+        const double th = 2.0 * kPi * (b * c / 256.0 + a * c / 16.0);
+        const double tr = std::cos(th), ti = -std::sin(th);
+        const int n = b + 16 * a;
+        const double we = wind(2 * n), wo = wind(2 * n + 1);
+        const double m[2][2] = {{tr * we, -ti * wo}, {ti * we, tr * wo}};      // [re/im of Y][even/odd sample]
+        for (int ri = 0; ri < 2; ++ri)
+          for (int eo = 0; eo < 2; ++eo) {
+            const double mh = 16.0 * m[ri][eo];
+            const __half h1 = __float2half_rn(static_cast<float>(mh));
+            put(b, 0, 2 * c + ri, 2 * a + eo, mh);
+            put(b, 1, 2 * c + ri, 2 * a + eo, mh - static_cast<double>(__half2float(h1)));
+            put(b, 2, 2 * c + ri, 2 * a + eo, m[ri][eo] / 128.0);
+          }
+      }
+  // ---- mel bank: steps (4 bins of one segment), 4 contiguous shares ----
+  std::vector<int> seg(n_bins);
+  for (int k = 0; k < n_bins; ++k) {
+    int sg = 0;
+    while (sg < n_mels && mel_f[sg + 1] <= fftfreqs[k]) ++sg;
+    seg[k] = sg;
+  }
+  auto W = [&](int i, int k) { return (i >= 0 && i < n_mels) ? pl->h_mel_dense[static_cast<size_t>(i) * n_bins + k] : 0.0f; };
+  struct Step { int q, seg; };
+  std::vector<Step> steps;
+  for (int sg = 0; sg <= n_mels; ++sg) {
+    int k0 = -1, k1 = -1;
+    for (int k = 0; k < n_bins; ++k)
+      if (seg[k] == sg && (W(sg - 1, k) != 0.0f || W(sg, k) != 0.0f)) { if (k0 < 0) k0 = k; k1 = k + 1; }
+    if (k0 < 0) continue;
+    for (int q = k0 / 4; q <= (k1 - 1) / 4; ++q) steps.push_back({q, sg});
+  }
+  const int ns = static_cast<int>(steps.size());
+  if (ns < 4) return true;
+  struct Piece { int q0, nsteps, w0, filter, group; };
+  std::vector<Piece> pieces;
+  std::vector<float> wtab;
+  std::vector<int> wrange(2 * 4, 0);
+  std::vector<std::vector<int>> contrib(n_mels);            // per filter: indices of the pieces that emit it
+  const float scale = 1.0f / 1073741824.0f;                 // the spectrum in TMEM is 2^30 |X|^2 (exact scaling)
+  for (int g = 0; g < 4; ++g) {
+    const int a = static_cast<int>(static_cast<long long>(g) * ns / 4), b = static_cast<int>(static_cast<long long>(g + 1) * ns / 4);
+    wrange[2 * g] = static_cast<int>(pieces.size());
+    int i = a;
+    for (int sg = steps[a].seg; sg <= steps[b - 1].seg; ++sg) {
+      Piece pc{0, 0, static_cast<int>(wtab.size() / 4), sg - 1, g};
+      if (i < b && steps[i].seg == sg) {
+        pc.q0 = steps[i].q;
+        while (i < b && steps[i].seg == sg) {
+          if (steps[i].q != pc.q0 + pc.nsteps) return true;            // steps of a segment are consecutive float4 groups
+          for (int e = 0; e < 4; ++e) {
+            const int k = 4 * steps[i].q + e;
+            const bool in = k < n_bins && seg[k] == sg;
+            wtab.push_back(in ? scale * W(sg - 1, k) : 0.0f);
+            wtab.push_back(in ? scale * W(sg, k) : 0.0f);
+          }
+          ++pc.nsteps; ++i;
+        }
+      }
+      pieces.push_back(pc);
+    }
+    pieces.push_back(Piece{0, 0, static_cast<int>(wtab.size() / 4), steps[b - 1].seg, g});   // the pending rise sum
+    wrange[2 * g + 1] = static_cast<int>(pieces.size()) - wrange[2 * g];
+  }
+  for (size_t i = 0; i < pieces.size(); ++i)
+    if (pieces[i].filter >= 0 && pieces[i].filter < n_mels) contrib[pieces[i].filter].push_back(static_cast<int>(i));
+  std::vector<int> ptab(4 * pieces.size(), 0), bnd;
+  int n_slots = 0;
+  for (size_t i = 0; i < pieces.size(); ++i) {
+    ptab[4 * i] = pieces[i].q0; ptab[4 * i + 1] = pieces[i].nsteps; ptab[4 * i + 2] = pieces[i].w0; ptab[4 * i + 3] = 0;
+  }
+  for (int f = 0; f < n_mels; ++f) {
+    const std::vector<int>& cl = contrib[f];
+    if (cl.size() == 1) { ptab[4 * cl[0] + 3] = f + 1; continue; }
+    bnd.push_back(f); bnd.push_back(n_slots); bnd.push_back(static_cast<int>(cl.size())); bnd.push_back(0);
+    for (int pi : cl) { ptab[4 * pi + 3] = (f + 1) | ((n_slots + 1) << 16); ++n_slots; }
+  }
+  if (n_slots > 16) return true;
+  pl->tc_n_slots = std::max(1, n_slots);
+  pl->tc_n_bnd = static_cast<int>(bnd.size() / 4);
+  std::vector<float> blob;
+  auto put_f = [&](const float* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.insert(blob.end(), src, src + n);
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  auto put_i = [&](const int* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.resize(blob.size() + n);
+    if (n) std::memcpy(blob.data() + off, src, n * sizeof(int));
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  pl->tc_off_wtab = put_f(wtab.data(), wtab.size());
+  pl->tc_off_pieces = put_i(ptab.data(), ptab.size());
+  pl->tc_off_wrange = put_i(wrange.data(), wrange.size());
+  if (bnd.empty()) bnd.assign(4, 0);
+  pl->tc_off_bnd = put_i(bnd.data(), bnd.size());
+  pl->tc_blob_f4 = static_cast<int>(blob.size() / 4);
+  if (cudaMalloc(&pl->tc_mats_dev, mats.size() * sizeof(__half)) != cudaSuccess) return false;
+  if (cudaMemcpy(pl->tc_mats_dev, mats.data(), mats.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  if (cudaMalloc(reinterpret_cast<void**>(&pl->tc_blob_dev), blob.size() * sizeof(float)) != cudaSuccess) return false;
+  if (cudaMemcpy(pl->tc_blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  if (tc_upload_constants() != cudaSuccess) return false;
+  if (cudaHostAlloc(reinterpret_cast<void**>(&pl->tc_dbg_host), 16 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    std::memset(pl->tc_dbg_host, 0, 16 * sizeof(int));
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&pl->tc_dbg_dev), pl->tc_dbg_host, 0) != cudaSuccess) pl->tc_dbg_dev = nullptr;
+  } else {
+    cudaGetLastError();
+    pl->tc_dbg_host = nullptr; pl->tc_dbg_dev = nullptr;
+  }
+  pl->tc_ok = 1;
+  return true;
+}
+
 struct FftShape { int M, G, P; };
 static bool fft_shape(int n_fft, FftShape* s) {
   switch (n_fft) {
@@ -585,7 +726,8 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
     cudaDeviceProp prop;
     pl->sm_count = (cudaGetDeviceProperties(&prop, pl->device) == cudaSuccess) ? prop.multiProcessorCount : 148;
   }
-  if (!build_frames_tables(pl, mel_f, fftfreqs, twp, twu) || !build_tile_tables_all(pl, mel_f, fftfreqs, twp, twu)) {
+  if (!build_frames_tables(pl, mel_f, fftfreqs, twp, twu) || !build_tile_tables_all(pl, mel_f, fftfreqs, twp, twu) ||
+      !build_tc_tables(pl, mel_f, fftfreqs)) {
     const cudaError_t e2 = cudaGetLastError();
     asr_plan_destroy(pl);
     return cuda_fail(e2, "asr_plan_create (frames-path tables)");
@@ -601,6 +743,9 @@ extern "C" void asr_plan_destroy(asr_plan* plan) {
   for (int c = 0; c < 2; ++c)
     if (plan->tl[c].blob_dev) cudaFree(plan->tl[c].blob_dev);
   if (plan->ws_dev) cudaFree(plan->ws_dev);
+  if (plan->tc_mats_dev) cudaFree(plan->tc_mats_dev);
+  if (plan->tc_blob_dev) cudaFree(plan->tc_blob_dev);
+  if (plan->tc_dbg_host) cudaFreeHost(plan->tc_dbg_host);
   delete plan;
 }
 
@@ -700,6 +845,38 @@ bool tiles_layout(const asr_plan* plan, int dtype, int noise_mode, TlLayout* lo)
   }
   return false;
 }
+struct TcLayout { int sm_hl, sm_a, sm_b, sm_slots, hl_stride, hl_rows, smem_bytes; };
+// Shared-memory layout of the tensor-core kernel: mel tables | staging array HL[16][stride] (8 bytes per sample pair) |
+// operand ring (2 x (hi tile + lo tile) of 8 KB) | matrix ring (4 x 6 KB) | boundary slots.
+bool tc_layout(const asr_plan* plan, TcLayout* lo) {
+  const asr_mfcc_params& p = plan->prm;
+  long long off = 16LL * plan->tc_blob_f4;
+  off = (off + 127) & ~127LL;
+  const long long fixed = 2 * (2 * 8192) + 4 * 6144 + 512LL * plan->tc_n_slots + 1024;
+  const long long budget = kMaxSmemBytes - tc_static_smem_bytes() - off - fixed;
+  // rows a tile needs when every sub-block of 16 frames is one run (+ alignment), and a generous allowance for ragged batches
+  const int typical = 8 * ((15 * p.hop_length + 512 + 31) / 32 + 1);
+  int rows = static_cast<int>(std::min<long long>(budget / (16 * 8) - 16, 2LL * typical));
+  if (rows < typical) return false;
+  int stride = rows + 1;
+  while ((stride & 15) != 1) ++stride;
+  lo->hl_rows = rows; lo->hl_stride = stride;
+  lo->sm_hl = static_cast<int>(off); off += 16LL * stride * 8;
+  off = (off + 127) & ~127LL;
+  lo->sm_a = static_cast<int>(off); off += 2 * (2 * 8192);
+  lo->sm_b = static_cast<int>(off); off += 4 * 6144;
+  lo->sm_slots = static_cast<int>(off); off += 512LL * plan->tc_n_slots;
+  lo->smem_bytes = static_cast<int>(off);
+  return off + tc_static_smem_bytes() <= kMaxSmemBytes;
+}
+// TC: the TILES conditions + int16 audio, hop a multiple of 32, no mixture noise; selected explicitly (ASR_PATH_TC) or by AUTO
+bool tc_path_usable(const asr_plan* plan, int n_clips, int max_length, int dtype, int noise_mode, bool aligned, TcLayout* lo) {
+  if (!plan->tc_ok || plan->path != ASR_PATH_TC) return false;
+  if (dtype != ASR_I16 || noise_mode == ASR_NOISE_MIXTURE || !aligned) return false;
+  const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
+  if (frames >= (1ll << 31) - 256) return false;
+  return tc_layout(plan, lo);
+}
 struct WsLayout { size_t off_fstart, off_nframes, off_clipmax, off_lm, bytes; };
 WsLayout ws_layout(const asr_plan* plan, int n_clips, int max_length) {
   WsLayout w;
@@ -722,7 +899,7 @@ bool frames_path_usable(const asr_plan* plan, int n_clips, int max_length, int d
 // TILES: n_fft = 512, hop and pad multiples of 8, no pre-emphasis, no mixture noise, 16-byte aligned arrays
 bool tiles_path_usable(const asr_plan* plan, int n_clips, int max_length, int dtype, int noise_mode, bool aligned,
                               TlLayout* lo) {
-  if (!plan->tl_ok || !(plan->path == ASR_PATH_AUTO || plan->path == ASR_PATH_TILES)) return false;
+  if (!plan->tl_ok || !(plan->path == ASR_PATH_AUTO || plan->path == ASR_PATH_TILES || plan->path == ASR_PATH_TC)) return false;
   if (noise_mode == ASR_NOISE_MIXTURE || !aligned) return false;
   const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
   if (frames >= (1ll << 31) - 64) return false;                  // flattened frame index is int32
@@ -735,17 +912,21 @@ extern "C" size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips
   FrLayout lo;
   if (!plan || n_clips <= 0 || max_length < 0) return 0;
   TlLayout tlo;
+  TcLayout tcl;
   if (!frames_path_usable(plan, n_clips, max_length, ASR_F64, ASR_NOISE_NONE, false, &lo) &&
-      !tiles_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tlo)) return 0;
+      !tiles_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tlo) &&
+      !tc_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tcl)) return 0;
   return ws_layout(plan, n_clips, max_length).bytes;
 }
 
 static bool frames_path_wanted(const asr_plan* plan, bool noisy) {
-  return plan->path == ASR_PATH_FRAMES || plan->path == ASR_PATH_TILES || (plan->path == ASR_PATH_AUTO && noisy);
+  return plan->path == ASR_PATH_FRAMES || plan->path == ASR_PATH_TILES || plan->path == ASR_PATH_TC || (plan->path == ASR_PATH_AUTO && noisy);
 }
 extern "C" int32_t asr_plan_launches(const asr_plan* plan, int32_t noisy) {
   FrLayout lo;
   TlLayout tlo;
+  TcLayout tcl;
+  if (plan && tc_path_usable(plan, 1, 0, ASR_I16, noisy ? ASR_NOISE_WHITE : ASR_NOISE_NONE, true, &tcl)) return 3;
   if (plan && tiles_path_usable(plan, 1, 0, ASR_F64, noisy ? ASR_NOISE_WHITE : ASR_NOISE_NONE, true, &tlo)) return 3;
   return (plan && plan->fr_ok && plan->path != ASR_PATH_CLIP && frames_path_wanted(plan, noisy != 0) &&
           frames_layout(plan, ASR_F64, ASR_NOISE_NONE, false, &lo)) ? 3 : 1;
@@ -755,9 +936,16 @@ extern "C" int32_t asr_plan_path_used(const asr_plan* plan, int32_t dtype, int32
   if (!plan) return ASR_PATH_CLIP;
   FrLayout lo;
   TlLayout tlo;
+  TcLayout tcl;
+  if (tc_path_usable(plan, 1, 0, dtype, noise_mode, true, &tcl)) return ASR_PATH_TC;
   if (tiles_path_usable(plan, 1, 0, dtype, noise_mode, true, &tlo)) return ASR_PATH_TILES;
   if (frames_path_wanted(plan, noise_mode != ASR_NOISE_NONE) && frames_path_usable(plan, 1, 0, dtype, noise_mode, true, &lo)) return ASR_PATH_FRAMES;
   return ASR_PATH_CLIP;
+}
+
+extern "C" int32_t asr_plan_debug_word(const asr_plan* plan, int32_t i) {
+  if (!plan || !plan->tc_dbg_host || i < 0 || i >= 16) return 0;
+  return reinterpret_cast<volatile int*>(plan->tc_dbg_host)[i];
 }
 
 extern "C" int asr_plan_set_stage_probe(asr_plan* plan, float* staged_dev) {
@@ -767,7 +955,7 @@ extern "C" int asr_plan_set_stage_probe(asr_plan* plan, float* staged_dev) {
 }
 
 extern "C" int asr_plan_set_path(asr_plan* plan, int32_t path) {
-  if (!plan || path < ASR_PATH_AUTO || path > ASR_PATH_TILES) { set_error("asr_plan_set_path: bad argument"); return ASR_ERR_INVALID; }
+  if (!plan || path < ASR_PATH_AUTO || path > ASR_PATH_TC) { set_error("asr_plan_set_path: bad argument"); return ASR_ERR_INVALID; }
   plan->path = path;
   return ASR_OK;
 }
@@ -810,6 +998,55 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
   {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     kp.vec_ok = al16(audio_dev) && (kp.noise_mode == ASR_NOISE_NONE || (al16(kp.z) && (kp.noise_mode != ASR_NOISE_MIXTURE || al16(kp.z2))));
+  }
+  // ---- n_fft = 512, int16 audio: tensor-core path (frame prefix -> tc512 -> cepstra) ----
+  TcLayout tcl;
+  if (tc_path_usable(plan, n_clips, max_length, dtype, kp.noise_mode, kp.vec_ok != 0, &tcl)) {
+    const WsLayout wl = ws_layout(plan, n_clips, max_length);
+    char* ws = static_cast<char*>(workspace_dev);
+    if (ws) {
+      if (workspace_bytes < wl.bytes || (reinterpret_cast<uintptr_t>(ws) & 15)) return bad("workspace too small or not 16-byte aligned");
+    } else {
+      asr_plan* mp = const_cast<asr_plan*>(plan);                // plan-owned scratch (documented: no concurrent launches)
+      if (mp->ws_bytes < wl.bytes) {
+        if (mp->ws_dev) ASR_CUDA_TRY(cudaFree(mp->ws_dev));
+        mp->ws_dev = nullptr; mp->ws_bytes = 0;
+        ASR_CUDA_TRY(cudaMalloc(&mp->ws_dev, wl.bytes));
+        mp->ws_bytes = wl.bytes;
+      }
+      ws = static_cast<char*>(mp->ws_dev);
+    }
+    FParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.audio = audio_dev; fp.offsets = kp.offsets; fp.lengths = lengths_dev; fp.dtype = dtype; fp.n_clips = n_clips;
+    fp.noise_mode = kp.noise_mode; fp.z = kp.z; fp.z2 = kp.z2; fp.sigma = kp.sigma;
+    fp.out = out_dev; fp.out_f64 = out_dtype == ASR_F64; fp.out_frames = out_frames;
+    fp.out_rows = p.n_mfcc * (1 + p.delta_orders); fp.logmel_only = logmel_only; fp.status = status_dev;
+    fp.n_fft = p.n_fft; fp.hop = p.hop_length; fp.pad = plan->pad; fp.pad_mode = p.pad_mode;
+    fp.n_mels = p.n_mels; fp.n_mfcc = p.n_mfcc; fp.delta_orders = p.delta_orders; fp.delta_width = p.delta_width;
+    fp.top_db = p.top_db; fp.amin = p.amin; fp.preemph = p.preemph;
+    fp.blob = reinterpret_cast<const float4*>(plan->tc_blob_dev); fp.blob_f4 = plan->tc_blob_f4;
+    fp.off_wtab = plan->tc_off_wtab; fp.off_steps = plan->tc_off_pieces; fp.off_wrange = plan->tc_off_wrange;
+    fp.tc_off_bnd = plan->tc_off_bnd; fp.tc_n_bnd = plan->tc_n_bnd;
+    fp.tc_mats = plan->tc_mats_dev;
+    fp.tc_dbg = plan->tc_dbg_dev;
+    fp.tc_sm_hl = tcl.sm_hl; fp.tc_sm_a = tcl.sm_a; fp.tc_sm_b = tcl.sm_b; fp.tc_sm_slots = tcl.sm_slots;
+    fp.tc_hl_stride = tcl.hl_stride; fp.tc_hl_rows = tcl.hl_rows;
+    fp.fstart = reinterpret_cast<int*>(ws + wl.off_fstart);
+    fp.nframes = reinterpret_cast<int*>(ws + wl.off_nframes);
+    fp.clipmax = reinterpret_cast<float*>(ws + wl.off_clipmax);
+    fp.lm = reinterpret_cast<float*>(ws + wl.off_lm);
+    const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
+    fp.lm_stride = static_cast<int>((frames + 31) & ~31LL);
+    fp.cep_blob = reinterpret_cast<const float4*>(plan->fr_blob_dev) + plan->cep_blob_f4;
+    fp.cep_tab_f4 = plan->cep_tab_f4; fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
+    fp.cep_off_col = plan->cep_smem_bytes / 4;
+    fp.cep_small = (p.n_mels <= 32 && plan->h_dct_t.size() <= static_cast<size_t>(kCepSmallTab) && p.delta_orders == 0 && !logmel_only) ? 1 : 0;
+    if (fp.cep_small) std::memcpy(fp.cep_dct, plan->h_dct_t.data(), plan->h_dct_t.size() * sizeof(float));
+    { const char* dbg = std::getenv("ASR_B200_DBG_SKIP"); fp.dbg_skip = dbg ? std::atoi(dbg) : 0; }
+    ASR_CUDA_TRY(launch_tc_path(fp, plan->sm_count, tcl.smem_bytes, plan->cep_smem_bytes + 4 * 128 * p.n_mels,
+                                std::max(1, asr_plan_num_frames(plan, max_length)), as_stream(stream)));
+    return ASR_OK;
   }
   // ---- n_fft = 512: TMA-staged block pipeline (frame prefix -> tiles -> cepstra) ----
   TlLayout tlo;

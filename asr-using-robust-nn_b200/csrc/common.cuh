@@ -157,6 +157,14 @@ struct FParams {
   int cep_off_col;    // cepstra_t_kernel: shared-memory offset (floats) of the [n_mels][128] log-mel column buffer
   int cep_small;      // 1: n_mels <= 32 and the transposed DCT table fits cep_dct: columns in registers, table from the constant bank
   float cep_dct[kCepSmallTab];   // [n_mels][4*NC4] transposed DCT x lifter (cep_small only)
+  // ---- tensor-core path (tc_kernel.cu) ----
+  const void* tc_mats;   // [16 b][MH1 | MH2 | ML][4 chunks][32 rows] x 16 bytes of float16: pass-1 matrices
+  int tc_sm_hl, tc_sm_a, tc_sm_b, tc_sm_slots;   // byte offsets inside the dynamic shared memory
+  int tc_hl_stride;   // uint2 entries between the residue rows of the staging array (1 mod 16: conflict-free both ways)
+  int tc_hl_rows;     // capacity of the staging array in pair rows (32 samples each) per tile
+  int tc_off_bnd;     // float offset of the boundary-filter list (int4: filter, first slot, slots, -) in the table blob
+  int tc_n_bnd;       // entries of that list
+  int* tc_dbg;        // mapped host memory (4 ints): breadcrumb of a wait that timed out
   int mix_f32;        // 1: fused white-noise mix in float32 with one rounding (timing experiments, ASR_B200_MIX_F32=1); 0: exact
   float* stage_probe; // parity probe (asr_plan_set_stage_probe): staged samples written back, packed like the audio; or null
 };
@@ -166,6 +174,11 @@ cudaError_t launch_frames_path(const FParams& fp, int sm_count, int frames_smem_
 cudaError_t launch_frame_prefix(const FParams& fp, cudaStream_t stream);          // frames_kernel.cu
 cudaError_t launch_tiles_path(const FParams& fp, int sm_count, int tile_smem_bytes, int cep_smem_bytes, int max_frames,
                               cudaStream_t stream);                              // tile_kernel.cu
+cudaError_t launch_cepstra_tail(const FParams& fp, int cep_smem_bytes, int max_frames, cudaStream_t stream);   // tile_kernel.cu
+cudaError_t launch_tc_path(const FParams& fp, int sm_count, int tc_smem_bytes, int cep_smem_bytes, int max_frames,
+                           cudaStream_t stream);                                 // tc_kernel.cu
+cudaError_t tc_upload_constants();                                               // tc_kernel.cu: unpack twiddles -> constant memory
+int tc_static_smem_bytes();                                                      // tc_kernel.cu
 
 // host-side launcher (mfcc_kernel.cu)
 cudaError_t launch_mfcc(const KParams& kp, int smem_bytes, cudaStream_t stream);
@@ -213,4 +226,11 @@ struct asr_plan {
   void* ws_dev;
   size_t ws_bytes;
   float* stage_probe;   // asr_plan_set_stage_probe
+  // ---- tensor-core path (n_fft = 512, int16 audio): pass-1 matrices and mel tables; tc_ok = 0 -> not available ----
+  int tc_ok;
+  void* tc_mats_dev;
+  float* tc_blob_dev;
+  int* tc_dbg_host;     // cudaHostAlloc(mapped): breadcrumb of a timed-out wait (asr_plan_debug_word)
+  int* tc_dbg_dev;
+  int tc_blob_f4, tc_off_wtab, tc_off_pieces, tc_off_wrange, tc_off_bnd, tc_n_bnd, tc_n_slots;
 };

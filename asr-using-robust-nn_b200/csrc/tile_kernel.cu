@@ -785,20 +785,8 @@ static cudaError_t launch_cep_t(const FParams& fp, dim3 grid, int smem_bytes, cu
   return cudaGetLastError();
 }
 
-cudaError_t launch_tiles_path(const FParams& fp, int sm_count, int tile_smem_bytes, int cep_smem_bytes, int max_frames,
-                              cudaStream_t stream) {
-  cudaError_t e = launch_frame_prefix(fp, stream);
-  if (e != cudaSuccess) return e;
-  const bool noise = fp.noise_mode == ASR_NOISE_WHITE;
-  switch (fp.dtype) {
-    case ASR_I16: e = noise ? launch_tile_dt<ASR_I16, true>(fp, sm_count, tile_smem_bytes, stream)
-                            : launch_tile_dt<ASR_I16, false>(fp, sm_count, tile_smem_bytes, stream); break;
-    case ASR_F32: e = noise ? launch_tile_dt<ASR_F32, true>(fp, sm_count, tile_smem_bytes, stream)
-                            : launch_tile_dt<ASR_F32, false>(fp, sm_count, tile_smem_bytes, stream); break;
-    default: e = noise ? launch_tile_dt<ASR_F64, true>(fp, sm_count, tile_smem_bytes, stream)
-                       : launch_tile_dt<ASR_F64, false>(fp, sm_count, tile_smem_bytes, stream); break;
-  }
-  if (e != cudaSuccess) return e;
+// cepstra stage of the transposed log-mel workspace (shared by the TILES and TC paths)
+cudaError_t launch_cepstra_tail(const FParams& fp, int cep_smem_bytes, int max_frames, cudaStream_t stream) {
   const int half = (fp.delta_orders > 0 && !fp.logmel_only) ? fp.delta_width / 2 : 0;
   const int tile = kCepTThreads - 2 * half;
   const int span = max(max_frames, fp.out_frames);
@@ -829,6 +817,24 @@ cudaError_t launch_tiles_path(const FParams& fp, int sm_count, int tile_smem_byt
     case 10: return launch_cep_t<10>(fp, grid, cep_smem_bytes, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+
+cudaError_t launch_tiles_path(const FParams& fp, int sm_count, int tile_smem_bytes, int cep_smem_bytes, int max_frames,
+                              cudaStream_t stream) {
+  cudaError_t e = launch_frame_prefix(fp, stream);
+  if (e != cudaSuccess) return e;
+  const bool noise = fp.noise_mode == ASR_NOISE_WHITE;
+  switch (fp.dtype) {
+    case ASR_I16: e = noise ? launch_tile_dt<ASR_I16, true>(fp, sm_count, tile_smem_bytes, stream)
+                            : launch_tile_dt<ASR_I16, false>(fp, sm_count, tile_smem_bytes, stream); break;
+    case ASR_F32: e = noise ? launch_tile_dt<ASR_F32, true>(fp, sm_count, tile_smem_bytes, stream)
+                            : launch_tile_dt<ASR_F32, false>(fp, sm_count, tile_smem_bytes, stream); break;
+    default: e = noise ? launch_tile_dt<ASR_F64, true>(fp, sm_count, tile_smem_bytes, stream)
+                       : launch_tile_dt<ASR_F64, false>(fp, sm_count, tile_smem_bytes, stream); break;
+  }
+  if (e != cudaSuccess) return e;
+  return launch_cepstra_tail(fp, cep_smem_bytes, max_frames, stream);
 }
 
 }  // namespace asr

@@ -150,7 +150,7 @@ class MfccPlan:
 
 
     def __init__(self, params: MfccParams, device: Optional[int] = None, path: str = "auto"):
-        """`path`: "auto", "clip" (one CTA per clip), "frames" (block-pipelined n_fft = 512 path) or "tiles" (the same with TMA staging); see asr_path."""
+        """`path`: "auto", "clip" (one CTA per clip), "frames" (block-pipelined n_fft = 512 path), "tiles" (the same with TMA staging) or "tc" (tensor-core path for int16 audio); see asr_path."""
         _require_cuda()
         self.params = params
         self.device = torch.cuda.current_device() if device is None else int(device)
@@ -158,7 +158,7 @@ class MfccPlan:
         with torch.cuda.device(self.device):
             pc = params.to_c()
             check(lib.asr_plan_create(C.byref(pc), C.byref(self._h)), "asr_plan_create")
-        check(lib.asr_plan_set_path(self._h, {"auto": 0, "clip": 1, "frames": 2, "tiles": 3}[path]), "asr_plan_set_path")
+        check(lib.asr_plan_set_path(self._h, {"auto": 0, "clip": 1, "frames": 2, "tiles": 3, "tc": 4}[path]), "asr_plan_set_path")
         self._ws = {}       # stream -> scratch tensor (the n_fft = 512 path keeps log-mel rows there between its launches)
 
     def __del__(self):
@@ -186,7 +186,7 @@ class MfccPlan:
     def path_used(self, dtype=np.int16, noisy: bool = False) -> str:
         """Kernel path a call with aligned arrays of `dtype` takes: "clip", "frames" or "tiles" (see asr_path)."""
         code = {np.dtype(np.int16): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}[np.dtype(dtype)]
-        return {1: "clip", 2: "frames", 3: "tiles"}[lib.asr_plan_path_used(self._h, code, 1 if noisy else 0)]
+        return {1: "clip", 2: "frames", 3: "tiles", 4: "tc"}[lib.asr_plan_path_used(self._h, code, 1 if noisy else 0)]
 
     def _workspace(self, n_clips: int, max_length: int, device) -> Optional[torch.Tensor]:
         need = lib.asr_mfcc_workspace_bytes(self._h, n_clips, max_length)

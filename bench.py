@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU per step")
-    ap.add_argument("--path", default="auto", choices=["auto", "clip", "frames", "tiles"], help="kernel path of the MFCC launch (asr_path)")
+    ap.add_argument("--path", default="auto", choices=["auto", "clip", "frames", "tiles", "tc"], help="kernel path of the MFCC launch (asr_path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -334,7 +334,8 @@ def main():
     gbs = byts * B / (ms_mfcc * 1e-3) / 1e9
     tfl = flops * B / (ms_mfcc * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                "traffic": ncu_traffic(args.workload, B), "kernel": {"tiles": "asr_mfcc_batch = frame_prefix_kernel + tile512_kernel (dominant) + cepstra_t_kernel",
+                "traffic": ncu_traffic(args.workload, B), "kernel": {"tc": "asr_mfcc_batch = frame_prefix_kernel + tc512_kernel (dominant, tcgen05) + cepstra_t_kernel",
+                                                                   "tiles": "asr_mfcc_batch = frame_prefix_kernel + tile512_kernel (dominant) + cepstra_t_kernel",
                                                                    "frames": "asr_mfcc_batch = frame_prefix_kernel + frames512_kernel (dominant) + cepstra_kernel",
                                                                    "clip": "asr_mfcc_batch = asr::mfcc_kernel"}[pipe.plan.path_used(np.int16, noisy)], "kernel_ms": ms_mfcc,
                 "kernel_timing": f"mean of {Kk} asr_mfcc_batch calls (the step's MFCC launches) on the step's buffers, one CUDA event pair "

@@ -163,10 +163,15 @@ size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips, int32_t m
  *                    (cp.async.bulk + mbarrier), a transposed log-mel workspace and the clip maximum taken by the
  *                    cepstra kernel; needs hop and n_fft/2 multiples of 8, no pre-emphasis, no mixture noise and
  *                    16-byte aligned arrays (clips that do not start on a 16-byte boundary are staged from global memory).
+ *   ASR_PATH_TC      tensor-core pipeline for int16 audio (hop a multiple of 32): tiles of 128 frames = the rows of a tcgen05
+ *                    accumulator in TMEM.  The window, the first (stride-16) DFT pass and the inter-pass twiddle run as
+ *                    float16 MMAs with a two-term split of both operands (float32-level accuracy), the second pass, the
+ *                    unpack and the mel stage on the CUDA cores with one frame per thread straight out of TMEM.  Falls back
+ *                    to TILES when its conditions do not hold.
  * ASR_PATH_AUTO (default) takes TILES when its conditions hold, else FRAMES when noise is fused into the launch
  * (each sample and its noise are then read and mixed once instead of once per overlapping frame), else CLIP.
  * Tests force every path. */
-typedef enum asr_path { ASR_PATH_AUTO = 0, ASR_PATH_CLIP = 1, ASR_PATH_FRAMES = 2, ASR_PATH_TILES = 3 } asr_path;
+typedef enum asr_path { ASR_PATH_AUTO = 0, ASR_PATH_CLIP = 1, ASR_PATH_FRAMES = 2, ASR_PATH_TILES = 3, ASR_PATH_TC = 4 } asr_path;
 int asr_plan_set_path(asr_plan* plan, int32_t path);
 /* Path a call with 16-byte aligned arrays of `dtype` and noise mode `noise_mode` takes (ASR_PATH_CLIP/FRAMES/TILES). */
 int32_t asr_plan_path_used(const asr_plan* plan, int32_t dtype, int32_t noise_mode);
@@ -260,6 +265,10 @@ int asr_resample_batch(const void* in_dev, int32_t dtype, const int64_t* in_offs
                        void* stream);
 
 /* ---- diagnostics ----
+ * Breadcrumb of the tensor-core kernel's bounded waits: word 0 = wait site that timed out (0 = none), 1 = CTA,
+ * 2 = thread, 3 = parity.  Lives in mapped host memory, so it can be read after a failed launch. */
+int32_t asr_plan_debug_word(const asr_plan* plan, int32_t i);
+/*
  * Self-test of the tcgen05 / TMEM plumbing the tensor-core path of asr_mfcc_batch relies on:
  * D[128][32] = A1[128][32] * B1[32][32]^T + A2 * B2^T with float16 operands (row-major, K contiguous) and float32
  * accumulation; d_dev receives D twice (2 x 128 x 32 floats: block loads, then strided two-column loads). */

@@ -21,7 +21,7 @@ ATOL, RTOL = 2e-3, 2e-5
 PATH = "auto"
 
 
-@pytest.fixture(params=["clip", "frames", "tiles"], autouse=True)
+@pytest.fixture(params=["clip", "frames", "tiles", "tc"], autouse=True)
 def _kernel_path(request):
     """Every test runs on both kernel paths: one CTA per clip, and the block-pipelined n_fft = 512 path
     (presets with another n_fft only have the first; "frames" then falls back to it)."""
