@@ -360,7 +360,7 @@ static bool build_tile_tables_all(asr_plan* pl, const std::vector<double>& mel_f
 // Pass 1 of the 16 x 16 decomposition of the 256-point complex FFT behind the real 512-point FFT, per residue b:
 //   Y_b[c] = W256^(b c) * sum_a W16^(a c) * (w[2n] x[2n] + i w[2n+1] x[2n+1]),  n = b + 16 a
 // as a real 32 x 32 matrix M_b (rows 2c + re/im, columns 2a + even/odd sample) in float64, stored as float16 pairs:
-// 16 M = MH1 + MH2 (value + residual), M / 128 = ML; see the head of tc_kernel.cu for the operand split they multiply.
+// 16 M = MH1 + MH2 (value + residual); see the head of tc_kernel.cu for the operand split they multiply.
 // The mel bank in segment form (as for the tiles path), dealt out to the 4 warps of a TMEM lane quarter; a filter whose
 // terms all lie in one share is finished in registers ("direct"), the others go through boundary slots.
 static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, const std::vector<double>& fftfreqs) {
@@ -374,9 +374,9 @@ static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, cons
     const double a0 = p.window == ASR_WIN_HANN ? 0.5 : 0.54, a1 = 1.0 - a0;
     return wl == 1 ? 1.0 : a0 - a1 * std::cos(2.0 * kPi * n / wl);
   };
-  std::vector<__half> mats(static_cast<size_t>(16) * 3 * 32 * 32);
+  std::vector<__half> mats(static_cast<size_t>(16) * 2 * 32 * 32);
   auto put = [&](int b, int mat, int n, int k, double v) {
-    mats[(((static_cast<size_t>(b) * 3 + mat) * 4 + k / 8) * 32 + n) * 8 + k % 8] = __float2half_rn(static_cast<float>(v));
+    mats[(((static_cast<size_t>(b) * 2 + mat) * 4 + k / 8) * 32 + n) * 8 + k % 8] = __float2half_rn(static_cast<float>(v));
   };
   for (int b = 0; b < 16; ++b)
     for (int c = 0; c < 16; ++c)
@@ -392,7 +392,6 @@ static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, cons
             const __half h1 = __float2half_rn(static_cast<float>(mh));
             put(b, 0, 2 * c + ri, 2 * a + eo, mh);
             put(b, 1, 2 * c + ri, 2 * a + eo, mh - static_cast<double>(__half2float(h1)));
-            put(b, 2, 2 * c + ri, 2 * a + eo, m[ri][eo] / 128.0);
           }
       }
   // ---- mel bank: steps (4 bins of one segment), 4 contiguous shares ----
@@ -847,12 +846,12 @@ bool tiles_layout(const asr_plan* plan, int dtype, int noise_mode, TlLayout* lo)
 }
 struct TcLayout { int sm_hl, sm_a, sm_b, sm_slots, hl_stride, hl_rows, smem_bytes; };
 // Shared-memory layout of the tensor-core kernel: mel tables | staging array HL[16][stride] (8 bytes per sample pair) |
-// operand ring (2 x (hi tile + lo tile) of 8 KB) | matrix ring (4 x 6 KB) | boundary slots.
+// operand ring (2 x (hi tile + lo tile) of 8 KB) | the 16 matrix sets (64 KB, resident) | boundary slots.
 bool tc_layout(const asr_plan* plan, TcLayout* lo) {
   const asr_mfcc_params& p = plan->prm;
   long long off = 16LL * plan->tc_blob_f4;
   off = (off + 127) & ~127LL;
-  const long long fixed = 2 * (2 * 8192) + 4 * 6144 + 512LL * plan->tc_n_slots + 1024;
+  const long long fixed = 2 * (2 * 8192) + 16 * 4096 + 512LL * plan->tc_n_slots + 1024;
   const long long budget = kMaxSmemBytes - tc_static_smem_bytes() - off - fixed;
   // rows a tile needs when every sub-block of 16 frames is one run (+ alignment), and a generous allowance for ragged batches
   const int typical = 8 * ((15 * p.hop_length + 512 + 31) / 32 + 1);
@@ -864,7 +863,7 @@ bool tc_layout(const asr_plan* plan, TcLayout* lo) {
   lo->sm_hl = static_cast<int>(off); off += 16LL * stride * 8;
   off = (off + 127) & ~127LL;
   lo->sm_a = static_cast<int>(off); off += 2 * (2 * 8192);
-  lo->sm_b = static_cast<int>(off); off += 4 * 6144;
+  lo->sm_b = static_cast<int>(off); off += 16 * 4096;
   lo->sm_slots = static_cast<int>(off); off += 512LL * plan->tc_n_slots;
   lo->smem_bytes = static_cast<int>(off);
   return off + tc_static_smem_bytes() <= kMaxSmemBytes;

@@ -158,7 +158,7 @@ struct FParams {
   int cep_small;      // 1: n_mels <= 32 and the transposed DCT table fits cep_dct: columns in registers, table from the constant bank
   float cep_dct[kCepSmallTab];   // [n_mels][4*NC4] transposed DCT x lifter (cep_small only)
   // ---- tensor-core path (tc_kernel.cu) ----
-  const void* tc_mats;   // [16 b][MH1 | MH2 | ML][4 chunks][32 rows] x 16 bytes of float16: pass-1 matrices
+  const void* tc_mats;   // [16 b][MH1 | MH2][4 chunks][32 rows] x 16 bytes of float16: pass-1 matrices
   int tc_sm_hl, tc_sm_a, tc_sm_b, tc_sm_slots;   // byte offsets inside the dynamic shared memory
   int tc_hl_stride;   // uint2 entries between the residue rows of the staging array (1 mod 16: conflict-free both ways)
   int tc_hl_rows;     // capacity of the staging array in pair rows (32 samples each) per tile

@@ -8,9 +8,9 @@
 //   PASS 1 (window, the stride-16 DFT over a, the inter-pass twiddle) is a real 32 x 32 linear map per residue b with
 //   CONSTANT coefficients - it runs on the tensor cores: D_b[128 frames][32] = A_b[128][32] * M_b^T, float16 operands,
 //   float32 accumulation in TMEM.  Float32 accuracy comes from a two-term split of both operands:
-//     sample v (int16 units, after the exact float64 noise mix) = 32 * (hi + lo / 2048), hi = fp16(v / 32),
-//     lo = fp16((v/32 - hi) * 2048)  - exact for int16 audio, 2^-22 relative otherwise;
-//     M * 16 = MH1 + MH2 (fp16 + fp16 residual), M / 128 = ML;   D = hi*MH1 + hi*MH2 + lo*ML  = 2^14 * Y
+//     sample v (int16 units, after the exact float64 noise mix) = 32 * (hi + lo), hi = fp16(v / 32),
+//     lo = fp16(v/32 - hi)  - exact for int16 audio, 2^-22 of the sample (3e-8 absolute below 0.25) otherwise;
+//     M * 16 = MH1 + MH2 (fp16 + fp16 residual);   D = hi*MH1 + hi*MH2 + lo*MH1  = 2^14 * Y
 //   (3 MMAs of K = 32 per b; the dropped terms are below 2^-22 of the frame's scale).
 //   PASS 2 (16-point DFT over b per column c), the real-input unpack, |X|^2 run on the CUDA cores with lanes <-> frames:
 //   a thread reads ITS frame's row from TMEM (tcgen05.ld), so every twiddle is a compile-time or constant-bank operand -
@@ -21,8 +21,8 @@
 //   Warp roles: 4 HELPER warps convert the samples of tile t+1 (dtype decode, float64 two-rounding noise mix,
 //   reflect / zero padding, hi/lo split) into a residue-major staging array HL[b][pair row] while the 16 MAIN warps work on
 //   tile t: phase A = per residue b: 128 rows x 64 B copied from HL[b] into the UMMA operand tile (K-major, unswizzled,
-//   chunk-major so that the copy is conflict-free), one elected thread issues the 6 MMAs, a 2-slot operand ring and a
-//   4-slot ring of the per-b matrices (cp.async.bulk from L2) keep the tensor core busy while the next tile is built;
+//   chunk-major so that the copy is conflict-free), one elected thread issues the 6 MMAs against the matrices of b (all 16 sets stay resident in
+//   shared memory, 64 KB), a 2-slot operand ring keeps the tensor core busy while the next operand tile is built;
 //   phase B = pass 2 / unpack / power / mel / log -> transposed log-mel workspace (then cepstra_*_kernel, tile_kernel.cu).
 //
 // Arithmetic restated from librosa.feature.mfcc (oracle/librosa_ref.py); call sites replaced:
@@ -46,10 +46,10 @@ constexpr int kTcMainWarps = 16, kTcHelpWarps = 4;
 constexpr int kTcMain = 32 * kTcMainWarps, kTcHelp = 32 * kTcHelpWarps, kTcThreads = kTcMain + kTcHelp;
 constexpr int kTcRing = 32;                  // sub-block descriptors alive: tiles t-1 (log-mel stores) .. t+1 (being assembled)
 constexpr int kTcCache = 32;
-constexpr int kTcNA = 2, kTcNB = 4;          // operand-tile ring, matrix ring
+constexpr int kTcNA = 2;                     // operand-tile ring
 constexpr int kTcATile = 16 * kTcRows * 4;   // bytes of one A tile (hi or lo): 4 chunks x 128 rows x 16 B
 constexpr int kTcBMat = 16 * 32 * 4;         // bytes of one 32 x 32 float16 matrix
-constexpr int kTcBSet = 3 * kTcBMat;         // MH1, MH2, ML of one residue b
+constexpr int kTcBSet = 2 * kTcBMat;         // MH1, MH2 of one residue b; all 16 sets stay resident in shared memory (64 KB)
 
 struct __align__(16) TcRun {      // 48 bytes
   long long base;   // element offset of the clip
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ TcBlock ring[kTcRing];
   __shared__ TcMeta s_meta[kTcCache];
-  __shared__ __align__(8) uint64_t bar_d_full, bar_a_free[kTcNA], bar_b_full[kTcNB];
+  __shared__ __align__(8) uint64_t bar_d_full, bar_a_free[kTcNA];
   __shared__ uint32_t s_tmem;
   __shared__ int s_ready, s_free;      // tiles converted by the helper warps / tiles whose operand copies are done (monotonic)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -189,12 +189,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
   float* s_tab = reinterpret_cast<float*>(smem_raw);                       // mel tables
   uint2* s_hl = reinterpret_cast<uint2*>(smem_raw + fp.tc_sm_hl);          // [16][tc_hl_stride] (hi pair, lo pair)
   unsigned char* s_a = smem_raw + fp.tc_sm_a;                              // [kTcNA][hi tile | lo tile]
-  unsigned char* s_b = smem_raw + fp.tc_sm_b;                              // [kTcNB][MH1 | MH2 | ML]
+  unsigned char* s_b = smem_raw + fp.tc_sm_b;                              // [16 b][MH1 | MH2], resident
   float* s_slots = reinterpret_cast<float*>(smem_raw + fp.tc_sm_slots);    // [tc_n_slots][128] boundary subtotals
   {
     float4* dst = reinterpret_cast<float4*>(s_tab);
     for (int i = tid; i < fp.blob_f4; i += kTcThreads) dst[i] = __ldg(fp.blob + i);
+    uint4* mb = reinterpret_cast<uint4*>(s_b);
+    const uint4* gm = reinterpret_cast<const uint4*>(fp.tc_mats);
+    for (int i = tid; i < 16 * kTcBSet / 16; i += kTcThreads) mb[i] = __ldg(gm + i);
   }
+  tc::fence_async_smem();                               // the matrices are read by the tensor core (async proxy)
   const float4* s_wtab = reinterpret_cast<const float4*>(s_tab + fp.off_wtab);
   const int4* s_pieces = reinterpret_cast<const int4*>(s_tab + fp.off_steps);
   const int2* s_wrange = reinterpret_cast<const int2*>(s_tab + fp.off_wrange);
@@ -203,14 +207,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
     s_ready = 0; s_free = 0;
     tc::mbar_init(&bar_d_full, 1);
     for (int i = 0; i < kTcNA; ++i) tc::mbar_init(&bar_a_free[i], 1);
-    for (int i = 0; i < kTcNB; ++i) tc::mbar_init(&bar_b_full[i], 1);
     tc::mbar_init_fence();
   }
   if (warp_u == 0) tc::tmem_alloc(&s_tmem, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem = s_tmem;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, s_tmem, 0);      // warp-uniform copy (uniform-register operand of the tcgen05 instructions)
 
   // bounded wait with a breadcrumb: on a protocol error the waiting thread leaves (site, CTA, thread, parity) in mapped
   // host memory and traps, so the launch fails with a diagnosis instead of hanging
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
           const float x1 = padded_at<ASR_I16>(fp, base, L, o0 + fp.pad + 2 * i + 1, sig) * 1024.0f;
           const __half2 hi = __floats2half2_rn(x0, x1);
           const float2 hf = __half22float2(hi);
-          const __half2 lo = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+          const __half2 lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
           const int P = p0 + i;
           uint2 w;
           w.x = *reinterpret_cast<const unsigned*>(&hi);
@@ -365,7 +368,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
         break;
       }
       if (t > 0) await(1, &s_free, t);                   // tile t-1's operand copies are done
-      for (int j = 0; j < kTcNSub; ++j) convert_sub(ring[(k0 + j) & (kTcRing - 1)]);
+      if (!(fp.dbg_skip & 2))                             // (timing experiments: main warps alone)
+        for (int j = 0; j < kTcNSub; ++j) convert_sub(ring[(k0 + j) & (kTcRing - 1)]);
       if (hw == 0)                                        // descriptors of tile t+1 (tile t-1's are still read by the main warps)
         for (int j = 0; j < kTcNSub; ++j) assemble(ring[(k0 + kTcNSub + j) & (kTcRing - 1)], j == 0);
       bar_help();
@@ -378,60 +382,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
     const int frow = 32 * q + lane;                                   // this thread's frame row in phase B
     const uint32_t tm_lane = tmem + (static_cast<uint32_t>(32 * q) << 16);
     const uint32_t idesc = tc::idesc_f16_f32(kTcRows, 32);
-    const unsigned char* g_mats = reinterpret_cast<const unsigned char*>(fp.tc_mats);
+    const uint64_t desc_a = tc::smem_desc(tc::smem_u32(s_a), 16 * kTcRows, 128);     // hi tile of slot 0, K step 0
+    const uint64_t desc_b = tc::smem_desc(tc::smem_u32(s_b), 512, 128);              // MH1 of b = 0, K step 0
     const int2 my_pieces = s_wrange[grp];
     uint32_t gbc = 0;                                                 // running count of (tile, b) steps
+    long long tk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};                // (profiling breadcrumbs, CTA 0 thread 0: cycles per phase)
+    const bool prof = fp.tc_dbg != nullptr && (fp.dbg_skip & 128) && blockIdx.x == 0 && tid == 0;
+    long long tlast = prof ? clock64() : 0;
+    auto lap = [&](const int i) { if (prof) { const long long now = clock64(); tk[i] += now - tlast; tlast = now; } };
     for (int t = 0;; ++t) {
       const int k0 = t * kTcNSub;
       await(2, &s_ready, t + 1);
+      lap(0);
       if (ring[k0 & (kTcRing - 1)].done) break;
       // ---------------- phase A: operand tiles + MMAs ----------------
-      if (tid == 0) {                                                 // matrices of b = 0, 1, 2
-        for (int b = 0; b < 3; ++b) {
-          const uint32_t sb = (gbc + b) & (kTcNB - 1);
-          tc::mbar_arrive_expect_tx(&bar_b_full[sb], kTcBSet);
-          tc_tma_g2s(s_b + sb * kTcBSet, g_mats + b * kTcBSet, kTcBSet, &bar_b_full[sb]);
-        }
-      }
       const int rowp = ring[(k0 + (row >> 4)) & (kTcRing - 1)].slot_row[row & 15];
       const uint2* src_row = s_hl + rowp + 4 * cq;
+      unsigned char* const a_dst = s_a + cq * (16 * kTcRows) + row * 16;
+#pragma unroll 1
       for (int b = 0; b < 16; ++b, ++gbc) {
-        const uint32_t sa = gbc & (kTcNA - 1), sb = gbc & (kTcNB - 1);
-        if (gbc >= kTcNA) dwait(3, &bar_a_free[sa], ((gbc >> 1) - 1) & 1);      // MMAs of step gbc - 2 have read this slot
-        {
+        const uint32_t sa = gbc & (kTcNA - 1);
+        if (gbc >= kTcNA) dwait(3, &bar_a_free[sa], ((gbc / kTcNA) - 1) & 1);   // MMAs of step gbc - kTcNA have read this slot
+        lap(1);
+        if (!(fp.dbg_skip & 32)) {
           const uint2* src = src_row + b * fp.tc_hl_stride;
           const uint2 w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
-          unsigned char* at = s_a + sa * (2 * kTcATile) + cq * (16 * kTcRows) + row * 16;
+          unsigned char* at = a_dst + sa * (2 * kTcATile);
           *reinterpret_cast<uint4*>(at) = make_uint4(w0.x, w1.x, w2.x, w3.x);
           *reinterpret_cast<uint4*>(at + kTcATile) = make_uint4(w0.y, w1.y, w2.y, w3.y);
         }
+        lap(2);
         tc::fence_async_smem();
+        lap(3);
         bar_main();
-        if (tid == 0) {
-          dwait(4, &bar_b_full[sb], (gbc >> 2) & 1);
+        lap(4);
+        if (warp_u == 0 && tc::elect_one()) {
           tc::tc_fence_after();
-          const uint32_t a_hi = tc::smem_u32(s_a + sa * (2 * kTcATile)), a_lo = a_hi + kTcATile;
-          const uint32_t bm = tc::smem_u32(s_b + sb * kTcBSet);
+          // descriptors differ in their start address only (bits 0..13, in 16-byte units)
+          const uint64_t dah = desc_a + (sa * (2 * kTcATile) >> 4), dal = dah + (kTcATile >> 4);
+          const uint64_t d1 = desc_b + (b * kTcBSet >> 4), d2 = d1 + (kTcBMat >> 4);
           const uint32_t dcol = tmem + 32 * b;
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t dah = tc::smem_desc(a_hi + ks * 2 * (16 * kTcRows), 16 * kTcRows, 128);
-            const uint64_t dal = tc::smem_desc(a_lo + ks * 2 * (16 * kTcRows), 16 * kTcRows, 128);
-            const uint64_t d1 = tc::smem_desc(bm + ks * 2 * 512, 512, 128);
-            const uint64_t d2 = tc::smem_desc(bm + kTcBMat + ks * 2 * 512, 512, 128);
-            const uint64_t d3 = tc::smem_desc(bm + 2 * kTcBMat + ks * 2 * 512, 512, 128);
-            tc::mma_f16(dcol, dah, d1, idesc, ks);
-            tc::mma_f16(dcol, dah, d2, idesc, 1);
-            tc::mma_f16(dcol, dal, d3, idesc, 1);
+          constexpr uint32_t kA = 2 * (16 * kTcRows) >> 4, kB = 2 * 512 >> 4;    // second K step: two chunks further
+          if (fp.dbg_skip & 256) {                        // (timing experiment: six independent accumulators)
+          tc::mma_f16(tmem + 0, dah, d1, idesc, 1);
+          tc::mma_f16(tmem + 64, dah + kA, d1 + kB, idesc, 1);
+          tc::mma_f16(tmem + 128, dah, d2, idesc, 1);
+          tc::mma_f16(tmem + 192, dah + kA, d2 + kB, idesc, 1);
+          tc::mma_f16(tmem + 256, dal, d1, idesc, 1);
+          tc::mma_f16(tmem + 320, dal + kA, d1 + kB, idesc, 1);
+          } else if (!(fp.dbg_skip & 16)) {
+          tc::mma_f16(dcol, dah, d1, idesc, 0);
+          tc::mma_f16(dcol, dah + kA, d1 + kB, idesc, 1);
+          if (!(fp.dbg_skip & 64)) {
+          tc::mma_f16(dcol, dah, d2, idesc, 1);
+          tc::mma_f16(dcol, dah + kA, d2 + kB, idesc, 1);
+          tc::mma_f16(dcol, dal, d1, idesc, 1);
+          tc::mma_f16(dcol, dal + kA, d1 + kB, idesc, 1);
+          }
           }
           tc::mma_commit(&bar_a_free[sa]);
-          if (b + 3 < 16) {                                           // matrices of b + 3 into the slot step gbc - 1 used
-            if (gbc >= 1) dwait(5, &bar_a_free[(gbc - 1) & (kTcNA - 1)], ((gbc - 1) >> 1) & 1);
-            const uint32_t sn = (gbc + 3) & (kTcNB - 1);
-            tc::mbar_arrive_expect_tx(&bar_b_full[sn], kTcBSet);
-            tc_tma_g2s(s_b + sn * kTcBSet, g_mats + (b + 3) * kTcBSet, kTcBSet, &bar_b_full[sn]);
-          }
         }
+        lap(5);
       }
       if (tid == 0) {
         tc::mma_commit(&bar_d_full);
@@ -442,14 +453,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
       const int gidx = (frow & 15) < myb.n_slots ? myb.g0 + (frow & 15) : -1;
       dwait(6, &bar_d_full, static_cast<uint32_t>(t & 1));
       tc::tc_fence_after();
+      lap(6);
+      if (!(fp.dbg_skip & 4)) {                         // (timing experiments)
       if (grp == 0) { tc_pair(tm_lane, 1); tc_pair(tm_lane, 2); }
       else if (grp == 1) { tc_pair(tm_lane, 3); tc_pair(tm_lane, 4); }
       else if (grp == 2) { tc_pair(tm_lane, 5); tc_pair(tm_lane, 6); }
       else { tc_pair(tm_lane, 7); tc_col0(tm_lane); tc_col8(tm_lane); }
+      }
       tmem_st_wait();
       tc::tc_fence_before();
       bar_main();
       tc::tc_fence_after();
+      lap(7);
       {
         // mel: this group's pieces in ascending-bin order, one piece per segment; filter seg-1 = rise(seg-1) + fall(seg)
         auto emit = [&](const int code, const float m) {
@@ -464,7 +479,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
         float pending = 0.0f;
         const int4* pp = s_pieces + my_pieces.x;
 #pragma unroll 1
-        for (int n = my_pieces.y; n > 0; --n, ++pp) {
+        for (int n = (fp.dbg_skip & 8) ? 0 : my_pieces.y; n > 0; --n, ++pp) {
           const int4 pc = *pp;                          // (first float4 of bins, steps, first weight float4, emit code)
           const float4* wp = s_wtab + pc.z;
           float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
@@ -494,6 +509,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
       tc::tc_fence_before();
       bar_main();                                       // TMEM is free again; boundary subtotals are visible
       tc::tc_fence_after();
+      lap(8);
       for (int idx = tid; idx < fp.tc_n_bnd * kTcRows; idx += kTcMain) {
         const int4 e = s_bnd[idx >> 7];                 // (filter, first slot, slots, -)
         const int r = idx & (kTcRows - 1);
@@ -504,12 +520,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc512_kernel(const __grid_const
           fp.lm[static_cast<long long>(e.x) * fp.lm_stride + rb.g0 + (r & 15)] = 3.01029995663981195f * tc_log2(fmaxf(fp.amin, m));
       }
       bar_main();                                       // slots may be rewritten by the next tile's mel
+      lap(9);
+    }
+    if (prof) {
+      volatile int* d = fp.tc_dbg;
+      for (int i = 0; i < 10; ++i) d[6 + i] = static_cast<int>(tk[i] >> 4);
+      __threadfence_system();
     }
     // every asynchronous arrival this CTA has asked for must have landed before its shared memory is released: the
     // commits of the last two steps are the only ones nobody has waited for
     if (tid == 0 && !(fp.dbg_skip & 1)) {
-      if (gbc >= 1) dwait(7, &bar_a_free[(gbc - 1) & (kTcNA - 1)], ((gbc - 1) >> 1) & 1);
-      if (gbc >= 2) dwait(8, &bar_a_free[(gbc - 2) & (kTcNA - 1)], ((gbc - 2) >> 1) & 1);
+      for (uint32_t i = 1; i <= kTcNA && i <= gbc; ++i) dwait(7, &bar_a_free[(gbc - i) & (kTcNA - 1)], ((gbc - i) / kTcNA) & 1);
     }
   }
   tc::tc_fence_before();

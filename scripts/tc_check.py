@@ -38,4 +38,9 @@ for B in sizes:
                   "breadcrumb", [lib.asr_plan_debug_word(ptc._h, i) for i in range(4)], flush=True)
             raise SystemExit(1)
         dt = (time.perf_counter() - t0) / reps
+        if int(os.environ.get("ASR_B200_DBG_SKIP", "0")) & 128:
+            from asr_b200._lib import lib
+            names = ["wait_hl", "wait_afree", "copy", "fence", "bar", "mma_issue", "wait_dfull", "epilogue", "mel", "combine"]
+            cyc = [lib.asr_plan_debug_word(ptc._h, 6 + i) * 16 for i in range(10)]
+            print("  CTA0 thread0 cycles per phase (last launch):", {n: c for n, c in zip(names, cyc)}, "total", sum(cyc), flush=True)
         print(f"B={B} noisy={noisy} ok maxdiff={float((out - ref).abs().max()):.2e} last call {dt * 1e3:.3f} ms", flush=True)
