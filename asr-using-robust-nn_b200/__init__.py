@@ -13,7 +13,7 @@ Drop-in for the data-parallel hot path of fmazilu/ASR-using-robust-NN:
 from ._lib import AsrError, LIB_PATH  # noqa: F401
 from .params import MfccParams, REF_VDR, REF_SR, C1, C3, C5, PRESETS  # noqa: F401
 from .frontend import (ClipBatch, Noise, MfccPlan, Standardizer, Resampler, clip_power, snr_sigma_host, snr_sigma_host_scalar,  # noqa: F401
-                       snr_sigma_device, mix_white, mix_mixture, mix_rows_white, mix_rows_mixture, randn)
+                       snr_sigma_device, mix_white, mix_mixture, babble_stream, babble_gain_host, mix_rows_white, mix_rows_mixture, randn)
 
 from .mlp import DenseStack, accuracy_vs_snr  # noqa: F401
 

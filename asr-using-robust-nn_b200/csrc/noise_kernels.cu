@@ -524,6 +524,40 @@ __global__ void __launch_bounds__(256) mix_white_kernel(const void* __restrict__
     out[base + i] = __dadd_rn(audio_f64(audio, dtype, base + i), __dmul_rn(s, __ldg(z + base + i)));
 }
 
+// Babble noise (BASELINE configs[1] "white/babble"; no reference implementation - the recipe is SURVEY.md 8(d)):
+//   b_i[n] = sum_{k=1..talkers} x_{(i + k*stride) mod B}[n]   (n < L_i; a talker shorter than n contributes nothing)
+// in float64 (a sum of at most 6 float32 / int16 values is exact in float64, so the order does not matter), and
+//   Pb_i = mean_n b_i[n]^2 in float64 in a FIXED order (256 strided partials per clip, then a binary tree).
+// The mix itself is the white-noise formula with z := b and sigma := gain (float64 x + gain*b, two roundings), so the
+// fused MFCC launch and asr_mix_white take the stream as it is.  One CTA per clip.
+__global__ void __launch_bounds__(256) babble_stream_kernel(const void* __restrict__ audio, const int dtype,
+                                                            const long long* __restrict__ offsets,
+                                                            const int* __restrict__ lengths, const int n_clips,
+                                                            const int stride, const int talkers,
+                                                            double* __restrict__ b_out, double* __restrict__ power_out) {
+  __shared__ double s_red[256];
+  const int i = blockIdx.x;
+  const int L = lengths[i];
+  const long long base = offsets[i];
+  double acc = 0.0;
+  for (int n = threadIdx.x; n < L; n += 256) {
+    double b = 0.0;
+    for (int k = 1; k <= talkers; ++k) {
+      const int j = static_cast<int>((static_cast<long long>(i) + static_cast<long long>(k) * stride) % n_clips);
+      if (n < lengths[j]) b += audio_f64(audio, dtype, offsets[j] + n);
+    }
+    b_out[base + n] = b;
+    acc = __dadd_rn(acc, __dmul_rn(b, b));
+  }
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) s_red[threadIdx.x] = __dadd_rn(s_red[threadIdx.x], s_red[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) power_out[i] = L > 0 ? s_red[0] / static_cast<double>(L) : 0.0;
+}
+
 __global__ void __launch_bounds__(256) mix_mixture_kernel(const void* __restrict__ audio, const int dtype,
                                                           const long long* __restrict__ offsets,
                                                           const int* __restrict__ lengths, const double* __restrict__ q,
@@ -674,6 +708,21 @@ extern "C" int asr_mix_white(const void* audio_dev, int32_t dtype, const int64_t
   if (n_clips == 0) return ASR_OK;
   mix_white_kernel<<<dim3(n_clips, 8), 256, 0, as_stream(stream)>>>(
       audio_dev, dtype, reinterpret_cast<const long long*>(offsets_dev), lengths_dev, z_dev, sigma_dev, out_dev);
+  ASR_CUDA_TRY(cudaGetLastError());
+  return ASR_OK;
+}
+
+extern "C" int asr_babble_stream(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
+                                 int32_t n_clips, int32_t stride, int32_t talkers, double* babble_dev, double* power_dev,
+                                 void* stream) {
+  if (!audio_dev || !offsets_dev || !lengths_dev || !babble_dev || !power_dev || n_clips < 0 || talkers < 1 || stride < 1 ||
+      dtype < ASR_I16 || dtype > ASR_F64) {
+    set_error("asr_babble_stream: invalid argument");
+    return ASR_ERR_INVALID;
+  }
+  if (n_clips == 0) return ASR_OK;
+  babble_stream_kernel<<<n_clips, 256, 0, as_stream(stream)>>>(audio_dev, dtype, reinterpret_cast<const long long*>(offsets_dev),
+                                                               lengths_dev, n_clips, stride, talkers, babble_dev, power_dev);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }

@@ -341,6 +341,32 @@ def mix_white(batch: ClipBatch, z: torch.Tensor, sigma: torch.Tensor) -> torch.T
     return out
 
 
+BABBLE_STRIDE, BABBLE_TALKERS = 97, 6      # six other clips of the batch, indices (i + k*97) mod B
+
+
+def babble_stream(batch: ClipBatch, stride: int = BABBLE_STRIDE, talkers: int = BABBLE_TALKERS,
+                  out: Optional[torch.Tensor] = None, power: Optional[torch.Tensor] = None):
+    """Babble stream of a batch (float64, packed like the audio) and its mean power per clip (float64 [B])."""
+    dev = batch.audio.device
+    if out is None:
+        out = torch.zeros(batch.audio.shape[0], dtype=torch.float64, device=dev)
+    if power is None:
+        power = torch.empty(batch.n_clips, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.asr_babble_stream(batch.audio.data_ptr(), batch.dtype_code, batch.offsets.data_ptr(), batch.lengths.data_ptr(),
+                                    batch.n_clips, int(stride), int(talkers), out.data_ptr(), power.data_ptr(), _stream()),
+              "asr_babble_stream")
+    return out, power
+
+
+def babble_gain_host(sigma: np.ndarray, babble_power: np.ndarray) -> np.ndarray:
+    """gain[b] = sigma[b] / sqrt(Pb[b]) in float64 (0 where the babble is silent): noise RMS = the white-noise sigma."""
+    pb = np.asarray(babble_power, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g = np.asarray(sigma, dtype=np.float64) / np.sqrt(pb)
+    return np.where(pb > 0, g, 0.0)
+
+
 def mix_mixture(batch: ClipBatch, q: torch.Tensor, g: torch.Tensor, p: float, alpha: float) -> torch.Tensor:
     out = torch.zeros(batch.audio.shape[0], dtype=torch.float64, device=batch.audio.device)
     with torch.cuda.device(batch.audio.device):

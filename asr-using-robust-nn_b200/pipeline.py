@@ -27,7 +27,8 @@ from typing import Optional
 
 import torch
 
-from .frontend import ClipBatch, MfccPlan, Noise, Standardizer, clip_power, snr_sigma_device, snr_sigma_host, randn
+from .frontend import (ClipBatch, MfccPlan, Noise, Standardizer, clip_power, snr_sigma_device, snr_sigma_host, randn,
+                       babble_stream, babble_gain_host)
 from .params import MfccParams
 
 # kernels of libasr_b200 launched by one `run_device` step besides the MFCC launches (`plan.launches`):
@@ -91,8 +92,8 @@ class NoisyFeaturePipeline:
             self._cache.clear()                            # captured graphs reference the old sigma vector
         return st
 
-    def _submit_power(self, batch) -> int:
-        """Enqueue power + read-back of `batch` on the current stream; returns the slot."""
+    def _submit_power(self, batch, babble: bool = False) -> int:
+        """Enqueue power (+ the babble stream and its power) and the read-back of `batch` on the current stream; returns the slot."""
         st = self._sig_state(batch.n_clips)
         k = st["turn"]
         st["turn"] ^= 1
@@ -102,37 +103,45 @@ class NoisyFeaturePipeline:
         B = batch.n_clips
         clip_power(batch, out=sl["P_dev"])
         sl["P_host"][:B].copy_(sl["P_dev"][:B], non_blocking=True)
+        if babble:
+            n = batch.audio.shape[0]
+            if sl.get("b_dev") is None or sl["b_dev"].numel() < n:
+                sl["b_dev"] = torch.zeros(n, dtype=torch.float64, device=self.device)
+                sl["Pb_dev"] = torch.empty(st["cap"], dtype=torch.float64, device=self.device)
+                sl["Pb_host"] = torch.empty(st["cap"], dtype=torch.float64).pin_memory()
+            babble_stream(batch, out=sl["b_dev"], power=sl["Pb_dev"])
+            sl["Pb_host"][:B].copy_(sl["Pb_dev"][:B], non_blocking=True)
         sl["event"].record()
         return k
 
-    def prefetch_power(self, batch) -> None:
+    def prefetch_power(self, batch, babble: bool = False) -> None:
         """Enqueue the power pass of a batch a later `run_device(..., snr_db)` will use (host sigma mode)."""
-        if self.sigma_mode == "host":
+        if self.sigma_mode == "host" or babble:
             self._sig_state(batch.n_clips)
-            self._sig["pending"][self._bkey(batch)] = self._submit_power(batch)
+            self._sig["pending"][self._bkey(batch) + (babble,)] = self._submit_power(batch, babble)
 
-    def _sigma_for(self, batch, snr_db, prefetch) -> torch.Tensor:
-        """Device sigma vector for this step (valid in stream order until the next call)."""
-        if self.sigma_mode == "device":
-            return snr_sigma_device(clip_power(batch), snr_db)
+    def _sigma_for(self, batch, snr_db, prefetch, babble: bool = False):
+        """(device sigma vector, noise stream or None) for this step, valid in stream order until the next call.  White
+        noise: sigma of VDR/attacks.py:235-241, the stream is the caller's z.  Babble: the stream is the batch's babble
+        sum and "sigma" the gain that gives it the white-noise sigma as RMS."""
+        if self.sigma_mode == "device" and not babble:
+            return snr_sigma_device(clip_power(batch), snr_db), None
         st = self._sig_state(batch.n_clips)
-        k = st["pending"].pop(self._bkey(batch), None)
+        k = st["pending"].pop(self._bkey(batch) + (babble,), None)
         if k is None:
-            k = self._submit_power(batch)
+            k = self._submit_power(batch, babble)
         if prefetch is not None:
-            self.prefetch_power(prefetch)                   # in front of this step's MFCC launch
+            self.prefetch_power(prefetch, babble)           # in front of this step's MFCC launch
             st = self._sig
         sl = st["slots"][k]
         B = batch.n_clips
         sl["event"].synchronize()
-        snr_sigma_host(sl["P_host"].numpy()[:B], snr_db, out=sl["sig_host"].numpy()[:B])
+        sig = sl["sig_host"].numpy()[:B]
+        snr_sigma_host(sl["P_host"].numpy()[:B], snr_db, out=sig)
+        if babble:
+            sig[:] = babble_gain_host(sig, sl["Pb_host"].numpy()[:B])
         st["sigma_dev"][:B].copy_(sl["sig_host"][:B], non_blocking=True)
-        return st["sigma_dev"][:B]
-
-    def _feat_buffer(self, B: int) -> torch.Tensor:
-        if self._feats is None or self._feats.shape[0] != B:
-            self._feats = torch.empty((B, self.rows, self.out_frames), dtype=torch.float32, device=self.device)
-        return self._feats
+        return st["sigma_dev"][:B], (sl["b_dev"] if babble else None)
 
     # ---- the three launch groups of a step ----------------------------------------------------------
     def _group1(self, batch, z, snr_db, feats, sigma=None):
@@ -149,13 +158,18 @@ class NoisyFeaturePipeline:
         return noise
 
     def run_device(self, batch: ClipBatch, z: Optional[torch.Tensor], snr_db: Optional[float],
-                   standardize: bool = True, out_dtype=torch.float32, prefetch: Optional[ClipBatch] = None) -> torch.Tensor:
+                   standardize: bool = True, out_dtype=torch.float32, prefetch: Optional[ClipBatch] = None,
+                   noise_kind: str = "white") -> torch.Tensor:
         """Inputs resident in HBM; the launches are asynchronous on the current stream (in host sigma mode the call
         waits for the 4*B-byte power read-back of THIS batch, which a previous call's ``prefetch=`` has usually
-        already enqueued).  ``prefetch``: the batch of the next noisy call."""
+        already enqueued).  ``prefetch``: the batch of the next noisy call.  ``noise_kind``: "white" (z is the caller's
+        standard-normal stream) or "babble" (z is ignored: the noise is the sum of six other clips of the batch)."""
         sigma = None
-        if snr_db is not None and self.sigma_mode == "host":
-            sigma = self._sigma_for(batch, snr_db, prefetch)
+        babble = noise_kind == "babble"
+        if snr_db is not None and (self.sigma_mode == "host" or babble):
+            sigma, zb = self._sigma_for(batch, snr_db, prefetch, babble)
+            if babble:
+                z = zb
         if self.use_graphs and self.ev_mfcc is None:
             return self._run_graphed(batch, z, snr_db, standardize, out_dtype, sigma)
         feats = self._feat_buffer(batch.n_clips)
@@ -254,7 +268,7 @@ class NoisyFeaturePipeline:
             batch, z, snr_db = cur
             sigma = None
             if snr_db is not None and self.sigma_mode == "host":
-                sigma = self._sigma_for(batch, snr_db, nxt[0] if nxt is not None and nxt[2] is not None else None)
+                sigma, _ = self._sigma_for(batch, snr_db, nxt[0] if nxt is not None and nxt[2] is not None else None)
             self._group1(batch, z, snr_db, feats[done:done + batch.n_clips], sigma)
             done += batch.n_clips
             cur = nxt
@@ -265,10 +279,11 @@ class NoisyFeaturePipeline:
         return self.std.transform(flat, out_dtype=out_dtype)
 
     def run_host(self, audio_host: torch.Tensor, snr_db: Optional[float], seed: int, out_host: torch.Tensor,
-                 first_index: int = 0) -> torch.Tensor:
-        """End to end from PINNED host memory: (B, L) int16/float32 host tensor in, standardised
-        float32 (B, D) rows written to the pinned `out_host`.  The noise stream is generated on the
-        device from `seed` (element index = first_index + position in this shard).
+                 first_index: int = 0, layout: Optional[ClipBatch] = None, noise_kind: str = "white") -> torch.Tensor:
+        """End to end from PINNED host memory: (B, L) int16/float32/float64 host tensor in - or, with ``layout`` (a
+        ``ClipBatch`` whose offsets / lengths describe it), a packed 1-D host tensor of ragged clips -, standardised
+        float32 (B, D) rows written to the pinned `out_host`.  The noise stream is generated on the device from `seed`
+        (element index = first_index + position in this shard).
 
         Three streams (host->device copy, compute, device->host copy) and two sets of device buffers: the
         upload of call i+1 overlaps the kernels of call i and the download of call i-1.  The caller's current
@@ -286,16 +301,21 @@ class NoisyFeaturePipeline:
         self._s_comp.wait_event(sl["uploaded"])
         self._s_comp.wait_event(sl["downloaded"])          # this slot's output buffer has been read back
         with torch.cuda.stream(self._s_comp):
-            batch = ClipBatch.from_matrix(sl["audio"])
+            batch = ClipBatch.from_matrix(sl["audio"]) if layout is None else layout.like(sl["audio"])
             z = None
-            if snr_db is not None:
+            if snr_db is not None and noise_kind == "white":
+                if sl["z"] is None:
+                    sl["z"] = torch.empty(sl["audio"].numel(), dtype=torch.float64, device=self.device)
                 z = sl["z"]
                 randn(seed, first_index, z.numel(), device=self.device, out=z)
-            out = self.run_device(batch, z, snr_db)
+            out = self.run_device(batch, z, snr_db, noise_kind=noise_kind)
             sl["computed"].record()
         self._s_d2h.wait_event(sl["computed"])
         with torch.cuda.stream(self._s_d2h):
             out_host.copy_(out, non_blocking=True)
+            # `out` (and the feature buffer behind it) belong to the compute stream's allocator: keep them alive until
+            # this copy has run, whatever graph mode the step used
+            out.record_stream(self._s_d2h)
             sl["downloaded"].record()
         cur.wait_event(sl["downloaded"])
         return out_host
@@ -307,7 +327,7 @@ class NoisyFeaturePipeline:
             hs = []
             for _ in range(2):
                 hs.append({"audio": torch.empty(audio_host.shape, dtype=audio_host.dtype, device=self.device),
-                           "z": torch.empty(audio_host.numel(), dtype=torch.float64, device=self.device),
+                           "z": None,          # float64 noise stream, allocated by the first white-noise call
                            "uploaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "downloaded": torch.cuda.Event()})
             self._hs = hs
             self._host_turn = 0

@@ -214,6 +214,16 @@ int asr_snr_sigma_host(const float* power_host, const float* log10_power_host, f
 int asr_mix_white(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
                   int32_t n_clips, const double* z_dev, const double* sigma_dev, double* out_dev, void* stream);
 
+/* Babble noise of BASELINE configs[1] ("white/babble").  The reference has NO babble implementation (parity unpinned);
+ * the recipe is SURVEY.md 8(d): babble[b][n] = sum over k = 1..talkers of clip (b + k*stride) mod n_clips at sample n
+ * (float64, exact), power[b] = mean(babble[b]^2) in float64 (fixed order).  The mix is the white-noise formula with
+ * z := babble and sigma[b] := sigma_snr[b] / sqrt(power[b]) (host), i.e. asr_mix_white / the fused launch take the
+ * stream unchanged: noise power = P / 10^(snr/10) by the same sigma law as VDR/attacks.py:233-241.
+ * babble_dev is packed like the audio (float64), power_dev is float64 [n_clips]. */
+int asr_babble_stream(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
+                      int32_t n_clips, int32_t stride, int32_t talkers, double* babble_dev, double* power_dev,
+                      void* stream);
+
 /* out = float64(x) + (|q|<p ? sigma1 : sigma0)*g - VDR/attacks.py:159-181 */
 int asr_mix_mixture(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
                     int32_t n_clips, const double* q_dev, const double* g_dev, double p, double sigma0,
@@ -263,6 +273,12 @@ int asr_resample_batch(const void* in_dev, int32_t dtype, const int64_t* in_offs
                        int32_t n_clips, int32_t max_in_length, int32_t up, int32_t down, const float* taps_dev,
                        int32_t n_taps, int32_t n_pre_remove, float* out_dev, const int64_t* out_offsets_dev,
                        void* stream);
+
+/* ---- measurement probes ----
+ * FP32 FMA peak of the device (non-tensor CUDA cores): n_blocks x 512 threads x iters x 64 dependent-chain FMAs, 8 chains
+ * per thread.  The caller times the launch with CUDA events: flops = n_blocks * 512 * iters * 64 * 2.  sink_dev receives
+ * n_blocks * 512 floats.  bench.py quotes the FP32 roofline against this measured figure. */
+int asr_fp32_peak_probe(int32_t n_blocks, int32_t iters, float* sink_dev, void* stream);
 
 /* ---- diagnostics ----
  * Breadcrumb of the tensor-core kernel's bounded waits: word 0 = wait site that timed out (0 = none), 1 = CTA,

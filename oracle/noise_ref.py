@@ -85,6 +85,31 @@ def add_white_noise_with_snr_z(audio, target_snr_db, z):
     return sample + noise_volts
 
 
+# ---- babble noise: BASELINE.json configs[1] ("white/babble"); NO reference implementation - PARITY UNPINNED ----
+# Recipe of SURVEY.md 8(d): the noise of clip i is the sum of 6 other clips of the batch, indices (i + k*97) mod B,
+# scaled by the sigma law of add_white_noise_with_snr so that noise power = P / 10^(snr/10).
+def babble_stream(clips, i, stride=97, talkers=6):
+    """float64 sum of the `talkers` other clips at every sample of clip i (a shorter talker contributes nothing past its end)."""
+    n = len(clips[i])
+    b = np.zeros(n, dtype=np.float64)
+    for k in range(1, talkers + 1):
+        c = np.asarray(clips[(i + k * stride) % len(clips)], dtype=np.float64)
+        m = min(n, len(c))
+        b[:m] += c[:m]
+    return b
+
+
+def add_babble_with_snr(clips, i, target_snr_db, stride=97, talkers=6, gain=None):
+    """clip i + gain * babble, gain = sigma(P_i, snr) / sqrt(mean(babble^2)); `gain` may be given (bit-exact mix test)."""
+    sample = np.asanyarray(clips[i])
+    b = babble_stream(clips, i, stride, talkers)
+    if gain is None:
+        sigma = snr_sigma(sample, target_snr_db)
+        pb = np.mean(b ** 2)
+        gain = float(sigma) / np.sqrt(pb) if pb > 0 else 0.0
+    return sample + float(gain) * b
+
+
 # ---- numpy's float32 pairwise summation, restated (used to explain / pin the device order) ---
 def pairwise_sum_f32(a: np.ndarray) -> np.float32:
     """Python replica of numpy's ``pairwise_sum`` for a contiguous float32 vector.

@@ -169,3 +169,33 @@ def test_fused_noise_mfcc_matches_oracle_pipeline():
         zs = [np.random.standard_normal(16000) for _ in clips]
         ref = pr.black_box_attack_on_audio_dataset_snr(to_f32(clips), snr, zs, utterance_length=101, p=lr.C1)
         assert np.abs(got - ref).max() <= 3e-3
+
+
+def test_babble_stream_and_mix():
+    """BASELINE configs[1] babble (no reference implementation; recipe of SURVEY.md 8(d)): the stream equals the oracle's
+    sum bit for bit, its power to 1e-13, and the mix - the white-noise formula on that stream - is bit-exact given the gain."""
+    import asr_b200 as A
+    from oracle import noise_ref as nr
+    rng = np.random.default_rng(9)
+    lengths = [16000] * 20 + rng.integers(3000, 17000, size=90).tolist()
+    clips = to_f32(synth_clips(len(lengths), 17000, 16000, 31))
+    clips = [c[:n] for c, n in zip(clips, lengths)]
+    batch = A.ClipBatch.from_arrays(clips)
+    b_dev, pb_dev = A.babble_stream(batch)
+    bs = batch.unpack(b_dev)
+    pb = pb_dev.cpu().numpy()
+    for i in range(len(clips)):
+        want = nr.babble_stream(clips, i)
+        assert np.array_equal(bs[i].view(np.uint64), want.view(np.uint64)), i
+        assert abs(pb[i] - np.mean(want ** 2)) <= 1e-13 * np.mean(want ** 2)
+    sigma = A.snr_sigma_host(A.clip_power(batch).cpu().numpy(), 5)
+    gain = A.babble_gain_host(sigma, pb)
+    noisy = batch.unpack(A.mix_white(batch, b_dev, torch.from_numpy(gain).cuda()))
+    for i in range(len(clips)):
+        want = nr.add_babble_with_snr(clips, i, 5, gain=gain[i])
+        assert np.array_equal(noisy[i].view(np.uint64), want.view(np.uint64)), i
+        free = nr.add_babble_with_snr(clips, i, 5)                     # the oracle's own gain: same signal to 1e-12
+        assert np.abs(free - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+        # realised SNR is the target (the point of the sigma law)
+        snr = 10 * np.log10(np.mean(clips[i].astype(np.float64) ** 2) / np.mean((want - clips[i]) ** 2))
+        assert abs(snr - 5) < 1e-3

@@ -101,3 +101,22 @@ def test_benchmarked_step_uses_the_reference_sigma_chain():
     dev = NoisyFeaturePipeline(A.C1, 101, sigma_mode="device")
     out = dev.run_device(batch, z, 10)
     assert torch.isfinite(out).all()
+
+
+def test_babble_step_matches_oracle():
+    """The C2 step with babble instead of white noise: features of the oracle's babble mix, standardised."""
+    import asr_b200 as A
+    from asr_b200.pipeline import NoisyFeaturePipeline
+    from oracle import librosa_ref as lr, noise_ref as nr, cmvn_ref as cr
+    B, L = 128, 16000
+    clips = synth_clips(B, L, 16000, 909)
+    audio = torch.from_numpy(np.stack(clips)).cuda()
+    batch = A.ClipBatch.from_matrix(audio)
+    pipe = NoisyFeaturePipeline(A.C1, 101)
+    xs = to_f32(clips)
+    for snr in (10, 0):
+        out = pipe.run_device(batch, None, snr, noise_kind="babble", prefetch=batch).cpu().numpy()
+        rows = np.stack([lr.mfcc(nr.add_babble_with_snr(xs, i, snr), lr.C1).astype(np.float64).flatten() for i in range(B)])
+        a, b, c = cr.standardize_dataset(rows[:1], rows[1:2], rows[2:])
+        ref = np.concatenate([a, b, c])
+        assert np.abs(out - ref).max() < 2e-2 and np.abs(out - ref).mean() < 2e-4
