@@ -57,6 +57,12 @@ SIGNATURES = {
     "asr_plan_set_stage_probe": (C.c_int, [_vp, _vp]),
     "asr_plan_debug_word": (_i32, [_vp, _i32]),
     "asr_fp32_peak_probe": (C.c_int, [_i32, _i32, _vp, _vp]),
+    "asr_cmvn_workspace_bytes": (C.c_size_t, [_i32]),
+    "asr_cmvn_partial_sums": (_i32, [_vp, _i32, _i64, _i32, _i64, C.POINTER(NoiseC), _i32, _i32, _i64, _i32, _vp, C.c_size_t, _vp]),
+    "asr_cmvn_local_message": (C.c_int, [_vp, C.c_size_t, _i32, _i32, _i64, _i32, _vp, _vp]),
+    "asr_cmvn_merge": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "asr_cmvn_apply2": (C.c_int, [_vp, _i32, _i64, _i32, _i64, C.POINTER(NoiseC), _vp, C.c_size_t, _i32, _i32, _i64, _vp, _vp, _vp,
+                                  _vp, _i32, _vp]),
     "asr_tc_selftest": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "asr_mfcc_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, C.POINTER(NoiseC), _vp, _i32, _i32, _vp,
                                  _vp, C.c_size_t, _vp]),
@@ -69,7 +75,8 @@ SIGNATURES = {
     "asr_clip_power": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "asr_snr_sigma": (C.c_int, [_vp, _f32, _vp, _i32, _vp]),
     "asr_snr_sigma_host": (C.c_int, [_vp, _vp, _f32, _vp, _i32]),
-    "asr_babble_stream": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "asr_babble_workspace_bytes": (C.c_size_t, [_i32, _i32]),
+    "asr_babble_stream": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
     "asr_mix_white": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "asr_mix_mixture": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _f64, _f64, _f64, _vp, _vp]),
     "asr_mix_rows_white": (C.c_int, [_vp, _i64, _vp, _f64, _vp, _vp]),

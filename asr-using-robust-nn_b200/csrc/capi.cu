@@ -1202,7 +1202,17 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     cs *= 2;
     smem_bytes = layout(cs, kp);
   }
-  ASR_CUDA_TRY(launch_mfcc(kp, static_cast<int>(smem_bytes), as_stream(stream)));
+  {
+    const cudaError_t le = launch_mfcc(kp, static_cast<int>(smem_bytes), as_stream(stream));
+    if (le == cudaErrorLaunchOutOfResources && cs > 1) {
+      cudaGetLastError();
+      set_error(std::string(who) + ": a cluster of " + std::to_string(cs) + " CTAs with " + std::to_string(smem_bytes) +
+                " bytes of shared memory each cannot be co-scheduled on this device (clip of " + std::to_string(max_length) +
+                " samples, " + std::to_string(t_all) + " frames)");
+      return ASR_ERR_TOO_LARGE;
+    }
+    ASR_CUDA_TRY(le);
+  }
   return ASR_OK;
 }
 

@@ -576,6 +576,21 @@ static cudaError_t launch_one(const KParams& kp, int smem_bytes, cudaStream_t st
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = kp.cluster_size > 1 ? 1 : 0;
+  if (kp.cluster_size > 1) {
+    // a cluster of this size and shared-memory footprint must be co-schedulable at all (non-portable size 16 with
+    // nearly full shared memory per CTA may not be): checked once per (cluster size, shared memory) and device
+    static int checked_cs[kMaxDevices] = {0}, checked_smem[kMaxDevices] = {0}, checked_ok[kMaxDevices] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices && (checked_cs[dev] != kp.cluster_size || checked_smem[dev] != smem_bytes)) {
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, mfcc_kernel<NFFT, DT>, &cfg);
+      if (e != cudaSuccess) return e;
+      checked_cs[dev] = kp.cluster_size; checked_smem[dev] = smem_bytes; checked_ok[dev] = n > 0;
+    }
+    if (dev >= 0 && dev < kMaxDevices && !checked_ok[dev]) return cudaErrorLaunchOutOfResources;
+  }
   return cudaLaunchKernelEx(&cfg, mfcc_kernel<NFFT, DT>, kp);
 }
 

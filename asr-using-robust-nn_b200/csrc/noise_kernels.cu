@@ -530,32 +530,69 @@ __global__ void __launch_bounds__(256) mix_white_kernel(const void* __restrict__
 //   Pb_i = mean_n b_i[n]^2 in float64 in a FIXED order (256 strided partials per clip, then a binary tree).
 // The mix itself is the white-noise formula with z := b and sigma := gain (float64 x + gain*b, two roundings), so the
 // fused MFCC launch and asr_mix_white take the stream as it is.  One CTA per clip.
+// Grid (clip, chunk of 2048 samples): the 256 threads of a CTA take 8 consecutive samples each (vector loads of every
+// talker), chunk partials go to `part` and the last CTA of a clip adds them in ascending chunk order.
+constexpr int kBabbleChunk = 2048;
 __global__ void __launch_bounds__(256) babble_stream_kernel(const void* __restrict__ audio, const int dtype,
                                                             const long long* __restrict__ offsets,
                                                             const int* __restrict__ lengths, const int n_clips,
                                                             const int stride, const int talkers,
-                                                            double* __restrict__ b_out, double* __restrict__ power_out) {
+                                                            double* __restrict__ b_out, double* __restrict__ part,
+                                                            int* __restrict__ counter, double* __restrict__ power_out,
+                                                            const int max_chunks) {
   __shared__ double s_red[256];
-  const int i = blockIdx.x;
+  __shared__ int s_last;
+  const int i = blockIdx.x, ch = blockIdx.y;
   const int L = lengths[i];
+  const int n_chunks = (L + kBabbleChunk - 1) / kBabbleChunk;
+  if (ch >= max(n_chunks, 1)) return;
   const long long base = offsets[i];
-  double acc = 0.0;
-  for (int n = threadIdx.x; n < L; n += 256) {
-    double b = 0.0;
-    for (int k = 1; k <= talkers; ++k) {
-      const int j = static_cast<int>((static_cast<long long>(i) + static_cast<long long>(k) * stride) % n_clips);
-      if (n < lengths[j]) b += audio_f64(audio, dtype, offsets[j] + n);
+  const int n0 = ch * kBabbleChunk + 8 * threadIdx.x;
+  double b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 1; k <= talkers; ++k) {
+    const int j = static_cast<int>((static_cast<long long>(i) + static_cast<long long>(k) * stride) % n_clips);
+    const int Lj = min(lengths[j], L);
+    const long long oj = offsets[j];
+    if (n0 + 8 <= Lj && dtype == ASR_I16 && ((oj + n0) & 7) == 0) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const short*>(audio) + oj + n0));
+      const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        b[2 * e] += static_cast<double>(static_cast<short>(w[e] & 0xFFFF)) * (1.0 / 32768.0);
+        b[2 * e + 1] += static_cast<double>(static_cast<short>(w[e] >> 16)) * (1.0 / 32768.0);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (n0 + e < Lj) b[e] += audio_f64(audio, dtype, oj + n0 + e);
     }
-    b_out[base + n] = b;
-    acc = __dadd_rn(acc, __dmul_rn(b, b));
   }
+  double acc = 0.0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (n0 + e < L) {
+      b_out[base + n0 + e] = b[e];
+      acc = __dadd_rn(acc, __dmul_rn(b[e], b[e]));
+    }
   s_red[threadIdx.x] = acc;
   __syncthreads();
   for (int w = 128; w > 0; w >>= 1) {
     if (threadIdx.x < w) s_red[threadIdx.x] = __dadd_rn(s_red[threadIdx.x], s_red[threadIdx.x + w]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) power_out[i] = L > 0 ? s_red[0] / static_cast<double>(L) : 0.0;
+  if (threadIdx.x == 0) {
+    part[static_cast<long long>(i) * max_chunks + ch] = s_red[0];
+    __threadfence();
+    s_last = atomicAdd(counter + i, 1) == max(n_chunks, 1) - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (int c = 0; c < n_chunks; ++c) t = __dadd_rn(t, __ldcg(part + static_cast<long long>(i) * max_chunks + c));
+    power_out[i] = L > 0 ? t / static_cast<double>(L) : 0.0;
+    counter[i] = 0;                                      // ready for the next call
+  }
 }
 
 __global__ void __launch_bounds__(256) mix_mixture_kernel(const void* __restrict__ audio, const int dtype,
@@ -712,17 +749,32 @@ extern "C" int asr_mix_white(const void* audio_dev, int32_t dtype, const int64_t
   return ASR_OK;
 }
 
+extern "C" size_t asr_babble_workspace_bytes(int32_t n_clips, int32_t max_length) {
+  if (n_clips <= 0 || max_length < 0) return 0;
+  const size_t chunks = static_cast<size_t>(std::max(1, (max_length + kBabbleChunk - 1) / kBabbleChunk));
+  return ((sizeof(int) * static_cast<size_t>(n_clips) + 255) & ~static_cast<size_t>(255)) + sizeof(double) * chunks * n_clips;
+}
+
 extern "C" int asr_babble_stream(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
-                                 int32_t n_clips, int32_t stride, int32_t talkers, double* babble_dev, double* power_dev,
-                                 void* stream) {
+                                 int32_t n_clips, int32_t max_length, int32_t stride, int32_t talkers, double* babble_dev,
+                                 double* power_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   if (!audio_dev || !offsets_dev || !lengths_dev || !babble_dev || !power_dev || n_clips < 0 || talkers < 1 || stride < 1 ||
-      dtype < ASR_I16 || dtype > ASR_F64) {
+      max_length < 0 || dtype < ASR_I16 || dtype > ASR_F64) {
     set_error("asr_babble_stream: invalid argument");
     return ASR_ERR_INVALID;
   }
   if (n_clips == 0) return ASR_OK;
-  babble_stream_kernel<<<n_clips, 256, 0, as_stream(stream)>>>(audio_dev, dtype, reinterpret_cast<const long long*>(offsets_dev),
-                                                               lengths_dev, n_clips, stride, talkers, babble_dev, power_dev);
+  if (!workspace_dev || workspace_bytes < asr_babble_workspace_bytes(n_clips, max_length) ||
+      (reinterpret_cast<uintptr_t>(workspace_dev) & 7)) {
+    set_error("asr_babble_stream: workspace too small (asr_babble_workspace_bytes) or misaligned; it must be zeroed once");
+    return ASR_ERR_INVALID;
+  }
+  const int chunks = std::max(1, (max_length + kBabbleChunk - 1) / kBabbleChunk);
+  int* counter = static_cast<int*>(workspace_dev);
+  double* part = reinterpret_cast<double*>(static_cast<char*>(workspace_dev) + ((sizeof(int) * static_cast<size_t>(n_clips) + 255) & ~static_cast<size_t>(255)));
+  babble_stream_kernel<<<dim3(n_clips, chunks), 256, 0, as_stream(stream)>>>(
+      audio_dev, dtype, reinterpret_cast<const long long*>(offsets_dev), lengths_dev, n_clips, stride, talkers, babble_dev, part,
+      counter, power_dev, chunks);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }

@@ -137,6 +137,16 @@ class Noise:
         # add_noise: sigma0 = alpha ; sigma1 = 10 * alpha   (VDR/attacks.py:176-178)
         return Noise(_lib.ASR_NOISE_MIXTURE, z=q, z2=g, p=float(p), sigma0=alpha, sigma1=10 * alpha)
 
+    @staticmethod
+    def rows_white(z: torch.Tensor, sigma: float) -> "Noise":
+        """Feature-domain white noise on an (N, D) matrix: x + sigma*z (add_white_noise_on_dataset, VDR/attacks.py:186-201)."""
+        return Noise(_lib.ASR_NOISE_WHITE, z=z, sigma0=float(sigma))
+
+    @staticmethod
+    def rows_mixture(q: torch.Tensor, g: torch.Tensor, p: float, alpha: float) -> "Noise":
+        """Feature-domain mixture noise (add_noise_mixture_on_dataset, VDR/attacks.py:204-219)."""
+        return Noise(_lib.ASR_NOISE_MIXTURE, z=q, z2=g, p=float(p), sigma0=alpha, sigma1=10 * alpha)
+
     def to_c(self) -> NoiseC:
         for t in (self.z, self.z2, self.sigma):
             if t is not None and (t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous()):
@@ -344,6 +354,9 @@ def mix_white(batch: ClipBatch, z: torch.Tensor, sigma: torch.Tensor) -> torch.T
 BABBLE_STRIDE, BABBLE_TALKERS = 97, 6      # six other clips of the batch, indices (i + k*97) mod B
 
 
+_BABBLE_WS: dict = {}
+
+
 def babble_stream(batch: ClipBatch, stride: int = BABBLE_STRIDE, talkers: int = BABBLE_TALKERS,
                   out: Optional[torch.Tensor] = None, power: Optional[torch.Tensor] = None):
     """Babble stream of a batch (float64, packed like the audio) and its mean power per clip (float64 [B])."""
@@ -352,10 +365,16 @@ def babble_stream(batch: ClipBatch, stride: int = BABBLE_STRIDE, talkers: int = 
         out = torch.zeros(batch.audio.shape[0], dtype=torch.float64, device=dev)
     if power is None:
         power = torch.empty(batch.n_clips, dtype=torch.float64, device=dev)
+    need = lib.asr_babble_workspace_bytes(batch.n_clips, batch.max_length)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _BABBLE_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=dev)       # zeroed once; the kernel leaves its counters at zero
+        _BABBLE_WS[key] = ws
     with torch.cuda.device(dev):
         check(lib.asr_babble_stream(batch.audio.data_ptr(), batch.dtype_code, batch.offsets.data_ptr(), batch.lengths.data_ptr(),
-                                    batch.n_clips, int(stride), int(talkers), out.data_ptr(), power.data_ptr(), _stream()),
-              "asr_babble_stream")
+                                    batch.n_clips, batch.max_length, int(stride), int(talkers), out.data_ptr(), power.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), _stream()), "asr_babble_stream")
     return out, power
 
 
@@ -447,13 +466,19 @@ class Resampler:
 
 # ---- standardisation ---------------------------------------------------------------------------------
 class Standardizer:
-    """``StandardScaler().fit_transform`` over row blocks that may live on several GPUs.
+    """``StandardScaler().fit_transform`` over row blocks that may live on several GPUs
+    (``standardize_dataset``, VDR/attacks.py:48-69).
 
-    ``fit`` runs sklearn's two passes on this rank's row blocks and - when a
-    ``torch.distributed`` process group is given - all-reduces the float64
-    accumulators (``[n, sum x]`` then ``[sum (x-mean), sum (x-mean)^2]``) over
-    NCCL/NVLink between the passes, so every rank ends with the statistics of the
-    whole dataset (``standardize_dataset``, VDR/attacks.py:48-69).
+    sklearn's two passes run on this rank's rows (pass 1: column sums; pass 2: sums of ``x - m`` and ``(x - m)^2`` about
+    the LOCAL mean), the rank's message ``[n, S, C, Q]`` (3 D + 1 float64) is exchanged ONCE (one all-gather over
+    NCCL / NVLink, the only inter-GPU exchange of the path) and every rank merges the messages in rank order, moving the
+    centred sums to the global mean (Chan's update) - with one rank the merge is the identity.  On a single GPU the
+    whole ``fit`` + ``transform`` of one matrix is three launches (`fit_transform`): the last reduction of each pass
+    happens inside the next launch.
+
+    ``noise=`` (``Noise.rows_white`` / ``Noise.rows_mixture``) makes every pass read ``x + noise`` instead of ``x``: the
+    MFCC-domain attacks of VDR/attacks.py:186-219 followed by ``standardize_dataset`` (:433-491) without writing the
+    noisy matrix.
     """
 
     def __init__(self, n_cols: int, device="cuda", group=None, distributed: bool = False):
@@ -462,18 +487,34 @@ class Standardizer:
         self.group = group
         self.distributed = distributed
         D = self.n_cols
-        # persistent float64 work vectors (stable addresses: the fit can be captured in CUDA graphs)
-        self.acc1 = torch.zeros(D + 1, dtype=torch.float64, device=self.device)    # [sum x (D), n]
-        self.acc2 = torch.zeros(2 * D, dtype=torch.float64, device=self.device)    # [sum (x-mean), sum (x-mean)^2]
+        # persistent float64 vectors (stable addresses: the fit can be captured in CUDA graphs)
+        self.msg = torch.zeros(3 * D + 1, dtype=torch.float64, device=self.device)     # [n, S (D), C (D), Q (D)] of this rank
+        self.msgs = self.msg.view(1, -1)                                               # all ranks' messages, rank order
         self.mean = torch.zeros(D, dtype=torch.float64, device=self.device)
         self.var = torch.zeros(D, dtype=torch.float64, device=self.device)
         self.scale = torch.ones(D, dtype=torch.float64, device=self.device)
-        self.n_total = 0
+        self.n_dev = torch.zeros(1, dtype=torch.float64, device=self.device)           # rows over all ranks (device copy)
+        self._n_total: Optional[int] = None
+        self._ws: Optional[torch.Tensor] = None
+        self._slabs = (0, 0)
+        self._n_local = 0
 
-    def _allreduce(self, t: torch.Tensor) -> None:
-        if self.distributed:
-            import torch.distributed as dist
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+    @property
+    def n_total(self) -> int:
+        if self._n_total is None:
+            self._n_total = int(round(float(self.n_dev.item())))
+        return self._n_total
+
+    def _world(self) -> int:
+        if not self.distributed:
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size(self.group)
+
+    def _workspace(self) -> torch.Tensor:
+        if self._ws is None:
+            self._ws = torch.empty(lib.asr_cmvn_workspace_bytes(self.n_cols), dtype=torch.uint8, device=self.device)
+        return self._ws
 
     @staticmethod
     def _mat(x: torch.Tensor):
@@ -481,63 +522,94 @@ class Standardizer:
             raise ValueError("row blocks must be 2-D float32/float64 with unit column stride")
         return x.data_ptr(), _DT[x.dtype], x.shape[0], x.shape[1], x.stride(0)
 
-    # The fit is three launch groups separated by the two all-reduces (the only inter-GPU exchange of the path).
-    def pass1_local(self, blocks: Sequence[torch.Tensor]) -> None:
-        """acc1 = [column sums of this rank's rows, number of rows]."""
+    @staticmethod
+    def _nz(noise):
+        return C.byref(noise.to_c()) if noise is not None else None
+
+    # ---- the launch groups of a fit (the sharded step is: local_stats, local_message | exchange | merge) ----
+    def local_stats(self, blocks: Sequence[torch.Tensor], noises: Optional[Sequence] = None) -> None:
+        """Both passes over this rank's row blocks: slab partials in the workspace (2 launches per block)."""
         D = self.n_cols
-        rows = 0
+        ws = self._workspace()
+        noises = list(noises) if noises is not None else [None] * len(blocks)
+        rows = sum(int(x.shape[0]) for x in blocks)
         with torch.cuda.device(self.device):
-            self.acc1.zero_()
-            for x in blocks:
-                p, dt, r, c, ld = self._mat(x)
-                if c != D:
-                    raise ValueError(f"row block has {c} columns, expected {D}")
-                if r == 0:
-                    continue
-                check(lib.asr_cmvn_colsum(p, dt, r, c, ld, self.acc1.data_ptr(), _stream()), "asr_cmvn_colsum")
-                rows += r
-            self.acc1[D:].fill_(float(rows))
+            counts = [0, 0]
+            for pas in (1, 2):
+                for x, nz in zip(blocks, noises):
+                    p, dt, r, c, ld = self._mat(x)
+                    if c != D:
+                        raise ValueError(f"row block has {c} columns, expected {D}")
+                    if r == 0:
+                        continue
+                    keep = nz.to_c() if nz is not None else None
+                    n = lib.asr_cmvn_partial_sums(p, dt, r, c, ld, C.byref(keep) if keep is not None else None, pas, counts[0],
+                                                  max(rows, 1), counts[pas - 1], ws.data_ptr(), ws.numel(), _stream())
+                    if n < 0:
+                        check(n, "asr_cmvn_partial_sums")
+                    counts[pas - 1] += n
+        self._slabs = (counts[0], counts[1])
+        self._n_local = rows
+        self._n_total = None
 
-    def pass2_local(self, blocks: Sequence[torch.Tensor], n_total: int) -> None:
-        """mean from the (all-reduced) acc1, then acc2 = centred sums of this rank's rows."""
-        D = self.n_cols
-        self.n_total = int(n_total)
+    def local_message(self) -> None:
+        ws = self._workspace()
         with torch.cuda.device(self.device):
-            check(lib.asr_cmvn_mean(self.acc1.data_ptr(), self.n_total, D, self.mean.data_ptr(), _stream()), "asr_cmvn_mean")
-            self.acc2.zero_()
-            for x in blocks:
-                p, dt, r, c, ld = self._mat(x)
-                if r == 0:
-                    continue
-                check(lib.asr_cmvn_colsum_centered(p, dt, r, c, ld, self.mean.data_ptr(), self.acc2.data_ptr(), _stream()),
-                      "asr_cmvn_colsum_centered")
+            check(lib.asr_cmvn_local_message(ws.data_ptr(), ws.numel(), self._slabs[0], self._slabs[1], self._n_local, self.n_cols,
+                                             self.msg.data_ptr(), _stream()), "asr_cmvn_local_message")
 
-    def finish(self) -> None:
-        """var / scale from the (all-reduced) acc2."""
+    def exchange(self) -> None:
+        """The one collective of the path: every rank's message to every rank."""
+        if not self.distributed:
+            self.msgs = self.msg.view(1, -1)
+            return
+        import torch.distributed as dist
+        w = self._world()
+        if self.msgs.shape[0] != w or self.msgs.data_ptr() == self.msg.data_ptr():
+            self.msgs = torch.zeros((w, self.msg.numel()), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(self.msgs.view(-1), self.msg, group=self.group)
+
+    def merge(self) -> None:
         with torch.cuda.device(self.device):
-            check(lib.asr_cmvn_finalize(self.acc2.data_ptr(), self.mean.data_ptr(), self.n_total, self.n_cols,
-                                        self.var.data_ptr(), self.scale.data_ptr(), _stream()), "asr_cmvn_finalize")
+            check(lib.asr_cmvn_merge(self.msgs.data_ptr(), self.msgs.shape[0], self.n_cols, self.mean.data_ptr(), self.var.data_ptr(),
+                                     self.scale.data_ptr(), self.n_dev.data_ptr(), _stream()), "asr_cmvn_merge")
+        self._n_total = None
 
-    def fit(self, blocks: Sequence[torch.Tensor], n_total: Optional[int] = None) -> "Standardizer":
-        """`n_total` (rows over ALL ranks) may be given when the caller knows it; that avoids the one
-        device->host read of the all-reduced count and keeps the whole fit asynchronous."""
-        self.pass1_local(blocks)
-        self._allreduce(self.acc1)
-        if n_total is None:
-            n_total = int(round(self.acc1[self.n_cols].item()))
-        self.pass2_local(blocks, n_total)
-        self._allreduce(self.acc2)
-        self.finish()
+    def fit(self, blocks: Sequence[torch.Tensor], n_total: Optional[int] = None, noises: Optional[Sequence] = None) -> "Standardizer":
+        """Statistics of the rows of all ranks.  (`n_total` is accepted for compatibility: the merge derives it.)"""
+        self.local_stats(blocks, noises)
+        self.local_message()
+        self.exchange()
+        self.merge()
+        if n_total is not None:
+            self._n_total = int(n_total)
         return self
 
-    def transform(self, x: torch.Tensor, out_dtype=torch.float64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def transform(self, x: torch.Tensor, out_dtype=torch.float64, out: Optional[torch.Tensor] = None, noise=None) -> torch.Tensor:
+        return self._apply(x, out_dtype, out, noise, fused=False)
+
+    def fit_transform(self, x: torch.Tensor, out_dtype=torch.float64, out: Optional[torch.Tensor] = None, noise=None) -> torch.Tensor:
+        """Single rank, one matrix: statistics and standardised rows in three launches."""
+        if self.distributed:
+            self.fit([x], noises=[noise])
+            return self.transform(x, out_dtype, out, noise)
+        self.local_stats([x], [noise])
+        res = self._apply(x, out_dtype, out, noise, fused=True)
+        self._n_total = int(x.shape[0])
+        return res
+
+    def _apply(self, x, out_dtype, out, noise, fused):
         p, dt, r, c, ld = self._mat(x)
         if out is None:
             out = torch.empty((r, c), dtype=out_dtype, device=x.device)
         elif out.shape != (r, c) or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous {(r, c)} tensor")
         out_dtype = out.dtype
+        keep = noise.to_c() if noise is not None else None
+        ws = self._workspace() if fused else None
         with torch.cuda.device(x.device):
-            check(lib.asr_cmvn_apply(p, dt, r, c, ld, self.mean.data_ptr(), self.scale.data_ptr(), out.data_ptr(),
-                                     _DT[out_dtype], _stream()), "asr_cmvn_apply")
+            check(lib.asr_cmvn_apply2(p, dt, r, c, ld, C.byref(keep) if keep is not None else None,
+                                      ws.data_ptr() if fused else None, ws.numel() if fused else 0, self._slabs[0], self._slabs[1],
+                                      max(self._n_local, 1), self.mean.data_ptr(), self.var.data_ptr(), self.scale.data_ptr(),
+                                      out.data_ptr(), _DT[out_dtype], _stream()), "asr_cmvn_apply2")
         return out

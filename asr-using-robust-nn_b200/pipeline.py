@@ -15,9 +15,9 @@ enqueued in front of THIS step's MFCC launch, so the host chain of step i+1 runs
 ``sigma_mode="device"`` evaluates the chain in float64 on the device (within 1 ulp of the host chain, not equal).
 
 The launches of one step are short (tens of microseconds each) and their number is fixed, so the step is
-captured once per (batch buffers, SNR) in CUDA graphs and replayed: one graph per launch group, the
-groups being separated by the two NCCL all-reduces of the standardisation when clips are sharded over
-several GPUs (a single graph for the whole step on one GPU).
+captured once per batch buffers in CUDA graphs and replayed: a single graph for the whole step on one GPU; when clips are
+sharded over several GPUs two graphs separated by the ONE collective of the path, the all-gather of the ranks'
+standardisation messages (`Standardizer.exchange`).
 """
 from __future__ import annotations
 
@@ -32,9 +32,10 @@ from .frontend import (ClipBatch, MfccPlan, Noise, Standardizer, clip_power, snr
 from .params import MfccParams
 
 # kernels of libasr_b200 launched by one `run_device` step besides the MFCC launches (`plan.launches`):
-# 2x colsum (partial + final), mean, finalize, apply; + power (and the sigma kernel in device mode) when noisy; the
-# e2e step adds randn
-LAUNCHES_CMVN = 7
+# standardisation: pass 1, pass 2, apply (single GPU; sharded: + message and merge); + power (and the sigma kernel in
+# device mode, the babble stream with babble noise) when noisy; the e2e step adds randn
+LAUNCHES_CMVN = 3
+LAUNCHES_CMVN_SHARDED = 5
 LAUNCHES_NOISE = 1
 
 
@@ -72,7 +73,8 @@ class NoisyFeaturePipeline:
 
     def launches_per_step(self, noisy: bool, standardize: bool = True) -> int:
         noise = (LAUNCHES_NOISE + (1 if self.sigma_mode == "device" else 0)) if noisy else 0
-        return self.plan.launches(noisy) + noise + (LAUNCHES_CMVN if standardize else 0)
+        cmvn = (LAUNCHES_CMVN_SHARDED if self.distributed else LAUNCHES_CMVN) if standardize else 0
+        return self.plan.launches(noisy) + noise + cmvn
 
     # ---- sigma: device power -> host chain -> device sigma, one step ahead when the caller prefetches -----------
     @staticmethod
@@ -143,6 +145,11 @@ class NoisyFeaturePipeline:
         st["sigma_dev"][:B].copy_(sl["sig_host"][:B], non_blocking=True)
         return st["sigma_dev"][:B], (sl["b_dev"] if babble else None)
 
+    def _feat_buffer(self, B: int) -> torch.Tensor:
+        if self._feats is None or self._feats.shape[0] != B:
+            self._feats = torch.empty((B, self.rows, self.out_frames), dtype=torch.float32, device=self.device)
+        return self._feats
+
     # ---- the three launch groups of a step ----------------------------------------------------------
     def _group1(self, batch, z, snr_db, feats, sigma=None):
         noise = None
@@ -177,8 +184,7 @@ class NoisyFeaturePipeline:
         flat = feats.view(batch.n_clips, self.D)
         if not standardize:
             return flat
-        self.std.fit([flat], n_total=batch.n_clips * self.world_size)
-        return self.std.transform(flat, out_dtype=out_dtype)
+        return self.std.fit_transform(flat, out_dtype=out_dtype)
 
     def _run_graphed(self, batch, z, snr_db, standardize, out_dtype, sigma=None):
         # host sigma mode: the graph reads the (fixed) device sigma vector, so one capture serves every SNR
@@ -194,10 +200,8 @@ class NoisyFeaturePipeline:
             sg.graphs[0].replay()
         else:
             sg.graphs[0].replay()
-            self.std._allreduce(self.std.acc1)
+            self.std.exchange()                            # the one collective of the step
             sg.graphs[1].replay()
-            self.std._allreduce(self.std.acc2)
-            sg.graphs[2].replay()
         return sg.out
 
     def _capture(self, batch, z, snr_db, standardize, out_dtype, sigma=None) -> _StepGraphs:
@@ -211,8 +215,7 @@ class NoisyFeaturePipeline:
         # warm the kernels once outside capture (lazy module loading is not capturable)
         self._group1(batch, z, snr_db, feats, sigma)
         if standardize:
-            self.std.fit([flat], n_total=n_total)
-            self.std.transform(flat, out=out)
+            self.std.fit_transform(flat, out=out)
         torch.cuda.synchronize(self.device)
         pool = torch.cuda.graph_pool_handle()
 
@@ -222,34 +225,31 @@ class NoisyFeaturePipeline:
                 fn()
             sg.graphs.append(g)
 
-        def g1():
+        def g1():                                           # sharded: everything up to this rank's message
             self._group1(batch, z, snr_db, feats, sigma)
-            if standardize:
-                self.std.pass1_local([flat])
+            self.std.local_stats([flat])
+            self.std.local_message()
 
-        def g2():
-            self.std.pass2_local([flat], n_total)
-
-        def g3():
-            self.std.finish()
+        def g2():                                           # sharded: after the all-gather
+            self.std.merge()
             self.std.transform(flat, out=out)
 
         if not standardize:
             cap(lambda: self._group1(batch, z, snr_db, feats, sigma))
         elif self.distributed:
-            # default: three graphs with the two NCCL all-reduces launched between them; opt-in: one graph for the whole
-            # step with the all-reduces captured inside it
+            # default: two graphs with the one NCCL all-gather launched between them; opt-in: one graph for the whole
+            # step with the collective captured inside it
             if self.capture_collectives:
                 try:
-                    cap(lambda: (g1(), self.std._allreduce(self.std.acc1), g2(), self.std._allreduce(self.std.acc2), g3()))
+                    cap(lambda: (g1(), self.std.exchange(), g2()))
                 except Exception:                       # noqa: BLE001  (capture errors surface as RuntimeError subclasses)
                     sg.graphs.clear()
                     self.capture_collectives = False
                     torch.cuda.synchronize(self.device)
             if not sg.graphs:
-                cap(g1); cap(g2); cap(g3)
+                cap(g1); cap(g2)
         else:
-            cap(lambda: (g1(), g2(), g3()))
+            cap(lambda: (self._group1(batch, z, snr_db, feats, sigma), self.std.fit_transform(flat, out=out)))
         return sg
 
     def run_corpus(self, batches, n_local: int, out_dtype=torch.float32):
@@ -275,8 +275,7 @@ class NoisyFeaturePipeline:
         if done != n_local:
             raise ValueError(f"the batches held {done} clips, expected {n_local}")
         flat = feats.view(n_local, self.D)
-        self.std.fit([flat], n_total=None if self.distributed else n_local)
-        return self.std.transform(flat, out_dtype=out_dtype)
+        return self.std.fit_transform(flat, out_dtype=out_dtype)
 
     def run_host(self, audio_host: torch.Tensor, snr_db: Optional[float], seed: int, out_host: torch.Tensor,
                  first_index: int = 0, layout: Optional[ClipBatch] = None, noise_kind: str = "white") -> torch.Tensor:

@@ -44,6 +44,27 @@ def standardize_dataset(train_data, val_data, test_data, group=None, distributed
     return tuple(st.transform(b).cpu().numpy() for b in blocks)
 
 
+def standardize_dataset_with_noisy_test(train_data, val_data, test_data, sigma=0, p=0, alpha=0, group=None, distributed=False):
+    """The MFCC-domain black-box sweep step in one pass (reference :433-491): ``add_white_noise_on_dataset(test, sigma)``
+    (or ``add_noise_mixture_on_dataset(test, p, alpha)``) followed by ``standardize_dataset(train, val, noisy_test)``.
+    The noise is drawn from numpy's global RNG in the reference's order and mixed inside the statistics and apply kernels
+    (float64, two roundings): the noisy test matrix is never written.  Returns the three standardised arrays."""
+    from ..frontend import Noise
+    blocks = [torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda() for a in (train_data, val_data, test_data)]
+    n, d = blocks[2].shape
+    noise = None
+    if sigma != 0:
+        z = torch.from_numpy(np.random.standard_normal((n, d))).cuda()
+        noise = Noise.rows_white(z, float(sigma))
+    elif p != 0 and alpha != 0:
+        qg = np.random.standard_normal((n, 2, d))
+        noise = Noise.rows_mixture(torch.from_numpy(np.ascontiguousarray(qg[:, 0])).cuda(),
+                                   torch.from_numpy(np.ascontiguousarray(qg[:, 1])).cuda(), p, alpha)
+    noises = [None, None, noise]
+    st = Standardizer(d, group=group, distributed=distributed).fit(blocks, noises=noises)
+    return tuple(st.transform(b, noise=nz).cpu().numpy() for b, nz in zip(blocks, noises))
+
+
 def _f64_host(x):
     return np.ascontiguousarray(np.asarray(x), dtype=np.float64)
 

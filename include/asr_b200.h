@@ -216,13 +216,14 @@ int asr_mix_white(const void* audio_dev, int32_t dtype, const int64_t* offsets_d
 
 /* Babble noise of BASELINE configs[1] ("white/babble").  The reference has NO babble implementation (parity unpinned);
  * the recipe is SURVEY.md 8(d): babble[b][n] = sum over k = 1..talkers of clip (b + k*stride) mod n_clips at sample n
- * (float64, exact), power[b] = mean(babble[b]^2) in float64 (fixed order).  The mix is the white-noise formula with
+ * (float64, exact), power[b] = mean(babble[b]^2) in float64 (fixed order: per 2048-sample chunk, chunks ascending).  The mix is the white-noise formula with
  * z := babble and sigma[b] := sigma_snr[b] / sqrt(power[b]) (host), i.e. asr_mix_white / the fused launch take the
  * stream unchanged: noise power = P / 10^(snr/10) by the same sigma law as VDR/attacks.py:233-241.
  * babble_dev is packed like the audio (float64), power_dev is float64 [n_clips]. */
+size_t asr_babble_workspace_bytes(int32_t n_clips, int32_t max_length);   /* scratch, ZEROED once by the caller */
 int asr_babble_stream(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
-                      int32_t n_clips, int32_t stride, int32_t talkers, double* babble_dev, double* power_dev,
-                      void* stream);
+                      int32_t n_clips, int32_t max_length, int32_t stride, int32_t talkers, double* babble_dev,
+                      double* power_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* out = float64(x) + (|q|<p ? sigma1 : sigma0)*g - VDR/attacks.py:159-181 */
 int asr_mix_mixture(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
@@ -256,6 +257,36 @@ int asr_cmvn_finalize(const double* acc2_dev, const double* mean_dev, int64_t n_
 /* out[r][c] = (x[r][c]-mean[c])/scale[c] ; out dtype ASR_F32 or ASR_F64, leading dimension n_cols */
 int asr_cmvn_apply(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld,
                    const double* mean_dev, const double* scale_dev, void* out_dev, int32_t out_dtype, void* stream);
+
+/* ---- standardisation, fused form: the same two passes and summation order in 3 launches on one GPU and with ONE
+ * exchange when the rows are sharded (standardize_dataset, VDR/attacks.py:48-69; with row noise: the MFCC-domain attacks
+ * add_white_noise_on_dataset / add_noise_mixture_on_dataset of :186-219 followed by standardize_dataset, :433-491).
+ *   asr_cmvn_partial_sums   pass 1 (column sums) or pass 2 (sums of x-m and (x-m)^2 about the LOCAL mean m, which every CTA
+ *                           finishes from the pass-1 partials) of one row block into slab partials of the workspace; returns
+ *                           the number of slabs written (>= 0) or a negative asr_status.  `slab_base` = slabs the earlier
+ *                           blocks of this pass wrote (train / dev / test are three blocks), `n_local_rows` = rows of ALL blocks
+ *                           of this rank, `n_slabs_pass1` = total slabs of pass 1 (pass 2 only).
+ *   asr_cmvn_local_message  this rank's message [n, S (D), C (D), Q (D)] (3*n_cols + 1 float64).
+ *   <exchange>              the one collective of the path: an all-gather of the messages (NCCL / peer memory; the caller's).
+ *   asr_cmvn_merge          messages of all ranks in rank order -> mean / var / scale of the whole dataset (Chan's update
+ *                           of the centred sums to the global mean; with one rank the identity), identical on every rank.
+ *   asr_cmvn_apply2         out = (x [+ noise] - mean) / scale.  workspace_dev != NULL (single rank): mean / var / scale are
+ *                           FINISHED inside this launch from the slab partials (no local_message / merge launch) and stored.
+ * `row_noise` (NULL = none): asr_noise with mode WHITE (z_dev = z, sigma0 = sigma: x + sigma*z) or MIXTURE (z_dev = q,
+ * z2_dev = g, p, sigma0, sigma1); the streams are contiguous [n_rows][n_cols] float64; two roundings, no FMA.
+ * The workspace (asr_cmvn_workspace_bytes(n_cols) bytes, 8-byte aligned) belongs to the caller. */
+size_t asr_cmvn_workspace_bytes(int32_t n_cols);
+int32_t asr_cmvn_partial_sums(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld,
+                              const asr_noise* row_noise, int32_t pass, int32_t n_slabs_pass1, int64_t n_local_rows,
+                              int32_t slab_base, void* workspace_dev, size_t workspace_bytes, void* stream);
+int asr_cmvn_local_message(const void* workspace_dev, size_t workspace_bytes, int32_t n_slabs_pass1, int32_t n_slabs_pass2,
+                           int64_t n_local_rows, int32_t n_cols, double* msg_dev, void* stream);
+int asr_cmvn_merge(const double* msgs_dev, int32_t world, int32_t n_cols, double* mean_dev, double* var_dev,
+                   double* scale_dev, double* n_total_dev /* may be NULL */, void* stream);
+int asr_cmvn_apply2(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld, const asr_noise* row_noise,
+                    const void* workspace_dev, size_t workspace_bytes, int32_t n_slabs_pass1, int32_t n_slabs_pass2,
+                    int64_t n_total_rows, double* mean_dev, double* var_dev, double* scale_dev, void* out_dev,
+                    int32_t out_dtype, void* stream);
 
 /* ---- audio ingest: the resampling step of librosa.load (VDR/extract...py:27, SR/extract...py:210) ----
  * librosa resamples every file to 22 050 Hz with resampy's `kaiser_best` table, which is not available; the

@@ -66,7 +66,7 @@ def main():
             done += batch.n_clips
         flat = feats.view(n_local, pipe.D)
         t1.record()
-        pipe.std.fit([flat], n_total=args.clips)
+        pipe.std.fit([flat])
         out = pipe.std.transform(flat)
         t2.record()
         torch.cuda.synchronize()

@@ -29,7 +29,7 @@ def lib():
 def test_header_declares_the_expected_surface():
     names = declared_functions()
     for must in ("asr_plan_create", "asr_plan_destroy", "asr_mfcc_batch", "asr_mfcc_batch_host", "asr_clip_power",
-                 "asr_snr_sigma", "asr_snr_sigma_host", "asr_babble_stream", "asr_plan_set_stage_probe", "asr_tc_selftest", "asr_plan_debug_word", "asr_fp32_peak_probe", "asr_mix_white", "asr_mix_mixture", "asr_randn_f64", "asr_cmvn_colsum",
+                 "asr_snr_sigma", "asr_snr_sigma_host", "asr_babble_stream", "asr_babble_workspace_bytes", "asr_plan_set_stage_probe", "asr_tc_selftest", "asr_cmvn_workspace_bytes", "asr_cmvn_partial_sums", "asr_cmvn_local_message", "asr_cmvn_merge", "asr_cmvn_apply2", "asr_plan_debug_word", "asr_fp32_peak_probe", "asr_mix_white", "asr_mix_mixture", "asr_randn_f64", "asr_cmvn_colsum",
                  "asr_cmvn_colsum_centered", "asr_cmvn_finalize", "asr_cmvn_apply", "asr_last_error", "asr_version"):
         assert must in names
     assert len(names) >= 24

@@ -53,3 +53,54 @@ def test_idempotence_full_size():
     st2 = A.Standardizer(880).fit([Y])
     assert st2.mean.abs().max().item() < 1e-12
     assert (st2.var - 1).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("kind", ["white", "mixture"])
+def test_noisy_test_rows_fused_into_standardisation(kind):
+    """VDR/attacks.py:433-491: MFCC-domain noise on the test rows, then standardize_dataset over train + dev + noisy test.
+    The fused form (noise mixed inside the statistics and apply kernels) equals the reference's two steps."""
+    from asr_b200.voice_digit import attacks
+    from oracle import noise_ref as nr, cmvn_ref as cr
+    rng = np.random.default_rng(4)
+    train, val, test = (rng.standard_normal((n, 880)) * 5 + 2 for n in (700, 200, 100))
+    if kind == "white":
+        np.random.seed(77)
+        noisy = np.stack([nr.add_white_noise(r, 0.5) for r in test])
+        np.random.seed(77)
+        got = attacks.standardize_dataset_with_noisy_test(train, val, test, sigma=0.5)
+    else:
+        np.random.seed(78)
+        noisy = np.stack([nr.add_noise(r, 0.01, 0.3) for r in test])
+        np.random.seed(78)
+        got = attacks.standardize_dataset_with_noisy_test(train, val, test, p=0.01, alpha=0.3)
+    want = cr.standardize_dataset(train, val, noisy)
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g, w, rtol=1e-9, atol=1e-9)
+
+
+def test_fused_single_gpu_form_equals_block_form():
+    """fit_transform (3 launches, statistics finished inside the apply launch) == fit + transform; also the merge of
+    several ranks' messages (emulated on one GPU: shards fitted separately, messages stacked) == the single-rank fit."""
+    import asr_b200 as A
+    from asr_b200._lib import lib, check
+    X = torch.randn(5000, 1313, dtype=torch.float32, device="cuda") * 3 + 1
+    a = A.Standardizer(1313)
+    ya = a.fit_transform(X, out_dtype=torch.float32)
+    b = A.Standardizer(1313).fit([X])
+    yb = b.transform(X, out_dtype=torch.float32)
+    assert torch.equal(a.mean, b.mean) and torch.equal(a.var, b.var) and torch.equal(a.scale, b.scale) and torch.equal(ya, yb)
+    assert b.n_total == 5000 and a.n_total == 5000
+    msgs = []
+    for lo, hi in ((0, 1250), (1250, 2500), (2500, 3750), (3750, 5000)):
+        s = A.Standardizer(1313)
+        s.local_stats([X[lo:hi]]); s.local_message()
+        msgs.append(s.msg.clone())
+    m = A.Standardizer(1313)
+    m.msgs = torch.stack(msgs)
+    m.merge()
+    torch.cuda.synchronize()
+    assert m.n_total == 5000
+    np.testing.assert_allclose(m.mean.cpu().numpy(), b.mean.cpu().numpy(), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(m.var.cpu().numpy(), b.var.cpu().numpy(), rtol=1e-11, atol=1e-13)
+    ym = m.transform(X, out_dtype=torch.float64)
+    np.testing.assert_allclose(ym.cpu().numpy(), b.transform(X).cpu().numpy(), rtol=1e-9, atol=1e-9)

@@ -1,9 +1,9 @@
 """world_size-2 `gloo` test (CPU) of the multi-GPU host protocol of the standardisation.
 
-The product's ``Standardizer.fit`` is: local pass 1 -> all-reduce [sum x, n] -> local pass 2 ->
-all-reduce [sum (x-mean), sum (x-mean)^2] -> finish.  The local passes are CUDA kernels; here they are
-replaced by a numpy TEST DOUBLE with the same accumulator contract (defined in this file, not in the
-product) so the protocol - accumulator layout, row counts, the two collectives, clip sharding by index -
+The product's ``Standardizer.fit`` is: local passes 1 and 2 (about the LOCAL mean) -> this rank's message
+``[n, S, C, Q]`` -> ONE all-gather -> merge in rank order (Chan's update to the global mean).  The local passes and the
+merge are CUDA kernels; here they are replaced by a numpy TEST DOUBLE with the same message contract (defined in this
+file, not in the product) so the protocol - message layout, row counts, the single collective, clip sharding by index -
 runs over a real 2-rank process group and is compared with the oracle on the full dataset.
 """
 import os
@@ -21,39 +21,48 @@ from oracle import cmvn_ref as cr
 
 
 class _NumpyLocalPasses(Standardizer):
-    """Test double: the three local launch groups in numpy (float64), same accumulator layout as the kernels."""
+    """Test double: the launch groups in numpy (float64), same message layout and merge formulas as the kernels."""
 
-    def pass1_local(self, blocks):
+    def local_stats(self, blocks, noises=None):
+        self._blocks = [b.numpy() for b in blocks]
+        self._n_local = sum(b.shape[0] for b in self._blocks)
+
+    def local_message(self):
         D = self.n_cols
-        self.acc1.zero_()
-        rows = 0
-        for x in blocks:
-            self.acc1[:D] += torch.from_numpy(x.numpy().sum(axis=0))
-            rows += x.shape[0]
-        self.acc1[D] = float(rows)
+        x = np.concatenate(self._blocks, axis=0) if self._blocks else np.zeros((0, D))
+        n = x.shape[0]
+        S = x.sum(axis=0)
+        m = S / max(n, 1)
+        c = x - m
+        self.msg[0] = float(n)
+        self.msg[1:1 + D] = torch.from_numpy(S)
+        self.msg[1 + D:1 + 2 * D] = torch.from_numpy(c.sum(axis=0))
+        self.msg[1 + 2 * D:] = torch.from_numpy((c * c).sum(axis=0))
 
-    def pass2_local(self, blocks, n_total):
+    def merge(self):
         D = self.n_cols
-        self.n_total = int(n_total)
-        self.mean.copy_(self.acc1[:D] / self.n_total)
-        self.acc2.zero_()
-        m = self.mean.numpy()
-        for x in blocks:
-            c = x.numpy() - m
-            self.acc2[:D] += torch.from_numpy(c.sum(axis=0))
-            self.acc2[D:] += torch.from_numpy((c * c).sum(axis=0))
-
-    def finish(self):
-        D, n = self.n_cols, self.n_total
-        var = self.acc2[D:] / n - (self.acc2[:D] / n) ** 2
-        self.var.copy_(var)
-        scale = torch.sqrt(var)
+        M = self.msgs.numpy()
+        n = M[:, 0].sum()
+        mu = M[:, 1:1 + D].sum(axis=0) / n
+        corr = np.zeros(D)
+        ssq = np.zeros(D)
+        for r in range(M.shape[0]):
+            nr = M[r, 0]
+            if nr <= 0:
+                continue
+            d = M[r, 1:1 + D] / nr - mu
+            C, Q = M[r, 1 + D:1 + 2 * D], M[r, 1 + 2 * D:]
+            corr += C + nr * d
+            ssq += Q + 2 * d * C + nr * d * d
+        var = (ssq - corr * corr / n) / n
         eps = np.finfo(np.float64).eps
-        constant = var <= n * eps * var + (n * self.mean * eps) ** 2      # sklearn _is_constant_feature
-        scale[constant] = 1.0
-        self.scale.copy_(scale)
+        scale = np.sqrt(var)
+        scale[var <= n * eps * var + (n * mu * eps) ** 2] = 1.0          # sklearn _is_constant_feature
+        self.mean.copy_(torch.from_numpy(mu)); self.var.copy_(torch.from_numpy(var)); self.scale.copy_(torch.from_numpy(scale))
+        self.n_dev[0] = n
+        self._n_total = None
 
-    def transform(self, x, out_dtype=torch.float64, out=None):
+    def transform(self, x, out_dtype=torch.float64, out=None, noise=None):
         return ((x - self.mean) / self.scale).to(out_dtype)
 
 
@@ -68,7 +77,7 @@ def _worker(rank, world, port, n_rows, n_cols, q):
         lo, hi = sharding.shard_bounds(n_rows, rank, world)
         mine = torch.from_numpy(full[lo:hi].copy())
         st = _NumpyLocalPasses(n_cols, device="cpu", distributed=True)
-        st.fit([mine])                                          # n_total comes from the all-reduced count
+        st.fit([mine])                                          # n_total comes from the gathered messages
         out = st.transform(mine)
         q.put((rank, lo, hi, st.n_total, st.mean.numpy().copy(), st.var.numpy().copy(), st.scale.numpy().copy(),
                out.numpy().copy()))

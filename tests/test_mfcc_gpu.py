@@ -294,3 +294,31 @@ def test_unaligned_packing(noisy):
         x = nr.add_white_noise_z(c, sig[i], z) if noisy else c
         r = lr.mfcc(np.asarray(x), lr.C1)
         _close(out[i:i + 1, :, :r.shape[1]].cpu().numpy(), r[None], atol=3e-3)
+
+
+@pytest.mark.parametrize("variant", ["mfcc", "logmel", "no_delta"])
+def test_c5_full_length_cluster_path(variant):
+    """BASELINE configs[4] at its stated size: 10 s clips (160 000 samples, 1001 frames x 80 mel = 320 KB of log-mel rows,
+    more than one SM holds) - the per-clip kernel spreads a clip over a thread-block cluster (clip maximum and delta halo
+    through distributed shared memory).  Plus one shorter clip in the same batch (ragged: its cluster has idle CTAs)."""
+    import asr_b200 as A
+    lr = _o()
+    clips = synth_clips(3, 160000, 16000, 55, lengths=[160000, 160000, 47111])
+    P = A.C5 if variant != "no_delta" else A.C5.replace(delta_orders=0)
+    Pr = lr.C5 if variant != "no_delta" else lr.C5.replace(delta_orders=0)
+    plan = A.MfccPlan(P, path=PATH)
+    batch = A.ClipBatch.from_arrays(clips)
+    T = P.num_frames(160000)
+    assert T == 1001
+    if variant == "logmel":
+        out, status = plan.logmel(batch, out_frames=T)
+    else:
+        out, status = plan.mfcc(batch, out_frames=T)
+    torch.cuda.synchronize()
+    assert int(status.max()) == 0
+    for i, c in enumerate(clips):
+        x = to_f32([c])[0]
+        ref = lr.log_mel(x, Pr) if variant == "logmel" else lr.mfcc(x, Pr)
+        t = ref.shape[1]
+        _close(out[i, :, :t].cpu().numpy(), ref)
+        assert (out[i, :, t:] == 0).all()
