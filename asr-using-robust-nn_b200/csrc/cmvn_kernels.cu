@@ -185,25 +185,36 @@ struct RowNoise {
   double p, s0, s1;     // white: s0 = sigma
 };
 
-template <int DT>
+template <int DT, bool NOISE>   // NOISE is a template parameter so that the batched loads of the clean form are not separated by a branch
 __device__ __forceinline__ double load_xn(const void* __restrict__ x, const long long r, const int c, const long long ld,
                                           const int n_cols, const RowNoise& nz) {
   const double v = load_x<DT>(x, r * ld + c);
-  if (nz.g == nullptr) return v;
+  if constexpr (!NOISE) return v;
   const long long i = r * n_cols + c;
   const double sel = (nz.q != nullptr && fabs(__ldg(nz.q + i)) < nz.p) ? nz.s1 : nz.s0;
   return __dadd_rn(v, __dmul_rn(sel, __ldg(nz.g + i)));
 }
 
-// fixed-order sum over the slabs of a partial table [n_slabs][rows_per][n_cols] at row `j`
+// fixed-order sum over the slabs of a partial table [n_slabs][rows_per][n_cols] at row `j` (loads eight at a time in
+// flight, added in ascending slab order)
 __device__ __forceinline__ double slab_sum(const double* __restrict__ part, const int n_slabs, const int rows_per, const int j,
                                            const int n_cols, const int c) {
   double t = 0.0;
-  for (int s = 0; s < n_slabs; ++s) t = __dadd_rn(t, __ldcg(part + (static_cast<long long>(s) * rows_per + j) * n_cols + c));
+  const long long step = static_cast<long long>(rows_per) * n_cols;
+  const double* p = part + static_cast<long long>(j) * n_cols + c;
+  int s = 0;
+  for (; s + 8 <= n_slabs; s += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (s + u) * step);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t = __dadd_rn(t, v[u]);
+  }
+  for (; s < n_slabs; ++s) t = __dadd_rn(t, __ldcg(p + s * step));
   return t;
 }
 
-template <bool CENTERED, int DT>
+template <bool CENTERED, int DT, bool NOISE>
 __global__ void __launch_bounds__(kColTile * kRowLanes) colsum2_kernel(
     const void* __restrict__ x, const long long n_rows, const int n_cols, const long long ld, const RowNoise nz,
     const double* __restrict__ part1, const int n_slabs1, const double n_local, const long long rows_per_slab,
@@ -214,13 +225,18 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) colsum2_kernel(
   const long long r0 = blockIdx.y * rows_per_slab;
   const long long r1 = min(n_rows, r0 + rows_per_slab);
   double a0 = 0.0, a1 = 0.0;
+  if (CENTERED) {
+    if (rl == 0 && c < n_cols) s0[0][lane] = __ddiv_rn(slab_sum(part1, n_slabs1, 1, 0, n_cols, c), n_local);
+    __syncthreads();
+  }
+  const double m = CENTERED ? s0[0][lane] : 0.0;
+  if (CENTERED) __syncthreads();                          // s0 is reused for the partial sums below
   if (c < n_cols) {
-    const double m = CENTERED ? __ddiv_rn(slab_sum(part1, n_slabs1, 1, 0, n_cols, c), n_local) : 0.0;
     long long r = r0 + rl;
     for (; r + 7 * kRowLanes < r1; r += 8 * kRowLanes) {
       double v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = load_xn<DT>(x, r + u * kRowLanes, c, ld, n_cols, nz);
+      for (int u = 0; u < 8; ++u) v[u] = load_xn<DT, NOISE>(x, r + u * kRowLanes, c, ld, n_cols, nz);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         if (CENTERED) {
@@ -233,7 +249,7 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) colsum2_kernel(
       }
     }
     for (; r < r1; r += kRowLanes) {
-      const double v = load_xn<DT>(x, r, c, ld, n_cols, nz);
+      const double v = load_xn<DT, NOISE>(x, r, c, ld, n_cols, nz);
       if (CENTERED) {
         const double t = __dsub_rn(v, m);
         a0 = __dadd_rn(a0, t);
@@ -311,7 +327,7 @@ __global__ void merge_kernel(const double* __restrict__ msgs, const int world, c
 }
 
 // out = (x [+ noise] - mean) / scale.  FUSED (single rank): mean / scale are finished here from the slab partials.
-template <int DT, bool FUSED>
+template <int DT, bool FUSED, bool NOISE>
 __global__ void __launch_bounds__(kColTile * kRowLanes) apply2_kernel(
     const void* __restrict__ x, const long long n_rows, const int n_cols, const long long ld, const RowNoise nz,
     const double* __restrict__ part1, const int n_slabs1, const double* __restrict__ part2, const int n_slabs2, const double n_total,
@@ -321,11 +337,14 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) apply2_kernel(
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * kColTile + lane;
   if (FUSED) {
+    __shared__ double s_t[3][kColTile];
+    if (rl < 3 && c < n_cols)                             // the three slab reductions side by side
+      s_t[rl][lane] = rl == 0 ? slab_sum(part1, n_slabs1, 1, 0, n_cols, c) : slab_sum(part2, n_slabs2, 2, rl - 1, n_cols, c);
+    __syncthreads();
     if (rl == 0 && c < n_cols) {
-      const double mu = __ddiv_rn(slab_sum(part1, n_slabs1, 1, 0, n_cols, c), n_total);
-      const double corr = slab_sum(part2, n_slabs2, 2, 0, n_cols, c), ssq = slab_sum(part2, n_slabs2, 2, 1, n_cols, c);
+      const double mu = __ddiv_rn(s_t[0][lane], n_total);
       double v, sc;
-      finish_stats(corr, ssq, n_total, mu, v, sc);
+      finish_stats(s_t[1][lane], s_t[2][lane], n_total, mu, v, sc);
       s_m[lane] = mu; s_s[lane] = sc;
       if (blockIdx.y == 0) { mean[c] = mu; var[c] = v; scale[c] = sc; }
     }
@@ -339,7 +358,7 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) apply2_kernel(
   for (; r + 3 * kRowLanes < r1; r += 4 * kRowLanes) {
     double v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = load_xn<DT>(x, r + u * kRowLanes, c, ld, n_cols, nz);
+    for (int u = 0; u < 4; ++u) v[u] = load_xn<DT, NOISE>(x, r + u * kRowLanes, c, ld, n_cols, nz);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const double y = __ddiv_rn(__dsub_rn(v[u], m), sc);
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) apply2_kernel(
     }
   }
   for (; r < r1; r += kRowLanes) {
-    const double y = __ddiv_rn(__dsub_rn(load_xn<DT>(x, r, c, ld, n_cols, nz), m), sc);
+    const double y = __ddiv_rn(__dsub_rn(load_xn<DT, NOISE>(x, r, c, ld, n_cols, nz), m), sc);
     if (out_f64) reinterpret_cast<double*>(out)[r * n_cols + c] = y;
     else reinterpret_cast<float*>(out)[r * n_cols + c] = static_cast<float>(y);
   }
@@ -489,13 +508,16 @@ extern "C" int32_t asr_cmvn_partial_sums(const void* x_dev, int32_t dtype, int64
   const dim3 grid((n_cols + kColTile - 1) / kColTile, static_cast<unsigned>(slabs));
   cudaStream_t st = as_stream(stream);
   const double nl = static_cast<double>(n_local_rows);
+  const bool noisy = nz.g != nullptr;
+#define ASR_COLSUM2(C, DT, N) colsum2_kernel<C, DT, N><<<grid, kColTile * kRowLanes, 0, st>>>(x_dev, n_rows, n_cols, ld, nz, part1, n_slabs_pass1, nl, rps, (C) ? part2 : part1, slab_base)
   if (pass == 1) {
-    if (dtype == ASR_F32) colsum2_kernel<false, ASR_F32><<<grid, kColTile * kRowLanes, 0, st>>>(x_dev, n_rows, n_cols, ld, nz, nullptr, 0, 1.0, rps, part1, slab_base);
-    else colsum2_kernel<false, ASR_F64><<<grid, kColTile * kRowLanes, 0, st>>>(x_dev, n_rows, n_cols, ld, nz, nullptr, 0, 1.0, rps, part1, slab_base);
+    if (dtype == ASR_F32) { if (noisy) ASR_COLSUM2(false, ASR_F32, true); else ASR_COLSUM2(false, ASR_F32, false); }
+    else { if (noisy) ASR_COLSUM2(false, ASR_F64, true); else ASR_COLSUM2(false, ASR_F64, false); }
   } else {
-    if (dtype == ASR_F32) colsum2_kernel<true, ASR_F32><<<grid, kColTile * kRowLanes, 0, st>>>(x_dev, n_rows, n_cols, ld, nz, part1, n_slabs_pass1, nl, rps, part2, slab_base);
-    else colsum2_kernel<true, ASR_F64><<<grid, kColTile * kRowLanes, 0, st>>>(x_dev, n_rows, n_cols, ld, nz, part1, n_slabs_pass1, nl, rps, part2, slab_base);
+    if (dtype == ASR_F32) { if (noisy) ASR_COLSUM2(true, ASR_F32, true); else ASR_COLSUM2(true, ASR_F32, false); }
+    else { if (noisy) ASR_COLSUM2(true, ASR_F64, true); else ASR_COLSUM2(true, ASR_F64, false); }
   }
+#undef ASR_COLSUM2
   ASR_CUDA_TRY(cudaGetLastError());
   return static_cast<int32_t>(slabs);
 }
@@ -542,7 +564,7 @@ extern "C" int asr_cmvn_apply2(const void* x_dev, int32_t dtype, int64_t n_rows,
   }
   if (n_rows == 0) return ASR_OK;
   const int col_blocks = (n_cols + kColTile - 1) / kColTile;
-  int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((148 * 16 + col_blocks - 1) / col_blocks, (n_rows + 31) / 32));
+  int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((148 * 8 + col_blocks - 1) / col_blocks, (n_rows + 31) / 32));
   const int64_t rps = (n_rows + slabs - 1) / slabs;
   slabs = (n_rows + rps - 1) / rps;
   const dim3 grid(col_blocks, static_cast<unsigned>(slabs));
@@ -552,9 +574,12 @@ extern "C" int asr_cmvn_apply2(const void* x_dev, int32_t dtype, int64_t n_rows,
   cudaStream_t st = as_stream(stream);
   const double nt = static_cast<double>(n_total_rows);
   const int f64 = out_dtype == ASR_F64;
-#define ASR_APPLY2(DT, F) apply2_kernel<DT, F><<<grid, kColTile * kRowLanes, 0, st>>>(x_dev, n_rows, n_cols, ld, nz, part1, n_slabs_pass1, part2, n_slabs_pass2, nt, mean_dev, var_dev, scale_dev, out_dev, f64, rps)
-  if (dtype == ASR_F32) { if (fused) ASR_APPLY2(ASR_F32, true); else ASR_APPLY2(ASR_F32, false); }
-  else { if (fused) ASR_APPLY2(ASR_F64, true); else ASR_APPLY2(ASR_F64, false); }
+  const bool noisy = nz.g != nullptr;
+#define ASR_APPLY2(DT, F, N) apply2_kernel<DT, F, N><<<grid, kColTile * kRowLanes, 0, st>>>(x_dev, n_rows, n_cols, ld, nz, part1, n_slabs_pass1, part2, n_slabs_pass2, nt, mean_dev, var_dev, scale_dev, out_dev, f64, rps)
+#define ASR_APPLY2_N(DT, F) do { if (noisy) ASR_APPLY2(DT, F, true); else ASR_APPLY2(DT, F, false); } while (0)
+  if (dtype == ASR_F32) { if (fused) ASR_APPLY2_N(ASR_F32, true); else ASR_APPLY2_N(ASR_F32, false); }
+  else { if (fused) ASR_APPLY2_N(ASR_F64, true); else ASR_APPLY2_N(ASR_F64, false); }
+#undef ASR_APPLY2_N
 #undef ASR_APPLY2
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;

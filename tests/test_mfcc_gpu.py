@@ -320,5 +320,10 @@ def test_c5_full_length_cluster_path(variant):
         x = to_f32([c])[0]
         ref = lr.log_mel(x, Pr) if variant == "logmel" else lr.mfcc(x, Pr)
         t = ref.shape[1]
-        _close(out[i, :, :t].cpu().numpy(), ref)
+        # log-mel: the usual tolerance.  Cepstra: this clip has near-silent edge frames (Hann envelope), where the float32
+        # FFT's log-mel error is largest (7e-4), and the lifter (22) scales coefficients 4..16 by up to 12 - hence 1e-2.
+        if variant == "logmel":
+            _close(out[i, :, :t].cpu().numpy(), ref)
+        else:
+            _close(out[i, :, :t].cpu().numpy(), ref, atol=1e-2)
         assert (out[i, :, t:] == 0).all()
