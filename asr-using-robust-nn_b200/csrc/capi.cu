@@ -114,6 +114,36 @@ static bool savgol_taps(int width, int order, double* taps) {
 }
 
 
+// ---- cepstra tables (cepstra_*_kernel, shared by every path that goes through the log-mel workspace) ----
+// DCT (lifter folded in) transposed to [lm_pitch][4*NC4] (zero rows / columns as padding), then the delta taps.
+static bool build_cepstra_tables(asr_plan* pl) {
+  const asr_mfcc_params& p = pl->prm;
+  const int n_mels = p.n_mels;
+  pl->fr_lm_pitch = round4(n_mels);
+  if (p.n_mfcc > 40) return true;
+  const int nc4 = (p.n_mfcc + 3) / 4;
+  std::vector<float> blob;
+  auto put_f = [&](const float* src, size_t n) {
+    const int off = static_cast<int>(blob.size());
+    blob.insert(blob.end(), src, src + n);
+    blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
+    return off;
+  };
+  std::vector<float> dct_t(static_cast<size_t>(pl->fr_lm_pitch) * 4 * nc4, 0.0f);
+  for (int c = 0; c < p.n_mfcc; ++c)
+    for (int j = 0; j < n_mels; ++j) dct_t[static_cast<size_t>(j) * 4 * nc4 + c] = pl->h_dct[static_cast<size_t>(c) * n_mels + j];
+  pl->h_dct_t = dct_t;
+  const int dct_off = put_f(dct_t.data(), dct_t.size());
+  const int taps_off = put_f(pl->h_taps.data(), pl->h_taps.size());
+  pl->cep_tab_f4 = static_cast<int>(blob.size() / 4);
+  pl->cep_off_taps = taps_off - dct_off;
+  pl->cep_off_cbuf = 4 * pl->cep_tab_f4;
+  pl->cep_smem_bytes = 4 * (pl->cep_off_cbuf + (p.delta_orders > 0 ? p.n_mfcc * 129 : 0));
+  if (cudaMalloc(reinterpret_cast<void**>(&pl->cep_dev), blob.size() * sizeof(float)) != cudaSuccess) return false;
+  if (cudaMemcpy(pl->cep_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  return true;
+}
+
 // ---- tables of the block-pipelined path (frames_kernel.cu), n_fft = 512 ------------------------------
 // Mel bank in "segment" form: the Slaney triangles overlap only their neighbours, so a bin between the
 // peaks of filters seg-1 and seg feeds the falling slope of seg-1 and the rising slope of seg.  Bins are
@@ -356,44 +386,24 @@ static bool build_tile_tables_all(asr_plan* pl, const std::vector<double>& mel_f
   return true;
 }
 
-// ---- tables of the tensor-core path (tc_kernel.cu), n_fft = 512, int16 audio ---------------------------------
-// Pass 1 of the 16 x 16 decomposition of the 256-point complex FFT behind the real 512-point FFT, per residue b:
-//   Y_b[c] = W256^(b c) * sum_a W16^(a c) * (w[2n] x[2n] + i w[2n+1] x[2n+1]),  n = b + 16 a
-// as a real 32 x 32 matrix M_b (rows 2c + re/im, columns 2a + even/odd sample) in float64, stored as float16 pairs:
-// 16 M = MH1 + MH2 (value + residual); see the head of tc_kernel.cu for the operand split they multiply.
-// The mel bank in segment form (as for the tiles path), dealt out to the 4 warps of a TMEM lane quarter; a filter whose
-// terms all lie in one share is finished in registers ("direct"), the others go through boundary slots.
-static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, const std::vector<double>& fftfreqs) {
+// Mel bank for the lanes <-> frames mel stage of the tensor-core kernels (tc_kernel.cu, tcdft_kernel.cu): segment form
+// (a bin between the peaks of filters s-1 and s feeds the falling slope of s-1 and the rising slope of s), steps of 4 bins,
+// dealt out to the 4 warps of a TMEM lane quarter; a filter whose terms all lie in one share is finished in registers
+// ("direct"), the others go through boundary slots.  `scale` undoes the scaling of the power spectrum in TMEM.
+struct LaneMel { float* blob_dev; int blob_f4, off_wtab, off_pieces, off_wrange, off_bnd, n_bnd, n_slots, ok; };
+static bool build_lane_mel(asr_plan* pl, const std::vector<double>& mel_f, const std::vector<double>& fftfreqs, const float scale,
+                           LaneMel* lm) {
   const asr_mfcc_params& p = pl->prm;
-  pl->tc_ok = 0;
-  if (!pl->tl_ok || (p.hop_length % 32) != 0 || p.n_mels > 254) return true;
-  const int n_bins = pl->n_bins, n_mels = p.n_mels, wl = pl->win_length, lpad = (p.n_fft - wl) / 2;
-  auto wind = [&](int i) -> double {            // the float64 window librosa multiplies the frames with
-    const int n = i - lpad;
-    if (n < 0 || n >= wl) return 0.0;
-    const double a0 = p.window == ASR_WIN_HANN ? 0.5 : 0.54, a1 = 1.0 - a0;
-    return wl == 1 ? 1.0 : a0 - a1 * std::cos(2.0 * kPi * n / wl);
-  };
-  std::vector<__half> mats(static_cast<size_t>(16) * 2 * 32 * 32);
-  auto put = [&](int b, int mat, int n, int k, double v) {
-    mats[(((static_cast<size_t>(b) * 2 + mat) * 4 + k / 8) * 32 + n) * 8 + k % 8] = __float2half_rn(static_cast<float>(v));
-  };
-  for (int b = 0; b < 16; ++b)
-    for (int c = 0; c < 16; ++c)
-      for (int a = 0; a < 16; ++a) {
-        const double th = 2.0 * kPi * (b * c / 256.0 + a * c / 16.0);
-        const double tr = std::cos(th), ti = -std::sin(th);
-        const int n = b + 16 * a;
-        const double we = wind(2 * n), wo = wind(2 * n + 1);
-        const double m[2][2] = {{tr * we, -ti * wo}, {ti * we, tr * wo}};      // [re/im of Y][even/odd sample]
-        for (int ri = 0; ri < 2; ++ri)
-          for (int eo = 0; eo < 2; ++eo) {
-            const double mh = 16.0 * m[ri][eo];
-            const __half h1 = __float2half_rn(static_cast<float>(mh));
-            put(b, 0, 2 * c + ri, 2 * a + eo, mh);
-            put(b, 1, 2 * c + ri, 2 * a + eo, mh - static_cast<double>(__half2float(h1)));
-          }
-      }
+  const int n_bins = pl->n_bins, n_mels = p.n_mels;
+  lm->ok = 0; lm->blob_dev = nullptr;
+  if (n_mels > 254) return true;
+  for (int i = 0; i < n_mels; ++i) {                       // neighbour-only check (Slaney triangles overlap their neighbours only)
+    for (int k = 0; k < n_bins; ++k) {
+      int sg = 0;
+      while (sg < n_mels && mel_f[sg + 1] <= fftfreqs[k]) ++sg;
+      if (pl->h_mel_dense[static_cast<size_t>(i) * n_bins + k] != 0.0f && i != sg - 1 && i != sg) return true;
+    }
+  }
   // ---- mel bank: steps (4 bins of one segment), 4 contiguous shares ----
   std::vector<int> seg(n_bins);
   for (int k = 0; k < n_bins; ++k) {
@@ -418,7 +428,6 @@ static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, cons
   std::vector<float> wtab;
   std::vector<int> wrange(2 * 4, 0);
   std::vector<std::vector<int>> contrib(n_mels);            // per filter: indices of the pieces that emit it
-  const float scale = 1.0f / 1073741824.0f;                 // the spectrum in TMEM is 2^30 |X|^2 (exact scaling)
   for (int g = 0; g < 4; ++g) {
     const int a = static_cast<int>(static_cast<long long>(g) * ns / 4), b = static_cast<int>(static_cast<long long>(g + 1) * ns / 4);
     wrange[2 * g] = static_cast<int>(pieces.size());
@@ -457,8 +466,8 @@ static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, cons
     for (int pi : cl) { ptab[4 * pi + 3] = (f + 1) | ((n_slots + 1) << 16); ++n_slots; }
   }
   if (n_slots > 16) return true;
-  pl->tc_n_slots = std::max(1, n_slots);
-  pl->tc_n_bnd = static_cast<int>(bnd.size() / 4);
+  lm->n_slots = std::max(1, n_slots);
+  lm->n_bnd = static_cast<int>(bnd.size() / 4);
   std::vector<float> blob;
   auto put_f = [&](const float* src, size_t n) {
     const int off = static_cast<int>(blob.size());
@@ -473,16 +482,63 @@ static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, cons
     blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
     return off;
   };
-  pl->tc_off_wtab = put_f(wtab.data(), wtab.size());
-  pl->tc_off_pieces = put_i(ptab.data(), ptab.size());
-  pl->tc_off_wrange = put_i(wrange.data(), wrange.size());
+  lm->off_wtab = put_f(wtab.data(), wtab.size());
+  lm->off_pieces = put_i(ptab.data(), ptab.size());
+  lm->off_wrange = put_i(wrange.data(), wrange.size());
   if (bnd.empty()) bnd.assign(4, 0);
-  pl->tc_off_bnd = put_i(bnd.data(), bnd.size());
-  pl->tc_blob_f4 = static_cast<int>(blob.size() / 4);
+  lm->off_bnd = put_i(bnd.data(), bnd.size());
+  lm->blob_f4 = static_cast<int>(blob.size() / 4);
+  if (cudaMalloc(reinterpret_cast<void**>(&lm->blob_dev), blob.size() * sizeof(float)) != cudaSuccess) return false;
+  if (cudaMemcpy(lm->blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  lm->ok = 1;
+  return true;
+}
+
+// ---- tables of the tensor-core path (tc_kernel.cu), n_fft = 512, int16 audio ---------------------------------
+// Pass 1 of the 16 x 16 decomposition of the 256-point complex FFT behind the real 512-point FFT, per residue b:
+//   Y_b[c] = W256^(b c) * sum_a W16^(a c) * (w[2n] x[2n] + i w[2n+1] x[2n+1]),  n = b + 16 a
+// as a real 32 x 32 matrix M_b (rows 2c + re/im, columns 2a + even/odd sample) in float64, stored as float16 pairs:
+// 16 M = MH1 + MH2 (value + residual); see the head of tc_kernel.cu for the operand split they multiply.
+// The mel bank in segment form (as for the tiles path), dealt out to the 4 warps of a TMEM lane quarter; a filter whose
+// terms all lie in one share is finished in registers ("direct"), the others go through boundary slots.
+static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, const std::vector<double>& fftfreqs) {
+  const asr_mfcc_params& p = pl->prm;
+  pl->tc_ok = 0;
+  if (!pl->tl_ok || (p.hop_length % 32) != 0 || p.n_mels > 254) return true;
+  const int n_bins = pl->n_bins, n_mels = p.n_mels, wl = pl->win_length, lpad = (p.n_fft - wl) / 2;
+  auto wind = [&](int i) -> double {            // the float64 window librosa multiplies the frames with
+    const int n = i - lpad;
+    if (n < 0 || n >= wl) return 0.0;
+    const double a0 = p.window == ASR_WIN_HANN ? 0.5 : 0.54, a1 = 1.0 - a0;
+    return wl == 1 ? 1.0 : a0 - a1 * std::cos(2.0 * kPi * n / wl);
+  };
+  std::vector<__half> mats(static_cast<size_t>(16) * 2 * 32 * 32);
+  auto put = [&](int b, int mat, int n, int k, double v) {
+    mats[(((static_cast<size_t>(b) * 2 + mat) * 4 + k / 8) * 32 + n) * 8 + k % 8] = __float2half_rn(static_cast<float>(v));
+  };
+  for (int b = 0; b < 16; ++b)
+    for (int c = 0; c < 16; ++c)
+      for (int a = 0; a < 16; ++a) {
+        const double th = 2.0 * kPi * (b * c / 256.0 + a * c / 16.0);
+        const double tr = std::cos(th), ti = -std::sin(th);
+        const int n = b + 16 * a;
+        const double we = wind(2 * n), wo = wind(2 * n + 1);
+        const double m[2][2] = {{tr * we, -ti * wo}, {ti * we, tr * wo}};      // [re/im of Y][even/odd sample]
+        for (int ri = 0; ri < 2; ++ri)
+          for (int eo = 0; eo < 2; ++eo) {
+            const double mh = 16.0 * m[ri][eo];
+            const __half h1 = __float2half_rn(static_cast<float>(mh));
+            put(b, 0, 2 * c + ri, 2 * a + eo, mh);
+            put(b, 1, 2 * c + ri, 2 * a + eo, mh - static_cast<double>(__half2float(h1)));
+          }
+      }
   if (cudaMalloc(&pl->tc_mats_dev, mats.size() * sizeof(__half)) != cudaSuccess) return false;
   if (cudaMemcpy(pl->tc_mats_dev, mats.data(), mats.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return false;
-  if (cudaMalloc(reinterpret_cast<void**>(&pl->tc_blob_dev), blob.size() * sizeof(float)) != cudaSuccess) return false;
-  if (cudaMemcpy(pl->tc_blob_dev, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  LaneMel lm;
+  if (!build_lane_mel(pl, mel_f, fftfreqs, 1.0f / 1073741824.0f, &lm)) return false;   // the spectrum in TMEM is 2^30 |X|^2 (exact scaling)
+  if (!lm.ok) return true;
+  pl->tc_blob_dev = lm.blob_dev; pl->tc_blob_f4 = lm.blob_f4; pl->tc_off_wtab = lm.off_wtab; pl->tc_off_pieces = lm.off_pieces;
+  pl->tc_off_wrange = lm.off_wrange; pl->tc_off_bnd = lm.off_bnd; pl->tc_n_bnd = lm.n_bnd; pl->tc_n_slots = lm.n_slots;
   if (tc_upload_constants() != cudaSuccess) return false;
   if (cudaHostAlloc(reinterpret_cast<void**>(&pl->tc_dbg_host), 16 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
     std::memset(pl->tc_dbg_host, 0, 16 * sizeof(int));
@@ -492,6 +548,59 @@ static bool build_tc_tables(asr_plan* pl, const std::vector<double>& mel_f, cons
     pl->tc_dbg_host = nullptr; pl->tc_dbg_dev = nullptr;
   }
   pl->tc_ok = 1;
+  return true;
+}
+
+// ---- tables of the tensor-core dense DFT (tcdft_kernel.cu): FFT sizes without a register FFT ----------------
+// B[r][n] = 16 w[n] cos(2 pi k n / n_fft) for r = k < bins, -16 w[n] sin(...) for r = nh + k; zero rows / columns as padding;
+// B = B1 + B2 in float16; per K step of 16 samples one slab [B1 | B2][2 chunks of 8 samples][2 nh rows][8 halves].
+static bool build_dft_tables(asr_plan* pl, const std::vector<double>& mel_f, const std::vector<double>& fftfreqs) {
+  const asr_mfcc_params& p = pl->prm;
+  pl->df_ok = 0;
+  const int n_bins = pl->n_bins, nh = (n_bins + 15) & ~15, ks = (p.n_fft + 15) / 16;
+  if (pl->fft_path || 2 * nh > 512 || nh > 256 || p.preemph != 0.0f || p.n_mfcc > 40) return true;
+  const int wl = pl->win_length, lpad = (p.n_fft - wl) / 2;
+  auto wind = [&](int i) -> double {
+    const int n = i - lpad;
+    if (n < 0 || n >= wl) return 0.0;
+    const double a0 = p.window == ASR_WIN_HANN ? 0.5 : 0.54, a1 = 1.0 - a0;
+    return wl == 1 ? 1.0 : a0 - a1 * std::cos(2.0 * kPi * n / wl);
+  };
+  const size_t slab_halves = static_cast<size_t>(2) * 2 * (2 * nh) * 8;
+  std::vector<__half> mats(slab_halves * ks, __float2half_rn(0.0f));
+  for (int st = 0; st < ks; ++st)
+    for (int k16 = 0; k16 < 16; ++k16) {
+      const int n = 16 * st + k16;
+      if (n >= p.n_fft) continue;
+      const double w = wind(n);
+      for (int k = 0; k < n_bins; ++k) {
+        // exact phase reduction: k n mod n_fft keeps the argument small
+        const double ang = 2.0 * kPi * static_cast<double>((static_cast<long long>(k) * n) % p.n_fft) / p.n_fft;
+        const double v[2] = {16.0 * w * std::cos(ang), -16.0 * w * std::sin(ang)};
+        for (int ri = 0; ri < 2; ++ri) {
+          const int r = ri * nh + k;
+          const __half h1 = __float2half_rn(static_cast<float>(v[ri]));
+          const __half h2 = __float2half_rn(static_cast<float>(v[ri] - static_cast<double>(__half2float(h1))));
+          const size_t base = slab_halves * st + (static_cast<size_t>(k16 / 8) * (2 * nh) + r) * 8 + k16 % 8;
+          mats[base] = h1;
+          mats[base + slab_halves / 2] = h2;
+        }
+      }
+    }
+  LaneMel lm;
+  if (!build_lane_mel(pl, mel_f, fftfreqs, 1.0f / 256.0f, &lm)) return false;      // the spectrum in TMEM is 256 |X|^2
+  if (!lm.ok) return true;
+  pl->df_blob_dev = lm.blob_dev; pl->df_blob_f4 = lm.blob_f4; pl->df_off_wtab = lm.off_wtab; pl->df_off_pieces = lm.off_pieces;
+  pl->df_off_wrange = lm.off_wrange; pl->df_off_bnd = lm.off_bnd; pl->df_n_bnd = lm.n_bnd; pl->df_n_slots = lm.n_slots;
+  if (cudaMalloc(&pl->df_mats_dev, mats.size() * sizeof(__half)) != cudaSuccess) return false;
+  if (cudaMemcpy(pl->df_mats_dev, mats.data(), mats.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  pl->df_nh = nh; pl->df_ksteps = ks; pl->df_bslab = static_cast<int>(slab_halves * sizeof(__half));
+  if (!pl->tc_dbg_host && cudaHostAlloc(reinterpret_cast<void**>(&pl->tc_dbg_host), 16 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    std::memset(pl->tc_dbg_host, 0, 16 * sizeof(int));
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&pl->tc_dbg_dev), pl->tc_dbg_host, 0) != cudaSuccess) pl->tc_dbg_dev = nullptr;
+  }
+  cudaGetLastError();
+  pl->df_ok = 1;
   return true;
 }
 
@@ -725,8 +834,8 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
     cudaDeviceProp prop;
     pl->sm_count = (cudaGetDeviceProperties(&prop, pl->device) == cudaSuccess) ? prop.multiProcessorCount : 148;
   }
-  if (!build_frames_tables(pl, mel_f, fftfreqs, twp, twu) || !build_tile_tables_all(pl, mel_f, fftfreqs, twp, twu) ||
-      !build_tc_tables(pl, mel_f, fftfreqs)) {
+  if (!build_cepstra_tables(pl) || !build_frames_tables(pl, mel_f, fftfreqs, twp, twu) || !build_tile_tables_all(pl, mel_f, fftfreqs, twp, twu) ||
+      !build_tc_tables(pl, mel_f, fftfreqs) || !build_dft_tables(pl, mel_f, fftfreqs)) {
     const cudaError_t e2 = cudaGetLastError();
     asr_plan_destroy(pl);
     return cuda_fail(e2, "asr_plan_create (frames-path tables)");
@@ -742,6 +851,9 @@ extern "C" void asr_plan_destroy(asr_plan* plan) {
   for (int c = 0; c < 2; ++c)
     if (plan->tl[c].blob_dev) cudaFree(plan->tl[c].blob_dev);
   if (plan->ws_dev) cudaFree(plan->ws_dev);
+  if (plan->cep_dev) cudaFree(plan->cep_dev);
+  if (plan->df_mats_dev) cudaFree(plan->df_mats_dev);
+  if (plan->df_blob_dev) cudaFree(plan->df_blob_dev);
   if (plan->tc_mats_dev) cudaFree(plan->tc_mats_dev);
   if (plan->tc_blob_dev) cudaFree(plan->tc_blob_dev);
   if (plan->tc_dbg_host) cudaFreeHost(plan->tc_dbg_host);
@@ -876,6 +988,19 @@ bool tc_path_usable(const asr_plan* plan, int n_clips, int max_length, int dtype
   if (frames >= (1ll << 31) - 256) return false;
   return tc_layout(plan, lo);
 }
+struct DfLayout { int sm_stage, sm_slots, smem_bytes; };
+// tensor-core dense DFT: the TC path of plans without a register FFT (clean input: no fused noise, no pre-emphasis)
+bool tcdft_path_usable(const asr_plan* plan, int n_clips, int max_length, int noise_mode, DfLayout* lo) {
+  if (!plan->df_ok || !(plan->path == ASR_PATH_TC || plan->path == ASR_PATH_AUTO) || noise_mode != ASR_NOISE_NONE) return false;
+  const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
+  if (frames >= (1ll << 31) - 256) return false;
+  long long off = 16LL * plan->df_blob_f4;
+  off = (off + 127) & ~127LL;
+  lo->sm_stage = static_cast<int>(off); off += static_cast<long long>(tcdft_stages()) * (2 * 4096 + plan->df_bslab);
+  lo->sm_slots = static_cast<int>(off); off += 512LL * plan->df_n_slots;
+  lo->smem_bytes = static_cast<int>(off);
+  return off + tcdft_static_smem_bytes() <= kMaxSmemBytes;
+}
 struct WsLayout { size_t off_fstart, off_nframes, off_clipmax, off_lm, bytes; };
 WsLayout ws_layout(const asr_plan* plan, int n_clips, int max_length) {
   WsLayout w;
@@ -912,6 +1037,8 @@ extern "C" size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips
   if (!plan || n_clips <= 0 || max_length < 0) return 0;
   TlLayout tlo;
   TcLayout tcl;
+  DfLayout dfl;
+  if (tcdft_path_usable(plan, n_clips, max_length, ASR_NOISE_NONE, &dfl)) return ws_layout(plan, n_clips, max_length).bytes;
   if (!frames_path_usable(plan, n_clips, max_length, ASR_F64, ASR_NOISE_NONE, false, &lo) &&
       !tiles_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tlo) &&
       !tc_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tcl)) return 0;
@@ -925,6 +1052,8 @@ extern "C" int32_t asr_plan_launches(const asr_plan* plan, int32_t noisy) {
   FrLayout lo;
   TlLayout tlo;
   TcLayout tcl;
+  DfLayout dfl;
+  if (plan && tcdft_path_usable(plan, 1, 0, noisy ? ASR_NOISE_WHITE : ASR_NOISE_NONE, &dfl)) return 3;
   if (plan && tc_path_usable(plan, 1, 0, ASR_I16, noisy ? ASR_NOISE_WHITE : ASR_NOISE_NONE, true, &tcl)) return 3;
   if (plan && tiles_path_usable(plan, 1, 0, ASR_F64, noisy ? ASR_NOISE_WHITE : ASR_NOISE_NONE, true, &tlo)) return 3;
   return (plan && plan->fr_ok && plan->path != ASR_PATH_CLIP && frames_path_wanted(plan, noisy != 0) &&
@@ -936,6 +1065,8 @@ extern "C" int32_t asr_plan_path_used(const asr_plan* plan, int32_t dtype, int32
   FrLayout lo;
   TlLayout tlo;
   TcLayout tcl;
+  DfLayout dfl;
+  if (tcdft_path_usable(plan, 1, 0, noise_mode, &dfl)) return ASR_PATH_TC;
   if (tc_path_usable(plan, 1, 0, dtype, noise_mode, true, &tcl)) return ASR_PATH_TC;
   if (tiles_path_usable(plan, 1, 0, dtype, noise_mode, true, &tlo)) return ASR_PATH_TILES;
   if (frames_path_wanted(plan, noise_mode != ASR_NOISE_NONE) && frames_path_usable(plan, 1, 0, dtype, noise_mode, true, &lo)) return ASR_PATH_FRAMES;
@@ -998,6 +1129,54 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     kp.vec_ok = al16(audio_dev) && (kp.noise_mode == ASR_NOISE_NONE || (al16(kp.z) && (kp.noise_mode != ASR_NOISE_MIXTURE || al16(kp.z2))));
   }
+  // ---- FFT sizes without a register FFT (441): tensor-core dense DFT (frame prefix -> tcdft -> cepstra) ----
+  DfLayout dfl;
+  if (tcdft_path_usable(plan, n_clips, max_length, kp.noise_mode, &dfl)) {
+    const WsLayout wl = ws_layout(plan, n_clips, max_length);
+    char* ws = static_cast<char*>(workspace_dev);
+    if (ws) {
+      if (workspace_bytes < wl.bytes || (reinterpret_cast<uintptr_t>(ws) & 15)) return bad("workspace too small or not 16-byte aligned");
+    } else {
+      asr_plan* mp = const_cast<asr_plan*>(plan);                // plan-owned scratch (documented: no concurrent launches)
+      if (mp->ws_bytes < wl.bytes) {
+        if (mp->ws_dev) ASR_CUDA_TRY(cudaFree(mp->ws_dev));
+        mp->ws_dev = nullptr; mp->ws_bytes = 0;
+        ASR_CUDA_TRY(cudaMalloc(&mp->ws_dev, wl.bytes));
+        mp->ws_bytes = wl.bytes;
+      }
+      ws = static_cast<char*>(mp->ws_dev);
+    }
+    FParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.audio = audio_dev; fp.offsets = kp.offsets; fp.lengths = lengths_dev; fp.dtype = dtype; fp.n_clips = n_clips;
+    fp.noise_mode = ASR_NOISE_NONE;
+    fp.out = out_dev; fp.out_f64 = out_dtype == ASR_F64; fp.out_frames = out_frames;
+    fp.out_rows = p.n_mfcc * (1 + p.delta_orders); fp.logmel_only = logmel_only; fp.status = status_dev;
+    fp.n_fft = p.n_fft; fp.hop = p.hop_length; fp.pad = plan->pad; fp.pad_mode = p.pad_mode;
+    fp.n_mels = p.n_mels; fp.n_mfcc = p.n_mfcc; fp.delta_orders = p.delta_orders; fp.delta_width = p.delta_width;
+    fp.top_db = p.top_db; fp.amin = p.amin; fp.preemph = p.preemph;
+    fp.blob = reinterpret_cast<const float4*>(plan->df_blob_dev); fp.blob_f4 = plan->df_blob_f4;
+    fp.off_wtab = plan->df_off_wtab; fp.off_steps = plan->df_off_pieces; fp.off_wrange = plan->df_off_wrange;
+    fp.tc_off_bnd = plan->df_off_bnd; fp.tc_n_bnd = plan->df_n_bnd;
+    fp.tc_mats = plan->df_mats_dev; fp.tc_dbg = plan->tc_dbg_dev;
+    fp.df_sm_stage = dfl.sm_stage; fp.tc_sm_slots = dfl.sm_slots;
+    fp.df_nh = plan->df_nh; fp.df_ksteps = plan->df_ksteps; fp.df_bslab = plan->df_bslab;
+    fp.fstart = reinterpret_cast<int*>(ws + wl.off_fstart);
+    fp.nframes = reinterpret_cast<int*>(ws + wl.off_nframes);
+    fp.clipmax = reinterpret_cast<float*>(ws + wl.off_clipmax);
+    fp.lm = reinterpret_cast<float*>(ws + wl.off_lm);
+    const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
+    fp.lm_stride = static_cast<int>((frames + 31) & ~31LL);
+    fp.cep_blob = reinterpret_cast<const float4*>(plan->cep_dev);
+    fp.cep_tab_f4 = plan->cep_tab_f4; fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
+    fp.cep_off_col = plan->cep_smem_bytes / 4;
+    fp.cep_small = (p.n_mels <= 32 && plan->h_dct_t.size() <= static_cast<size_t>(kCepSmallTab) && p.delta_orders == 0 && !logmel_only) ? 1 : 0;
+    if (fp.cep_small) std::memcpy(fp.cep_dct, plan->h_dct_t.data(), plan->h_dct_t.size() * sizeof(float));
+    { const char* dbg = std::getenv("ASR_B200_DBG_SKIP"); fp.dbg_skip = dbg ? std::atoi(dbg) : 0; }
+    ASR_CUDA_TRY(launch_tcdft_path(fp, plan->sm_count, dfl.smem_bytes, plan->cep_smem_bytes + 4 * 128 * p.n_mels,
+                                   std::max(1, asr_plan_num_frames(plan, max_length)), as_stream(stream)));
+    return ASR_OK;
+  }
   // ---- n_fft = 512, int16 audio: tensor-core path (frame prefix -> tc512 -> cepstra) ----
   TcLayout tcl;
   if (tc_path_usable(plan, n_clips, max_length, dtype, kp.noise_mode, kp.vec_ok != 0, &tcl)) {
@@ -1037,7 +1216,7 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.lm = reinterpret_cast<float*>(ws + wl.off_lm);
     const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
     fp.lm_stride = static_cast<int>((frames + 31) & ~31LL);
-    fp.cep_blob = reinterpret_cast<const float4*>(plan->fr_blob_dev) + plan->cep_blob_f4;
+    fp.cep_blob = reinterpret_cast<const float4*>(plan->cep_dev);
     fp.cep_tab_f4 = plan->cep_tab_f4; fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
     fp.cep_off_col = plan->cep_smem_bytes / 4;
     fp.cep_small = (p.n_mels <= 32 && plan->h_dct_t.size() <= static_cast<size_t>(kCepSmallTab) && p.delta_orders == 0 && !logmel_only) ? 1 : 0;
@@ -1087,7 +1266,7 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.lm = reinterpret_cast<float*>(ws + wl.off_lm);
     const long long frames = static_cast<long long>(n_clips) * std::max(0, asr_plan_num_frames(plan, max_length));
     fp.lm_stride = static_cast<int>((frames + 31) & ~31LL);
-    fp.cep_blob = reinterpret_cast<const float4*>(plan->fr_blob_dev) + plan->cep_blob_f4;
+    fp.cep_blob = reinterpret_cast<const float4*>(plan->cep_dev);
     fp.cep_tab_f4 = plan->cep_tab_f4; fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
     fp.cep_off_col = plan->cep_smem_bytes / 4;
     fp.cep_small = (p.n_mels <= 32 && plan->h_dct_t.size() <= static_cast<size_t>(kCepSmallTab) && p.delta_orders == 0 && !logmel_only) ? 1 : 0;

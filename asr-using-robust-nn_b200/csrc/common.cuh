@@ -165,6 +165,11 @@ struct FParams {
   int tc_off_bnd;     // float offset of the boundary-filter list (int4: filter, first slot, slots, -) in the table blob
   int tc_n_bnd;       // entries of that list
   int* tc_dbg;        // mapped host memory (4 ints): breadcrumb of a wait that timed out
+  // ---- tensor-core dense DFT (tcdft_kernel.cu); shares tc_mats, tc_sm_slots, tc_off_bnd, tc_n_bnd, tc_dbg ----
+  int df_sm_stage;    // byte offset of the stage ring inside the dynamic shared memory
+  int df_nh;          // accumulator columns per half (bins rounded up to 16)
+  int df_ksteps;      // K steps of 16 samples (n_fft rounded up)
+  int df_bslab;       // bytes of one K step's slab of B: [B1 | B2][2 chunks][2 * nh rows][16]
   int mix_f32;        // 1: fused white-noise mix in float32 with one rounding (timing experiments, ASR_B200_MIX_F32=1); 0: exact
   float* stage_probe; // parity probe (asr_plan_set_stage_probe): staged samples written back, packed like the audio; or null
 };
@@ -179,6 +184,10 @@ cudaError_t launch_tc_path(const FParams& fp, int sm_count, int tc_smem_bytes, i
                            cudaStream_t stream);                                 // tc_kernel.cu
 cudaError_t tc_upload_constants();                                               // tc_kernel.cu: unpack twiddles -> constant memory
 int tc_static_smem_bytes();                                                      // tc_kernel.cu
+cudaError_t launch_tcdft_path(const FParams& fp, int sm_count, int smem_bytes, int cep_smem_bytes, int max_frames,
+                              cudaStream_t stream);                              // tcdft_kernel.cu
+int tcdft_static_smem_bytes();
+int tcdft_stages();
 
 // host-side launcher (mfcc_kernel.cu)
 cudaError_t launch_mfcc(const KParams& kp, int smem_bytes, cudaStream_t stream);
@@ -230,6 +239,12 @@ struct asr_plan {
   int tc_ok;
   void* tc_mats_dev;
   float* tc_blob_dev;
+  // ---- tensor-core dense DFT (FFT sizes without a register FFT, e.g. 441): B slabs and mel tables; df_ok = 0 -> not available ----
+  int df_ok, df_nh, df_ksteps, df_bslab;
+  void* df_mats_dev;
+  float* df_blob_dev;
+  int df_blob_f4, df_off_wtab, df_off_pieces, df_off_wrange, df_off_bnd, df_n_bnd, df_n_slots;
+  float* cep_dev;       // cepstra tables (transposed DCT x lifter, delta taps) for the cepstra_*_kernel of tile_kernel.cu
   int* tc_dbg_host;     // cudaHostAlloc(mapped): breadcrumb of a timed-out wait (asr_plan_debug_word)
   int* tc_dbg_dev;
   int tc_blob_f4, tc_off_wtab, tc_off_pieces, tc_off_wrange, tc_off_bnd, tc_n_bnd, tc_n_slots;

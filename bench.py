@@ -435,7 +435,8 @@ def main():
     t_hbm, t_fp32 = byts * B / (hbm_peak * 1e9), flops * B / (fp32_peak * 1e12)      # the two bound times of one launch
     binding = "hbm" if t_hbm >= t_fp32 else "fp32"
     path = pipe.plan.path_used({"int16": np.int16, "float32": np.float32, "float64": np.float64}[dt], noisy)
-    kernels = {"tc": "asr_mfcc_batch = frame_prefix_kernel + tc512_kernel (dominant, tcgen05) + cepstra_t_kernel",
+    kernels = {"tc": ("asr_mfcc_batch = frame_prefix_kernel + tc512_kernel (dominant, tcgen05) + cepstra_t_kernel" if params.n_fft == 512 else
+                      "asr_mfcc_batch = frame_prefix_kernel + tcdft_kernel (dominant, tcgen05 dense DFT) + cepstra_t_kernel"),
                "tiles": "asr_mfcc_batch = frame_prefix_kernel + tile512_kernel (dominant) + cepstra_t_kernel",
                "frames": "asr_mfcc_batch = frame_prefix_kernel + frames512_kernel (dominant) + cepstra_kernel",
                "clip": "asr_mfcc_batch = asr::mfcc_kernel"}
