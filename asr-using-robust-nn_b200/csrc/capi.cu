@@ -354,7 +354,20 @@ static bool build_tile_tables(asr_plan* pl, int cfg, int n_vw, bool pair_equal, 
     blob.resize(round4(static_cast<int>(blob.size())), 0.0f);
     return off;
   };
-  tt.off_twp = put_f(twp.data(), twp.size());
+  {
+    // second-pass lane twiddles of tile_fft512 (dft16_twisted): exp(-2 pi i (l + 16 j) / (16 m)) for (m, j) =
+    // (2,0) (4,0) (8,0) (8,1) (16,0..3), lane l = 0..15: 8 complex values per lane
+    (void)twp;
+    static const int mm[8] = {2, 4, 8, 8, 16, 16, 16, 16}, jj[8] = {0, 0, 0, 1, 0, 1, 2, 3};
+    std::vector<float> twl(16 * 16);
+    for (int l = 0; l < 16; ++l)
+      for (int e = 0; e < 8; ++e) {
+        const double a = -2.0 * M_PI * (l + 16 * jj[e]) / (16.0 * mm[e]);
+        twl[16 * l + 2 * e] = static_cast<float>(std::cos(a));
+        twl[16 * l + 2 * e + 1] = static_cast<float>(std::sin(a));
+      }
+    tt.off_twp = put_f(twl.data(), twl.size());
+  }
   {
     std::vector<float> twu2(twu);
     for (float& v : twu2) v *= 2.0f;                       // the tile kernel unpacks 2X (exact scaling)
@@ -1271,7 +1284,6 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.cep_off_col = plan->cep_smem_bytes / 4;
     fp.cep_small = (p.n_mels <= 32 && plan->h_dct_t.size() <= static_cast<size_t>(kCepSmallTab) && p.delta_orders == 0 && !logmel_only) ? 1 : 0;
     if (fp.cep_small) std::memcpy(fp.cep_dct, plan->h_dct_t.data(), plan->h_dct_t.size() * sizeof(float));
-    { const char* mf = std::getenv("ASR_B200_MIX_F32"); fp.mix_f32 = (mf && std::atoi(mf) != 0) ? 1 : 0; }
     fp.stage_probe = plan->stage_probe;
     ASR_CUDA_TRY(launch_tiles_path(fp, plan->sm_count, tlo.smem_bytes, plan->cep_smem_bytes + 4 * 128 * p.n_mels,
                                    std::max(1, asr_plan_num_frames(plan, max_length)), as_stream(stream)));

@@ -170,7 +170,6 @@ struct FParams {
   int df_nh;          // accumulator columns per half (bins rounded up to 16)
   int df_ksteps;      // K steps of 16 samples (n_fft rounded up)
   int df_bslab;       // bytes of one K step's slab of B: [B1 | B2][2 chunks][2 * nh rows][16]
-  int mix_f32;        // 1: fused white-noise mix in float32 with one rounding (timing experiments, ASR_B200_MIX_F32=1); 0: exact
   float* stage_probe; // parity probe (asr_plan_set_stage_probe): staged samples written back, packed like the audio; or null
 };
 

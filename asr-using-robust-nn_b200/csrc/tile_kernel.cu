@@ -95,21 +95,31 @@ __device__ __forceinline__ float tl_log2(const float x) {     // x >= amin > 0
 // access of the conversion is a dense, conflict-free row).
 // int16 stays UNSCALED (the window table carries the exact 2^-15): bits(2^23 + (s + 32768)) - (2^23 + 32768) = s.
 // Noise (VDR/attacks.py:241-244): the reference forms float64(x) + sigma*z with two float64 roundings and hands that
-// signal to librosa; the frame sample is its float32 rounding.  EXACT (default): the same two float64 operations
+// signal to librosa; the frame sample is its float32 rounding.  The kernel performs the same two float64 operations
 // (__dmul_rn, __dadd_rn: no FMA contraction) and one conversion, so the staged sample equals float32(reference signal)
-// bit for bit (asr_plan_set_stage_probe reads them back; tests/test_tiles_gpu.py).  `fast` (ASR_B200_MIX_F32=1, timing
-// experiments only): int16 / float32 audio mixed in float32 with one rounding, fma(float(z), sigma, x).
-// `sigf` = float(sigma) (x 2^15 for int16).
+// bit for bit (asr_plan_set_stage_probe reads them back; tests/test_tiles_gpu.py).  For int16 the whole chain runs in
+// int16 units (`sig` = sigma * 2^15, an exact scaling, so fl64(s + fl64(sig z)) = 2^15 fl64(x + fl64(sigma z))).
 template <int DT, bool NOISE>
-__device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const char* __restrict__ pz, const double sig, const float sigf,
-                                           const bool fast) {
-  float2 v;
+__device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const char* __restrict__ pz, const double sig) {
   if constexpr (DT == ASR_I16) {
-    const unsigned w = *reinterpret_cast<const unsigned*>(pa) ^ 0x80008000u;
-    v.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8421376.0f;
-    v.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8421376.0f;
+    const unsigned w = *reinterpret_cast<const unsigned*>(pa) ^ 0x80008000u;      // biased halves u = s + 32768
+    if constexpr (NOISE) {
+      // exact double(s) without a conversion instruction: bits(2^52 + u) - (2^52 + 32768); `sig` carries the 2^15
+      const double2 z = *reinterpret_cast<const double2*>(pz);
+      const double s0 = __hiloint2double(0x43300000, static_cast<int>(w & 0xFFFFu)) - 4503599627403264.0;
+      const double s1 = __hiloint2double(0x43300000, static_cast<int>(w >> 16)) - 4503599627403264.0;
+      return make_float2(static_cast<float>(__dadd_rn(s0, __dmul_rn(sig, z.x))), static_cast<float>(__dadd_rn(s1, __dmul_rn(sig, z.y))));
+    }
+    return make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8421376.0f,
+                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8421376.0f);
   } else if constexpr (DT == ASR_F32) {
-    v = *reinterpret_cast<const float2*>(pa);
+    const float2 v = *reinterpret_cast<const float2*>(pa);
+    if constexpr (NOISE) {
+      const double2 z = *reinterpret_cast<const double2*>(pz);
+      return make_float2(static_cast<float>(__dadd_rn(static_cast<double>(v.x), __dmul_rn(sig, z.x))),
+                         static_cast<float>(__dadd_rn(static_cast<double>(v.y), __dmul_rn(sig, z.y))));
+    }
+    return v;
   } else {
     const double2 a = *reinterpret_cast<const double2*>(pa);
     if constexpr (NOISE) {
@@ -118,57 +128,71 @@ __device__ __forceinline__ float2 convert2(const char* __restrict__ pa, const ch
     }
     return make_float2(static_cast<float>(a.x), static_cast<float>(a.y));
   }
-  if constexpr (NOISE) {
-    const double2 z = *reinterpret_cast<const double2*>(pz);
-    if (fast) {
-      v.x = fmaf(static_cast<float>(z.x), sigf, v.x);
-      v.y = fmaf(static_cast<float>(z.y), sigf, v.y);
-    } else if constexpr (DT == ASR_I16) {
-      // x = s / 32768 exactly; the staged value is the float32 signal x 32768 (both scalings are exact)
-      const float rx = static_cast<float>(__dadd_rn(static_cast<double>(v.x) * 0.000030517578125, __dmul_rn(sig, z.x)));
-      const float ry = static_cast<float>(__dadd_rn(static_cast<double>(v.y) * 0.000030517578125, __dmul_rn(sig, z.y)));
-      v.x = rx * 32768.0f;
-      v.y = ry * 32768.0f;
-    } else {
-      v.x = static_cast<float>(__dadd_rn(static_cast<double>(v.x), __dmul_rn(sig, z.x)));
-      v.y = static_cast<float>(__dadd_rn(static_cast<double>(v.y), __dmul_rn(sig, z.y)));
-    }
-  }
-  return v;
 }
 
 // one sample (clip edges): original index o, pa/pz point at original sample 0 of the raw copy
 template <int DT, bool NOISE>
-__device__ __forceinline__ float convert1(const char* __restrict__ pa, const char* __restrict__ pz, const int o, const double sig,
-                                          const float sigf, const bool fast) {
-  float x;
+__device__ __forceinline__ float convert1(const char* __restrict__ pa, const char* __restrict__ pz, const int o, const double sig) {
+  double xd;
   if constexpr (DT == ASR_I16) {
-    x = static_cast<float>(reinterpret_cast<const short*>(pa)[o]);          // unscaled
+    const short s = reinterpret_cast<const short*>(pa)[o];                  // unscaled
+    if constexpr (!NOISE) return static_cast<float>(s);
+    xd = static_cast<double>(s);
   } else if constexpr (DT == ASR_F32) {
-    x = reinterpret_cast<const float*>(pa)[o];
+    const float x = reinterpret_cast<const float*>(pa)[o];
+    if constexpr (!NOISE) return x;
+    xd = static_cast<double>(x);
   } else {
-    const double xd = reinterpret_cast<const double*>(pa)[o];
-    if constexpr (NOISE) return static_cast<float>(__dadd_rn(xd, __dmul_rn(sig, reinterpret_cast<const double*>(pz)[o])));
-    return static_cast<float>(xd);
+    xd = reinterpret_cast<const double*>(pa)[o];
+    if constexpr (!NOISE) return static_cast<float>(xd);
   }
-  if constexpr (NOISE) {
-    const double z = reinterpret_cast<const double*>(pz)[o];
-    if (fast) x = fmaf(static_cast<float>(z), sigf, x);
-    else if constexpr (DT == ASR_I16)
-      x = static_cast<float>(__dadd_rn(static_cast<double>(x) * 0.000030517578125, __dmul_rn(sig, z))) * 32768.0f;
-    else x = static_cast<float>(__dadd_rn(static_cast<double>(x), __dmul_rn(sig, z)));
+  return static_cast<float>(__dadd_rn(xd, __dmul_rn(sig, reinterpret_cast<const double*>(pz)[o])));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second pass of the 16 x 16 decomposition with the inter-pass twiddle merged into the butterflies ("twisted" DIT):
+//   Z[l + 16 k1] = sum_n1 A[n1] W256^(n1 (l + 16 k1))     (A = pass-1 output of residue k2 = l, no twiddle applied)
+// is a radix-2 DIT whose stage-m butterfly j uses  W_{16m}^(l + 16 j) = W_{16m}^l * W_m^j  in place of W_m^j: one rounded
+// table value per butterfly instead of a twiddle multiply followed by a butterfly, and j -> j + m/4 is a factor -i, so
+// a lane keeps 1 + 1 + 2 + 4 = 8 complex values in registers for the whole kernel (tw[0]: m = 2, tw[1]: m = 4,
+// tw[2..3]: m = 8, tw[4..7]: m = 16).  32 butterflies x 6 FMA; no table loads.  Input bit-reversed, output natural.
+__device__ __forceinline__ void dft16_twisted(float (&re)[16], float (&im)[16], const float (&twr)[8], const float (&twi)[8]) {
+#pragma unroll
+  for (int m = 2; m <= 16; m *= 2) {
+    const int h = m / 2, base = (m == 2) ? 0 : (m == 4 ? 1 : (m == 8 ? 2 : 4)), nq = (h > 1) ? h / 2 : 1;
+#pragma unroll
+    for (int g = 0; g < 16; g += m) {
+#pragma unroll
+      for (int j = 0; j < h; ++j) {
+        const int a = g + j, b = a + h;
+        const float ar = re[a], ai = im[a], br = re[b], bi = im[b];
+        float nr, ni;
+        if (j < nq) {                               // w = tw
+          const float wr = twr[base + j], wi = twi[base + j];
+          nr = fmaf(-wi, bi, fmaf(wr, br, ar));
+          ni = fmaf(wi, br, fmaf(wr, bi, ai));
+        } else {                                    // w = -i tw = (wi, -wr)
+          const float wr = twr[base + j - nq], wi = twi[base + j - nq];
+          nr = fmaf(wr, bi, fmaf(wi, br, ar));
+          ni = fmaf(-wr, br, fmaf(wi, bi, ai));
+        }
+        re[a] = nr; im[a] = ni;
+        re[b] = fmaf(2.0f, ar, -nr);
+        im[b] = fmaf(2.0f, ai, -ni);
+      }
+    }
   }
-  return x;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Power spectrum of one real frame of 512 staged samples by a group of 16 lanes: 256-point complex FFT of
 // z[n] = x[2n] + i x[2n+1] (n = n1 + 16 n2, k = k2 + 16 k1; lane = n1 in pass 1, k2 in pass 2), then the real-input
 // unpack.  Differences from frame_power_fft<512> (fft_core.cuh): the window multiply is fused into the first
-// radix-2 stage (p = xa*wa; p +- xb*wb), and the unpack works on 2X: X' = (A + conj B) + w'(A - conj B),
-// Y' = 2(A + conj B) - X', with w' = 2w; the spectrum row holds 4|X|^2 and the mel weights of this path carry the 1/4.
+// radix-2 stage (p = xa*wa; p +- xb*wb), the inter-pass twiddles live in the second pass's butterflies (dft16_twisted),
+// and the unpack works on 2X: X' = (A + conj B) + w'(A - conj B), Y' = 2(A + conj B) - X', with w' = 2w; the spectrum
+// row holds 4|X|^2 and the mel weights of this path carry the 1/4.
 __device__ __forceinline__ void tile_fft512(const float2* __restrict__ xs2, const float2* __restrict__ win2,
-                                            const float* __restrict__ twp, const float2* __restrict__ twu2,
+                                            const float (&twr)[8], const float (&twi)[8], const float2* __restrict__ twu2,
                                             float* buf, const int l) {
   constexpr int M = 256, G = 16, P = 16;
   float re[P], im[P];
@@ -182,21 +206,6 @@ __device__ __forceinline__ void tile_fft512(const float2* __restrict__ xs2, cons
     im[g] = fmaf(xb.y, wb.y, pi); im[g + 1] = fmaf(-xb.y, wb.y, pi);
   }
   dft_dit_from<P, 4>(re, im);
-  {
-    const float4* tw4 = reinterpret_cast<const float4*>(twp + l * (2 * P + 4));
-#pragma unroll
-    for (int k2 = 0; k2 < P; k2 += 2) {
-      const float4 t = tw4[k2 / 2];
-      if (k2 != 0) {
-        const float r = re[k2], i = im[k2];
-        re[k2] = fmaf(r, t.x, -i * t.y);
-        im[k2] = fmaf(r, t.y, i * t.x);
-      }
-      const float r = re[k2 + 1], i = im[k2 + 1];
-      re[k2 + 1] = fmaf(r, t.z, -i * t.w);
-      im[k2 + 1] = fmaf(r, t.w, i * t.z);
-    }
-  }
   float2* xb2 = reinterpret_cast<float2*>(buf);
   float ur[G], ui[G];
   __syncwarp();
@@ -209,7 +218,7 @@ __device__ __forceinline__ void tile_fft512(const float2* __restrict__ xs2, cons
     ur[brev<G>(n1)] = a.x;
     ui[brev<G>(n1)] = a.y;
   }
-  dft_dit<G>(ur, ui);
+  dft16_twisted(ur, ui, twr, twi);
   __syncwarp();                                    // exchange data consumed; buf becomes the spectrum row
   const int partner = (G - l) & (G - 1);
 #pragma unroll
@@ -269,7 +278,6 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
     if (tid < 128) dst[fp.blob_f4 + tid] = __ldg(fp.blob + fp.off_window / 4 + tid);
   }
   const float2* s_win2 = reinterpret_cast<const float2*>(smem + 4 * fp.blob_f4);
-  const float* s_twp = smem + fp.off_twp;
   const float2* s_twu = reinterpret_cast<const float2*>(smem + fp.off_twu);
   const float4* s_wtab = reinterpret_cast<const float4*>(smem + fp.off_wtab);
   const int4* s_pieces = reinterpret_cast<const int4*>(smem + fp.off_steps);
@@ -386,7 +394,6 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
   // raw -> float32 frame samples of a block, once per sample
   const float scale = DT == ASR_I16 ? 32768.0f : 1.0f;   // int16 is staged unscaled (the slow path computes scaled values)
   const float inv_scale = DT == ASR_I16 ? (1.0f / 32768.0f) : 1.0f;
-  const bool fast_mix = fp.mix_f32 != 0;
   float* const probe = fp.stage_probe;                   // parity probe: staged samples back to global memory, packed like the audio
   auto convert_block = [&](const TBlock& blk, float* aud) {       // helper warps
     const int nr = blk.n_runs;
@@ -395,7 +402,7 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
       const int4 q0 = rq[0], q1 = rq[1], q2 = rq[2], q3 = rq[3];
       const long long base = (static_cast<long long>(q0.y) << 32) | static_cast<unsigned>(q0.x);
       const double sig = __hiloint2double(q0.w, q0.z);
-      const float sigf = static_cast<float>(sig * scale);
+      const double sigs = sig * scale;                   // int16 is mixed in int16 units (exact scaling)
       const int L = q1.x, o0 = q1.y, count = q1.z, nu = q2.x, ra = q2.y;
       float* dst = aud + q1.w;
       if (nu == 0) {                                    // clip not on a 16-byte boundary: sample by sample from global memory
@@ -414,8 +421,8 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
         if (og >= 0 && og + 128 <= L && c0 + 128 <= count) {       // (warp-uniform) all 128 samples inside the clip
           const char* qa = pa + (og + 2 * lane) * esz;
           const char* qz = pz + (og + 2 * lane) * 8;
-          const float2 v0 = convert2<DT, NOISE>(qa, qz, sig, sigf, fast_mix);
-          const float2 v1 = convert2<DT, NOISE>(qa + 64 * esz, qz + 512, sig, sigf, fast_mix);
+          const float2 v0 = convert2<DT, NOISE>(qa, qz, sigs);
+          const float2 v1 = convert2<DT, NOISE>(qa + 64 * esz, qz + 512, sigs);
           float2* qd = reinterpret_cast<float2*>(dst + c0) + lane;
           qd[0] = v0;
           qd[32] = v1;
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
               bool zero = false;
               if (o < 0) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = -o; }
               else if (o >= L) { zero = fp.pad_mode != ASR_PAD_REFLECT; o = 2 * (L - 1) - o; }
-              e[j] = zero ? 0.0f : convert1<DT, NOISE>(pa, pz, o, sig, sigf, fast_mix);
+              e[j] = zero ? 0.0f : convert1<DT, NOISE>(pa, pz, o, sigs);
               if (probe && o == orig + j) probe[base + o] = e[j] * inv_scale;     // samples of the clip itself (not their reflections)
             }
             *reinterpret_cast<float2*>(dst + i) = make_float2(e[0], e[1]);
@@ -498,6 +505,15 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
 
   // ---- main warps: per-thread constants of the phases ----
   const int fft_h = lane >> 4, fft_l = lane & 15;
+  float twr[8], twi[8];                                            // this lane's second-pass twiddles (dft16_twisted)
+  {
+    const float4* t4 = reinterpret_cast<const float4*>(smem + fp.off_twp + 16 * fft_l);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = t4[q];
+      twr[2 * q] = t.x; twi[2 * q] = t.y; twr[2 * q + 1] = t.z; twi[2 * q + 1] = t.w;
+    }
+  }
   const int fft_slot0 = 8 * (warp >> 2) + (warp & 3);            // half-warps 4 slots apart: complementary bank halves of S
   const int fft_slot = fft_slot0 + 4 * fft_h;
   float* const fft_buf = s_S + fft_slot * kTlRS;
@@ -529,7 +545,7 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
     if (cur.n_slots == 0) break;                       // uniform over the CTA
     // ---- fft (block it) ----
     if (fft_slot0 < cur.n_slots)
-      tile_fft512(reinterpret_cast<const float2*>(s_aud + (it & 1) * fp.aud_cap + cur.slot_aud[fft_slot]), s_win2, s_twp, s_twu,
+      tile_fft512(reinterpret_cast<const float2*>(s_aud + (it & 1) * fp.aud_cap + cur.slot_aud[fft_slot]), s_win2, twr, twi, s_twu,
                   fft_buf, fft_l);
     bar_main();
     // ---- mel (block it): lanes <-> frames, this virtual warp's pieces ----
