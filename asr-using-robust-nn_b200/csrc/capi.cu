@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -857,6 +858,8 @@ extern "C" int asr_plan_create(const asr_mfcc_params* params, asr_plan** plan_ou
   return ASR_OK;
 }
 
+void free_host_state(asr_plan* plan);   // host-buffer pipeline state (defined beside asr_mfcc_batch_host)
+
 extern "C" void asr_plan_destroy(asr_plan* plan) {
   if (!plan) return;
   if (plan->blob_dev) cudaFree(plan->blob_dev);
@@ -870,6 +873,7 @@ extern "C" void asr_plan_destroy(asr_plan* plan) {
   if (plan->tc_mats_dev) cudaFree(plan->tc_mats_dev);
   if (plan->tc_blob_dev) cudaFree(plan->tc_blob_dev);
   if (plan->tc_dbg_host) cudaFreeHost(plan->tc_dbg_host);
+  free_host_state(plan);
   delete plan;
 }
 
@@ -1425,19 +1429,29 @@ extern "C" int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int
 
 // ------------------------------------------------------------------------------------------------
 // Host-buffer pipeline: clips are cut into chunks; chunk i+1's H2D copy overlaps chunk i's kernels
-// and chunk i-1's D2H copy (two streams, two sets of device buffers).
+// and chunk i-1's D2H copy (two streams, two sets of device buffers).  The streams, the device buffers and the pinned
+// per-chunk descriptors live in the plan (grown on demand, freed by asr_plan_destroy), so a call allocates nothing once
+// the plan has seen its batch shape; calls on one plan are serialised by a mutex (the plan's tables stay immutable).
 namespace {
 struct Slot {
   cudaStream_t st = nullptr;
-  void* audio = nullptr;
-  long long* offsets = nullptr;
-  int* lengths = nullptr;
-  void* out = nullptr;
-  int* status = nullptr;
-  float* power = nullptr;
-  double* sigma = nullptr;
-  double* z = nullptr;
-  void* ws = nullptr;
+  void* audio = nullptr;      size_t audio_cap = 0;
+  long long* offsets = nullptr; int* lengths = nullptr; int* status = nullptr; size_t clip_cap = 0;
+  void* out = nullptr;        size_t out_cap = 0;
+  float* power = nullptr;     double* sigma = nullptr; size_t snr_cap = 0;
+  double* z = nullptr;        size_t z_cap = 0;
+  void* ws = nullptr;         size_t ws_cap = 0;
+  long long* reb_pinned = nullptr; size_t reb_cap = 0;     // rebased offsets of the chunk in flight (pinned: no sync after the copy)
+  cudaEvent_t uploaded = nullptr;                          // the chunk's descriptors have left reb_pinned
+  template <typename T>
+  static cudaError_t grow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+  }
   void release() {
     if (ws) cudaFree(ws);
     if (audio) cudaFree(audio);
@@ -1448,10 +1462,25 @@ struct Slot {
     if (power) cudaFree(power);
     if (sigma) cudaFree(sigma);
     if (z) cudaFree(z);
+    if (reb_pinned) cudaFreeHost(reb_pinned);
+    if (uploaded) cudaEventDestroy(uploaded);
     if (st) cudaStreamDestroy(st);
   }
 };
+struct HostState {
+  std::mutex mu;
+  Slot slots[2];
+  int device = -1;
+};
 }  // namespace
+
+void free_host_state(asr_plan* plan) {
+  if (!plan || !plan->host_state) return;
+  HostState* hs = static_cast<HostState*>(plan->host_state);
+  for (int s = 0; s < 2; ++s) hs->slots[s].release();
+  delete hs;
+  plan->host_state = nullptr;
+}
 
 extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host, int32_t dtype,
                                    const int64_t* offsets_host, const int32_t* lengths_host, int32_t n_clips,
@@ -1497,24 +1526,55 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
     max_clips = std::max(max_clips, b - a);
   }
   for (int i = 0; i < n_clips; ++i) max_len = std::max(max_len, lengths_host[i]);
-  Slot slots[2];
+  static std::mutex create_mu;
+  HostState* hs;
+  {
+    std::lock_guard<std::mutex> g(create_mu);
+    if (!plan->host_state) const_cast<asr_plan*>(plan)->host_state = new HostState();
+    hs = static_cast<HostState*>(plan->host_state);
+  }
+  std::lock_guard<std::mutex> lock(hs->mu);
+  Slot* slots = hs->slots;
   int rc = ASR_OK;
   auto fail = [&](cudaError_t e, const char* what) { rc = cuda_fail(e, what); };
+  const size_t ws_bytes = asr_mfcc_workspace_bytes(plan, max_clips, max_len);
   for (int s = 0; s < 2 && rc == ASR_OK; ++s) {
     Slot& sl = slots[s];
-    cudaError_t e = cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&sl.audio, std::max<size_t>(16, max_span * esz));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.offsets), sizeof(long long) * max_clips);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.lengths), sizeof(int) * max_clips);
-    if (e == cudaSuccess) e = cudaMalloc(&sl.out, out_per_clip * osz * max_clips);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.status), sizeof(int) * max_clips);
-    if (e == cudaSuccess && snr_mode) {
-      e = cudaMalloc(reinterpret_cast<void**>(&sl.power), sizeof(float) * max_clips);
-      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.sigma), sizeof(double) * max_clips);
-      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&sl.z), sizeof(double) * std::max<size_t>(1, max_span));
+    cudaError_t e = cudaSuccess;
+    if (!sl.st) e = cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess && !sl.uploaded) e = cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = Slot::grow(&sl.audio, &sl.audio_cap, std::max<size_t>(16, max_span * esz));
+    if (e == cudaSuccess && static_cast<size_t>(max_clips) > sl.clip_cap) {
+      size_t c0 = 0, c1 = 0, c2 = 0;                       // the three per-clip arrays grow together
+      if (sl.offsets) cudaFree(sl.offsets);
+      if (sl.lengths) cudaFree(sl.lengths);
+      if (sl.status) cudaFree(sl.status);
+      sl.offsets = nullptr; sl.lengths = nullptr; sl.status = nullptr; sl.clip_cap = 0;
+      e = Slot::grow(&sl.offsets, &c0, sizeof(long long) * max_clips);
+      if (e == cudaSuccess) e = Slot::grow(&sl.lengths, &c1, sizeof(int) * max_clips);
+      if (e == cudaSuccess) e = Slot::grow(&sl.status, &c2, sizeof(int) * max_clips);
+      if (e == cudaSuccess) sl.clip_cap = static_cast<size_t>(max_clips);
     }
-    const size_t ws_bytes = asr_mfcc_workspace_bytes(plan, max_clips, max_len);
-    if (e == cudaSuccess && ws_bytes) e = cudaMalloc(&sl.ws, ws_bytes);
+    if (e == cudaSuccess) e = Slot::grow(&sl.out, &sl.out_cap, out_per_clip * osz * max_clips);
+    if (e == cudaSuccess && snr_mode) {
+      if (static_cast<size_t>(max_clips) > sl.snr_cap) {
+        size_t c0 = 0, c1 = 0;
+        if (sl.power) cudaFree(sl.power);
+        if (sl.sigma) cudaFree(sl.sigma);
+        sl.power = nullptr; sl.sigma = nullptr; sl.snr_cap = 0;
+        e = Slot::grow(&sl.power, &c0, sizeof(float) * max_clips);
+        if (e == cudaSuccess) e = Slot::grow(&sl.sigma, &c1, sizeof(double) * max_clips);
+        if (e == cudaSuccess) sl.snr_cap = static_cast<size_t>(max_clips);
+      }
+      if (e == cudaSuccess) e = Slot::grow(&sl.z, &sl.z_cap, sizeof(double) * std::max<size_t>(1, max_span));
+    }
+    if (e == cudaSuccess && ws_bytes) e = Slot::grow(&sl.ws, &sl.ws_cap, ws_bytes);
+    if (e == cudaSuccess && static_cast<size_t>(max_clips) > sl.reb_cap) {
+      if (sl.reb_pinned) cudaFreeHost(sl.reb_pinned);
+      sl.reb_pinned = nullptr; sl.reb_cap = 0;
+      e = cudaHostAlloc(reinterpret_cast<void**>(&sl.reb_pinned), sizeof(long long) * max_clips, cudaHostAllocDefault);
+      if (e == cudaSuccess) sl.reb_cap = static_cast<size_t>(max_clips);
+    }
     if (e != cudaSuccess) fail(e, "asr_mfcc_batch_host (allocation)");
   }
   for (size_t k = 0; k + 1 < cuts.size() && rc == ASR_OK; ++k) {
@@ -1522,15 +1582,16 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
     const int a = cuts[k], b = cuts[k + 1], nc = b - a;
     const int64_t first = offsets_host[a];
     const size_t span = static_cast<size_t>(offsets_host[b - 1] + lengths_host[b - 1] - first);
-    cudaError_t e = cudaStreamSynchronize(sl.st);   // slot free again
-    if (e != cudaSuccess) { fail(e, "stream sync"); break; }
-    std::vector<long long> reb(nc);
-    for (int i = 0; i < nc; ++i) reb[i] = offsets_host[a + i] - first;
+    // the slot's previous chunk (k-2) must have left the pinned descriptor buffer; its kernels and copies are ordered on the
+    // slot's stream, so nothing else has to be waited for here: chunk k's upload overlaps chunk k-1's kernels / download
+    cudaError_t e = k >= 2 ? cudaEventSynchronize(sl.uploaded) : cudaSuccess;
+    if (e != cudaSuccess) { fail(e, "event sync"); break; }
+    for (int i = 0; i < nc; ++i) sl.reb_pinned[i] = offsets_host[a + i] - first;
     e = cudaMemcpyAsync(sl.audio, static_cast<const char*>(audio_host) + first * esz, span * esz,
                         cudaMemcpyHostToDevice, sl.st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.offsets, reb.data(), sizeof(long long) * nc, cudaMemcpyHostToDevice, sl.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.offsets, sl.reb_pinned, sizeof(long long) * nc, cudaMemcpyHostToDevice, sl.st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(sl.lengths, lengths_host + a, sizeof(int) * nc, cudaMemcpyHostToDevice, sl.st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(sl.st);   // `reb` is a local pageable vector
+    if (e == cudaSuccess) e = cudaEventRecord(sl.uploaded, sl.st);
     if (e != cudaSuccess) { fail(e, "H2D copy"); break; }
     asr_noise nz;
     std::memset(&nz, 0, sizeof(nz));
@@ -1542,8 +1603,7 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
       nz.mode = ASR_NOISE_WHITE; nz.z_dev = sl.z; nz.sigma_dev = sl.sigma;
     }
     rc = asr_mfcc_batch(plan, sl.audio, dtype, reinterpret_cast<const int64_t*>(sl.offsets), sl.lengths, nc, max_len,
-                        snr_mode ? &nz : nullptr, sl.out, out_dtype, out_frames, sl.status, sl.ws,
-                        sl.ws ? asr_mfcc_workspace_bytes(plan, max_clips, max_len) : 0, sl.st);
+                        snr_mode ? &nz : nullptr, sl.out, out_dtype, out_frames, sl.status, sl.ws, sl.ws ? sl.ws_cap : 0, sl.st);
     if (rc != ASR_OK) break;
     e = cudaMemcpyAsync(static_cast<char*>(out_host) + static_cast<size_t>(a) * out_per_clip * osz, sl.out,
                         out_per_clip * osz * nc, cudaMemcpyDeviceToHost, sl.st);
@@ -1556,6 +1616,5 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
       const cudaError_t e = cudaStreamSynchronize(slots[s].st);
       if (e != cudaSuccess && rc == ASR_OK) fail(e, "final sync");
     }
-  for (int s = 0; s < 2; ++s) slots[s].release();
   return rc;
 }

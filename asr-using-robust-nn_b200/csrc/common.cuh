@@ -234,6 +234,7 @@ struct asr_plan {
   void* ws_dev;
   size_t ws_bytes;
   float* stage_probe;   // asr_plan_set_stage_probe
+  void* host_state = nullptr;   // asr_mfcc_batch_host: persistent streams / device buffers / pinned descriptors (capi.cu: HostState)
   // ---- tensor-core path (n_fft = 512, int16 audio): pass-1 matrices and mel tables; tc_ok = 0 -> not available ----
   int tc_ok;
   void* tc_mats_dev;

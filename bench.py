@@ -416,8 +416,26 @@ def main():
             tt = torch.tensor([ms_e], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt.item())
+        # the C-ABI host-buffer entry point INTEGRATION.md tells a maintainer to bind (asr_mfcc_batch_host: MFCC [+ SNR noise
+        # with the device sigma chain], features back on the host, no standardisation): a blocking call, host clock
+        capi = None
+        if noise in (None, "white") and dt != "float64" or not noisy:
+            try:
+                offs = np.asarray(layout.offsets_host, dtype=np.int64)
+                lens = np.asarray(lengths, dtype=np.int32)
+                feats_host = torch.empty((B, pipe.rows * pipe.out_frames), dtype=torch.float32).pin_memory().numpy()
+                snr_c = 10.0 if noisy else None
+                for _ in range(2):
+                    pipe.plan.mfcc_host(audio_host.numpy(), offs, lens, pipe.out_frames, snr_db=snr_c, seed=99, out=feats_host)
+                t0 = time.perf_counter()
+                for _ in range(Ke):
+                    pipe.plan.mfcc_host(audio_host.numpy(), offs, lens, pipe.out_frames, snr_db=snr_c, seed=99, out=feats_host)
+                capi = {"value": B * Ke / (time.perf_counter() - t0), "unit": UNIT, "scope": "this rank; asr_mfcc_batch_host, pinned host audio in, "
+                        "float32 feature rows out to pinned host memory, blocking call timed on the host clock, chunks double-buffered inside the call"}
+            except Exception as e:                                   # noqa: BLE001
+                capi = {"error": str(e).splitlines()[0][:120]}
         e2e = {"value": B * world * Ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(audio_host.numel() * audio_host.element_size()),
-               "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": Ke,
+               "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": Ke, "capi_host_call": capi,
                "note": f"per GPU bytes; pinned host {dt} in, standardised float32 rows back in pinned host memory, every step; "
                        "noise generated on the device (white: from the seed; babble: from the batch); upload / kernels / download "
                        "of consecutive steps overlap on three streams"}

@@ -77,3 +77,30 @@ def test_host_buffer_abi_entry_point():
     a, _ = plan.mfcc_host(audio, offsets, lengths, out_frames=101, snr_db=10, seed=7)
     b, _ = plan.mfcc_host(audio, offsets, lengths, out_frames=101, snr_db=10, seed=7)
     assert np.array_equal(a, b) and np.abs(a - out).max() > 1
+
+
+@pytest.mark.gpu
+def test_capi_host_call_persistent_slots_chunks_and_growth():
+    """asr_mfcc_batch_host keeps its streams / buffers in the plan: a small call, then a larger one that needs several chunks
+    (> 4096 clips) and bigger buffers, then the small one again - rows must equal the device-path rows of the same clips."""
+    import torch
+    import asr_b200 as A
+    base = synth_clips(64, 4000, 16000, 11)
+    plan = A.MfccPlan(A.C1)
+
+    def run(n):
+        clips = [np.roll(base[i % 64], 13 * (i // 64))[: 3000 + 7 * (i % 100)] for i in range(n)]
+        lengths = np.array([len(c) for c in clips], dtype=np.int32)
+        offsets, total = A.ClipBatch.layout(lengths)
+        audio = np.zeros(total, dtype=np.int16)
+        for c, o in zip(clips, offsets):
+            audio[o:o + len(c)] = c
+        out, status = plan.mfcc_host(audio, offsets, lengths, out_frames=30, out_dtype=np.float32)
+        dev, st = plan.mfcc(A.ClipBatch.from_arrays(clips), out_frames=30)
+        torch.cuda.synchronize()
+        assert (status == 0).all() and int(st.max()) == 0
+        assert np.array_equal(out, dev.cpu().numpy().reshape(n, -1))
+
+    run(50)
+    run(9000)        # three chunks (4096 + 4096 + 808): both slots are reused, pinned descriptor buffers re-filled
+    run(50)
