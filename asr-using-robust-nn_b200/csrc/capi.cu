@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <dlfcn.h>
 #include <numeric>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -1425,6 +1427,38 @@ extern "C" int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int
                                 void* workspace_dev, size_t workspace_bytes, void* stream) {
   return launch_common(plan, audio_dev, dtype, offsets_dev, lengths_dev, n_clips, max_length, noise, out_dev, ASR_F32,
                        out_frames, status_dev, workspace_dev, workspace_bytes, stream, 1, "asr_logmel_batch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// The one collective of the sharded path behind the C-ABI: ncclAllGather of the standardisation messages, resolved from the
+// NCCL library the process has already loaded (no link-time dependency, no second copy of NCCL).
+namespace {
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+nccl_allgather_fn resolve_nccl_allgather() {
+  static nccl_allgather_fn fn = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  if (fn) return fn;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    void* h = dlopen(n, RTLD_NOW | RTLD_NOLOAD);               // only a copy that is already in the process
+    if (h) {
+      fn = reinterpret_cast<nccl_allgather_fn>(dlsym(h, "ncclAllGather"));
+      if (fn) return fn;
+    }
+  }
+  fn = reinterpret_cast<nccl_allgather_fn>(dlsym(RTLD_DEFAULT, "ncclAllGather"));   // statically linked into the host program
+  return fn;
+}
+}  // namespace
+
+extern "C" int asr_cmvn_exchange_nccl(void* nccl_comm, const double* msg_dev, double* msgs_dev, int32_t n_cols, void* stream) {
+  if (!nccl_comm || !msg_dev || !msgs_dev || n_cols < 1) { set_error("asr_cmvn_exchange_nccl: bad argument"); return ASR_ERR_INVALID; }
+  const nccl_allgather_fn fn = resolve_nccl_allgather();
+  if (!fn) { set_error("asr_cmvn_exchange_nccl: no NCCL library is loaded in this process (load the one that created nccl_comm first)"); return ASR_ERR_INVALID; }
+  const int rc = fn(msg_dev, msgs_dev, static_cast<size_t>(3) * n_cols + 1, 8 /* ncclFloat64 */, nccl_comm, reinterpret_cast<cudaStream_t>(stream));
+  if (rc != 0) { set_error("asr_cmvn_exchange_nccl: ncclAllGather failed with ncclResult_t " + std::to_string(rc)); return ASR_ERR_CUDA; }
+  return ASR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -281,6 +281,13 @@ int32_t asr_cmvn_partial_sums(const void* x_dev, int32_t dtype, int64_t n_rows, 
                               int32_t slab_base, void* workspace_dev, size_t workspace_bytes, void* stream);
 int asr_cmvn_local_message(const void* workspace_dev, size_t workspace_bytes, int32_t n_slabs_pass1, int32_t n_slabs_pass2,
                            int64_t n_local_rows, int32_t n_cols, double* msg_dev, void* stream);
+/* The exchange as a C-ABI call for callers without torch (a ctypes / cgo stub on the reference side that owns an NCCL
+ * communicator): ncclAllGather of this rank's message (3*n_cols + 1 float64) into msgs_dev[world][3*n_cols + 1] in rank
+ * order, on `stream`.  `nccl_comm` is the caller's ncclComm_t.  libasr_b200.so does not link NCCL: the symbol is resolved
+ * at run time from the NCCL library ALREADY LOADED in the process (the one that created the communicator), so versions
+ * cannot mix; ASR_ERR_INVALID if no NCCL is loaded.  Replaces the reduction hidden in StandardScaler().fit of
+ * standardize_dataset (VDR/attacks.py:48-69) when the rows are sharded over GPUs. */
+int asr_cmvn_exchange_nccl(void* nccl_comm, const double* msg_dev, double* msgs_dev, int32_t n_cols, void* stream);
 int asr_cmvn_merge(const double* msgs_dev, int32_t world, int32_t n_cols, double* mean_dev, double* var_dev,
                    double* scale_dev, double* n_total_dev /* may be NULL */, void* stream);
 int asr_cmvn_apply2(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld, const asr_noise* row_noise,
