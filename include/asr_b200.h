@@ -216,11 +216,12 @@ int asr_mix_white(const void* audio_dev, int32_t dtype, const int64_t* offsets_d
 
 /* Babble noise of BASELINE configs[1] ("white/babble").  The reference has NO babble implementation (parity unpinned);
  * the recipe is SURVEY.md 8(d): babble[b][n] = sum over k = 1..talkers of clip (b + k*stride) mod n_clips at sample n
- * (float64, exact), power[b] = mean(babble[b]^2) in float64 (fixed order: per 2048-sample chunk, chunks ascending).  The mix is the white-noise formula with
+ * (float64, exact), power[b] = mean(babble[b]^2) in float64 (fixed order: per 2048-sample chunk 256 thread sums of 8 samples and a binary tree, chunks ascending).  The mix is the white-noise formula with
  * z := babble and sigma[b] := sigma_snr[b] / sqrt(power[b]) (host), i.e. asr_mix_white / the fused launch take the
  * stream unchanged: noise power = P / 10^(snr/10) by the same sigma law as VDR/attacks.py:233-241.
  * babble_dev is packed like the audio (float64), power_dev is float64 [n_clips]. */
-size_t asr_babble_workspace_bytes(int32_t n_clips, int32_t max_length);   /* scratch, ZEROED once by the caller */
+size_t asr_babble_workspace_bytes(int32_t n_clips, int32_t max_length);   /* scratch (kept in the ABI; since round 2 a clip's chunks
+                                                                             are summed inside its CTA and the scratch is not touched) */
 int asr_babble_stream(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
                       int32_t n_clips, int32_t max_length, int32_t stride, int32_t talkers, double* babble_dev,
                       double* power_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
