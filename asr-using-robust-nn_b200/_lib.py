@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libasr_b200.so")
+# ASR_B200_LIB: another build of the same library (the -DASR_TILE_DEBUG build `make debug` produces); there is still no fallback
+LIB_PATH = os.environ.get("ASR_B200_LIB") or os.path.join(_HERE, "libasr_b200.so")
 
 ASR_I16, ASR_F32, ASR_F64 = 0, 1, 2
 ASR_NOISE_NONE, ASR_NOISE_WHITE, ASR_NOISE_MIXTURE = 0, 1, 2

@@ -1278,7 +1278,7 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     fp.off_steps = tt.off_steps; fp.off_wrange = tt.off_wrange;
     fp.sm_aud = tlo.sm_aud; fp.sm_S = tlo.sm_S; fp.sm_part = tlo.sm_part; fp.sm_raw = tlo.sm_raw;
     fp.max_runs = tlo.max_runs; fp.vec_ok = 1; fp.aud_cap = tlo.aud_cap;
-    fp.t_npart = tt.npart; fp.t_npc = tt.npc; fp.t_nw = tlo.nw;
+    fp.t_npart = tt.npart; fp.t_npc = tt.npc; fp.t_nw = tlo.nw; fp.t_smem_bytes = tlo.smem_bytes;
     fp.fstart = reinterpret_cast<int*>(ws + wl.off_fstart);
     fp.nframes = reinterpret_cast<int*>(ws + wl.off_nframes);
     fp.clipmax = reinterpret_cast<float*>(ws + wl.off_clipmax);

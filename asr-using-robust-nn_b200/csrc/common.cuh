@@ -152,6 +152,7 @@ struct FParams {
   int t_npart;        // rows of 32 floats in the partial buffer: (n_mels + 1) * t_npc * 2
   int t_npc;          // pieces per mel segment
   int t_nw;           // warps per CTA: 16 (one CTA per SM) or 8 (two CTAs per SM)
+  int t_smem_bytes;   // dynamic shared memory of the launch (bounds checks of the debug build)
   int lm_stride;      // tiles path: lm is [n_mels][lm_stride] (transposed), lm_stride >= total frames
   const float4* cep_blob;   // cepstra tables (global)
   int cep_off_col;    // cepstra_t_kernel: shared-memory offset (floats) of the [n_mels][128] log-mel column buffer

@@ -29,6 +29,15 @@
 #include "fft_core.cuh"
 #include "sample_access.cuh"
 
+// -DASR_TILE_DEBUG (make debug -> libasr_b200_dbg.so, loaded with ASR_B200_LIB): device-side checks of the staging
+// protocol - raw-buffer bounds of every bulk copy, bytes announced to the mbarrier against bytes issued, sample-buffer
+// bounds of every run, descriptor ring / slot ranges.  A failed check traps (the launch fails, nothing hangs).
+#ifdef ASR_TILE_DEBUG
+#define TL_CHECK(cond) do { if (!(cond)) { printf("tile512_kernel check failed: %s (line %d, CTA %d, thread %d)\n", #cond, __LINE__, blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define TL_CHECK(cond) do { } while (0)
+#endif
+
 namespace asr {
 
 constexpr int kTlHelpDiv = 16;    // helper threads per main warp: 8 -> NW/4 helper warps, 16 -> NW/2
@@ -352,7 +361,13 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
       load_meta(cache_base);
       __syncwarp();
     }
-    if (lane == 0) { blk.n_runs = n_runs; blk.n_slots = n_slots; blk.g0 = g0; blk.tx_bytes = tx; }
+    if (lane == 0) {
+      blk.n_runs = n_runs; blk.n_slots = n_slots; blk.g0 = g0; blk.tx_bytes = tx;
+      TL_CHECK(n_runs <= fp.max_runs && n_runs <= kTlMaxRuns && n_slots <= kTlBlock);
+      TL_CHECK(aud <= fp.aud_cap);                                   // the block's samples fit one sample buffer
+      TL_CHECK(fp.sm_raw * 4 + raw_off <= fp.t_smem_bytes);          // the block's raw bytes fit the raw buffer
+      TL_CHECK(g0 >= g_begin && g0 + n_slots <= g_end);
+    }
     __syncwarp();
     const int nr = blk.n_runs, ns = blk.n_slots;
     int a = 0;                                          // (lanes >= kTlBlock: ns <= kTlBlock keeps them at 0)
@@ -368,9 +383,19 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
   auto issue_copies = [&](const TBlock& blk) {         // whole descriptor warp
     const int nr = blk.n_runs;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#ifdef ASR_TILE_DEBUG
+    {
+      int issued = 0;
+      if (lane < nr && blk.run[lane].nu > 0) issued = max(0, (blk.run[lane].rb & ~7) - blk.run[lane].ra) * (esz + (NOISE ? 8 : 0));
+      for (int o = 16; o > 0; o >>= 1) issued += __shfl_xor_sync(0xffffffffu, issued, o);
+      TL_CHECK(issued == blk.tx_bytes);                              // what the mbarrier expects is what the copies deliver
+    }
+#endif
     if (lane < nr && blk.run[lane].nu > 0) {
       const TRun& run = blk.run[lane];
       const int nfull = (run.rb & ~7) - run.ra;
+      TL_CHECK(run.raw_a >= 0 && (run.raw_a & 15) == 0 && (run.ra & 7) == 0 && run.rb <= run.L && run.ra <= run.rb);
+      TL_CHECK(fp.sm_raw * 4 + run.raw_a + max(nfull, 0) * esz <= fp.t_smem_bytes);
       if (nfull > 0) {
         tma_bulk_g2s(s_raw + run.raw_a, reinterpret_cast<const char*>(fp.audio) + (run.base + run.ra) * esz,
                      static_cast<unsigned>(nfull * esz), &s_bar);
@@ -544,6 +569,7 @@ __global__ void __launch_bounds__(NW * 32 + NW * kTlHelpDiv, NW == 8 ? 2 : 1) ti
     }
     if (cur.n_slots == 0) break;                       // uniform over the CTA
     // ---- fft (block it) ----
+    TL_CHECK(cur.n_slots <= kTlBlock && cur.slot_aud[fft_slot] >= 0 && cur.slot_aud[fft_slot] + 512 <= fp.aud_cap);
     if (fft_slot0 < cur.n_slots)
       tile_fft512(reinterpret_cast<const float2*>(s_aud + (it & 1) * fp.aud_cap + cur.slot_aud[fft_slot]), s_win2, twr, twi, s_twu,
                   fft_buf, fft_l);
