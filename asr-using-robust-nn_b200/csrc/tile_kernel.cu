@@ -629,8 +629,9 @@ __global__ void __launch_bounds__(kCepTThreads) cepstra_t_kernel(const __grid_co
   {
     const int z_lo = max(t_out, t_lo), z_hi = min(fp.out_frames, t_lo + tile);
     const int w = z_hi - z_lo;
-    for (int e = tid; w > 0 && e < rows * w; e += kCepTThreads)
-      store(out_base + static_cast<long long>(e / w) * fp.out_frames + z_lo + e % w, 0.0f);
+    if (w > 0)                                           // threads <-> columns, rows in the loop: no division per element
+      for (int r = 0; r < rows; ++r)
+        for (int x = tid; x < w; x += kCepTThreads) store(out_base + static_cast<long long>(r) * fp.out_frames + z_lo + x, 0.0f);
   }
   if (t_lo >= t_out) return;
 
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(kCepTThreads) cepstra_t_kernel(const __grid_co
   float mx = -3.0e38f;
   if (live) {
     const float* col = lm0 + t;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < fp.n_mels; ++j) {
       const float v = __ldcg(col + static_cast<long long>(j) * fp.lm_stride);
       s_col[j * kCepTThreads] = v;
@@ -724,14 +725,40 @@ __global__ void __launch_bounds__(kCepTThreads) cepstra_t_kernel(const __grid_co
   if (tid < tile && to < t_out) {
     const int tc = min(max(to, half), T - 1 - half);
     const int i0 = tc - half - c_lo;                     // first tap position in s_cep
-    for (int c = 0; c < fp.n_mfcc; ++c) {
-      const float* cr = s_cep + c * cp;
-      store(out_base + static_cast<long long>(c) * fp.out_frames + to, cr[to - c_lo]);
-      for (int o = 1; o <= fp.delta_orders; ++o) {
-        const float* taps = s_taps + (o - 1) * fp.delta_width;
-        float v = 0.0f;
-        for (int j = 0; j < fp.delta_width; ++j) v = fmaf(taps[j], cr[i0 + j], v);
-        store(out_base + static_cast<long long>(o * fp.n_mfcc + c) * fp.out_frames + to, v);
+    if (fp.delta_width == 9 && fp.delta_orders <= 2) {
+      // librosa's default width: taps of both orders in registers, the nine cepstra of the window loaded once per
+      // coefficient and used for both orders (same products in the same order as the general loop below)
+      float tp[2][9];
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) tp[o][j] = (o < fp.delta_orders) ? s_taps[o * 9 + j] : 0.0f;
+      for (int c = 0; c < fp.n_mfcc; ++c) {
+        const float* cr = s_cep + c * cp;
+        float x[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) x[j] = cr[i0 + j];
+        store(out_base + static_cast<long long>(c) * fp.out_frames + to, cr[to - c_lo]);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          if (o < fp.delta_orders) {
+            float v = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) v = fmaf(tp[o][j], x[j], v);
+            store(out_base + static_cast<long long>((o + 1) * fp.n_mfcc + c) * fp.out_frames + to, v);
+          }
+        }
+      }
+    } else {
+      for (int c = 0; c < fp.n_mfcc; ++c) {
+        const float* cr = s_cep + c * cp;
+        store(out_base + static_cast<long long>(c) * fp.out_frames + to, cr[to - c_lo]);
+        for (int o = 1; o <= fp.delta_orders; ++o) {
+          const float* taps = s_taps + (o - 1) * fp.delta_width;
+          float v = 0.0f;
+          for (int j = 0; j < fp.delta_width; ++j) v = fmaf(taps[j], cr[i0 + j], v);
+          store(out_base + static_cast<long long>(o * fp.n_mfcc + c) * fp.out_frames + to, v);
+        }
       }
     }
   }
@@ -756,8 +783,9 @@ __global__ void __launch_bounds__(kCepTThreads) cepstra_small_kernel(const __gri
   {                                                     // zero padding in the feature domain (VDR/extract...py:36-37)
     const int z_lo = max(t_out, t_lo), z_hi = min(fp.out_frames, t_lo + kCepTThreads);
     const int w = z_hi - z_lo;
-    for (int e = tid; w > 0 && e < fp.out_rows * w; e += kCepTThreads)
-      store(out_base + static_cast<long long>(e / w) * fp.out_frames + z_lo + e % w, 0.0f);
+    if (w > 0)
+      for (int r = 0; r < fp.out_rows; ++r)
+        for (int x = tid; x < w; x += kCepTThreads) store(out_base + static_cast<long long>(r) * fp.out_frames + z_lo + x, 0.0f);
   }
   if (t_lo >= t_out) return;
   const int g0 = __ldg(fp.fstart + b);
