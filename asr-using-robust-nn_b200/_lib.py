@@ -58,6 +58,7 @@ SIGNATURES = {
     "asr_plan_set_stage_probe": (C.c_int, [_vp, _vp]),
     "asr_plan_debug_word": (_i32, [_vp, _i32]),
     "asr_fp32_peak_probe": (C.c_int, [_i32, _i32, _vp, _vp]),
+    "asr_mlp_forward": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "asr_cmvn_workspace_bytes": (C.c_size_t, [_i32]),
     "asr_cmvn_partial_sums": (_i32, [_vp, _i32, _i64, _i32, _i64, C.POINTER(NoiseC), _i32, _i32, _i64, _i32, _vp, C.c_size_t, _vp]),
     "asr_cmvn_local_message": (C.c_int, [_vp, C.c_size_t, _i32, _i32, _i64, _i32, _vp, _vp]),

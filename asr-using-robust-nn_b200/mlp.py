@@ -5,16 +5,23 @@ training statistics -> ``model.predict`` -> accuracy.
 The network is the reference's ``get_model`` (VDR/train_constraints.py:63-88): 880 -> 1024 -> 512 -> 256 -> 128 -> 64
 (ReLU, BatchNormalization after each) -> 10 (softmax).  At inference every BatchNormalization is an affine map; it is
 folded into the FOLLOWING Dense layer once, at construction (in float64, rounded to float32), so a forward pass is six
-plain float32 GEMMs with bias (+ ReLU) - library GEMMs (cuBLAS through ``torch.addmm``, TF32 off), which is what the
-build rules prescribe for plain GEMMs; the softmax / argmax / accuracy stay on the device.  The reference's trained
-``.h5`` files are not in its tree, so weights come from the caller (``from_keras_weights``) or are synthetic.
+float32 affine maps (+ ReLU) and a softmax: ONE launch of this repository's ``mlp_forward_kernel`` through the C-ABI entry
+``asr_mlp_forward`` (``csrc/mlp_kernel.cu``: 16 rows per CTA through all layers, activations in shared memory, weights
+streamed from L2, float32 FMA accumulation like ``model.predict``); logits, probabilities and decisions come out of that
+launch.  ``logits_library`` keeps the cuBLAS form (``torch.addmm``, TF32 off) as an independent check for the tests.  The
+reference's trained ``.h5`` files are not in its tree, so weights come from the caller (``from_keras_weights``) or are
+synthetic.
 """
 from __future__ import annotations
 
 from typing import Iterable, Optional, Sequence
 
+import ctypes as C
+
 import numpy as np
 import torch
+
+from ._lib import lib, check
 
 BN_EPS = 1e-3      # keras.layers.BatchNormalization default epsilon
 
@@ -41,8 +48,14 @@ class DenseStack:
                 scale, shift = inv, np.asarray(ly["beta"], np.float64) - np.asarray(ly["moving_mean"], np.float64) * inv
             else:
                 scale = shift = None
-        self.weights, self.biases = ws, bs
+        self.weights, self.biases = [w.contiguous() for w in ws], [b.contiguous() for b in bs]
         self.n_in, self.n_out = ws[0].shape[0], ws[-1].shape[1]
+        n = len(ws)
+        if n > 8 or max(w.shape[1] for w in ws) > 1024:
+            raise ValueError("asr_mlp_forward takes 1..8 layers with outputs up to 1024 wide")
+        self._dims = (C.c_int32 * (n + 1))(*([ws[0].shape[0]] + [w.shape[1] for w in ws]))
+        self._wptr = (C.c_void_p * n)(*[w.data_ptr() for w in self.weights])
+        self._bptr = (C.c_void_p * n)(*[b.data_ptr() for b in self.biases])
 
     @staticmethod
     def from_keras_weights(arrays: Iterable[np.ndarray], device="cuda") -> "DenseStack":
@@ -60,7 +73,29 @@ class DenseStack:
             layers.append(ly)
         return DenseStack(layers, device=device)
 
+    def _forward(self, x: torch.Tensor, want_logits: bool, want_probs: bool, want_argmax: bool):
+        """One ``asr_mlp_forward`` launch on the current stream; returns (logits, probs, argmax), None where not asked."""
+        if x.dim() != 2 or x.shape[1] != self.n_in:
+            raise ValueError(f"expected (N, {self.n_in}) features")
+        h = x.to(self.device, torch.float32)
+        if h.stride(1) != 1:
+            h = h.contiguous()
+        n = h.shape[0]
+        lg = torch.empty((n, self.n_out), dtype=torch.float32, device=self.device) if want_logits else None
+        pr = torch.empty((n, self.n_out), dtype=torch.float32, device=self.device) if want_probs else None
+        am = torch.empty(n, dtype=torch.int32, device=self.device) if want_argmax else None
+        with torch.cuda.device(self.device):
+            check(lib.asr_mlp_forward(h.data_ptr(), n, h.stride(0) if n > 0 else self.n_in, len(self.weights), self._dims, self._wptr,
+                                      self._bptr, lg.data_ptr() if want_logits else None, pr.data_ptr() if want_probs else None,
+                                      am.data_ptr() if want_argmax else None, torch.cuda.current_stream(self.device).cuda_stream),
+                  "asr_mlp_forward")
+        return lg, pr, am
+
     def logits(self, x: torch.Tensor) -> torch.Tensor:
+        return self._forward(x, True, False, False)[0]
+
+    def logits_library(self, x: torch.Tensor) -> torch.Tensor:
+        """The same forward pass through cuBLAS (``torch.addmm``, TF32 off): an independent implementation for the tests."""
         if x.dim() != 2 or x.shape[1] != self.n_in:
             raise ValueError(f"expected (N, {self.n_in}) features")
         prev = torch.backends.cuda.matmul.allow_tf32
@@ -77,14 +112,18 @@ class DenseStack:
 
     def predict(self, x: torch.Tensor) -> torch.Tensor:
         """``model.predict``: float32 softmax probabilities (N, n_classes), on the device."""
-        return torch.softmax(self.logits(x), dim=1)
+        return self._forward(x, False, True, False)[1]
+
+    def decide(self, x: torch.Tensor) -> torch.Tensor:
+        """``np.argmax(model.predict(x), axis=1)`` (VDR/attacks.py:412), int32 on the device."""
+        return self._forward(x, False, False, True)[2]
 
     def accuracy(self, x: torch.Tensor, labels: torch.Tensor) -> float:
         """VDR/attacks.py:412-414; `labels` are class indices or one-hot rows."""
         lab = labels.to(self.device)
         if lab.dim() == 2:
             lab = lab.argmax(dim=1)
-        return float((self.logits(x).argmax(dim=1) == lab).float().mean().item())
+        return float((self.decide(x).long() == lab.long()).float().mean().item())
 
 
 def accuracy_vs_snr(models: Sequence[DenseStack], batch, labels: torch.Tensor, snrs: Sequence[float], plan,

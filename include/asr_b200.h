@@ -313,6 +313,19 @@ int asr_resample_batch(const void* in_dev, int32_t dtype, const int64_t* in_offs
                        int32_t n_taps, int32_t n_pre_remove, float* out_dev, const int64_t* out_offsets_dev,
                        void* stream);
 
+/* ---- classifier forward pass of the accuracy-vs-SNR sweep ----
+ * model.predict + np.argmax of VDR/attacks.py:409-414 for the Dense stack of VDR/train_constraints.py:63-88 (SR twin),
+ * BatchNormalization folded into the following Dense layer by the caller:
+ *   h_0 = x ; h_{l+1} = act(h_l W_l + b_l), act = ReLU except after the last layer ; probs = softmax(h_L).
+ * One fused launch (a CTA takes 32 rows through all layers, activations in shared memory, weights streamed from L2),
+ * float32 FMA accumulation in ascending k like a float32 predict.  x_dev: [n_rows] rows of dims[0] floats with leading
+ * dimension ld_x; weights_dev[l]: [dims[l]][dims[l+1]] row-major (the layout of a Keras Dense kernel); biases_dev[l]:
+ * [dims[l+1]]; dims_host, weights_dev, biases_dev are HOST arrays (of ints / of device pointers); 1..8 layers, layer outputs
+ * 1..1024 wide, the input width bounded by shared memory (2020 for the speaker network fits).  logits_dev / probs_dev ([n_rows][dims[n_layers]]) and argmax_dev ([n_rows]) may each be NULL. */
+int asr_mlp_forward(const float* x_dev, int64_t n_rows, int64_t ld_x, int32_t n_layers, const int32_t* dims_host,
+                    const float* const* weights_dev, const float* const* biases_dev, float* logits_dev, float* probs_dev,
+                    int32_t* argmax_dev, void* stream);
+
 /* ---- measurement probes ----
  * FP32 FMA peak of the device (non-tensor CUDA cores): n_blocks x 512 threads x iters x 64 dependent-chain FMAs, 8 chains
  * per thread.  The caller times the launch with CUDA events: flops = n_blocks * 512 * iters * 64 * 2.  sink_dev receives

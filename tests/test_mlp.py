@@ -83,3 +83,26 @@ def test_accuracy_vs_snr_sweep_runs_on_device():
     r = std.transform(f.reshape(24, -1), out_dtype=torch.float32)
     assert acc[20][0] == model.accuracy(r, labels)
     assert acc[60][0] >= acc[0][0]                       # 60 dB of SNR perturbs the decisions less than 0 dB
+
+
+@pytest.mark.gpu
+def test_mlp_forward_kernel_against_library_gemms_and_odd_shapes():
+    """asr_mlp_forward (one fused launch of this repository's kernel) against the cuBLAS form of the same folded network:
+    row counts that are not multiples of the 16-row tile, a strided input view, narrow and wide layers, 1 and 8 layers."""
+    import torch
+    import asr_b200 as A
+    rng = np.random.default_rng(11)
+    for sizes, n in (((880, 1024, 512, 256, 128, 64, 10), 1037), ((2020, 1024, 512, 256, 128, 64, 20), 50),
+                     ((7, 3), 1), ((33, 1000, 5), 17), ((16, 32, 48, 64, 80, 96, 112, 128, 9), 129)):
+        layers = mr.random_weights(3, sizes)             # (2020 inputs: the speaker network's rows)
+        model = A.DenseStack(layers)
+        wide = torch.from_numpy((2.0 * rng.standard_normal((n, sizes[0] + 5))).astype(np.float32)).cuda()
+        x = wide[:, 2:2 + sizes[0]]                      # leading dimension > width, unaligned start
+        lg = model.logits(x)
+        ref = model.logits_library(x.contiguous())
+        scale = float(ref.abs().max()) + 1e-6
+        assert float((lg - ref).abs().max()) <= 2e-5 * scale + 1e-6
+        pr = model.predict(x)
+        assert torch.allclose(pr.sum(1), torch.ones(n, device=pr.device), atol=1e-5)
+        assert torch.equal(model.decide(x).long(), lg.argmax(1))
+        np.testing.assert_allclose(pr.cpu().numpy(), mr.predict(x.cpu().numpy(), layers), rtol=0, atol=3e-5)
