@@ -3,7 +3,7 @@
 // `model.predict` + argmax of VDR/attacks.py:409-414, as ONE launch.  BatchNormalization is folded into the following Dense layer
 // by the host (asr_b200/mlp.py), so a layer is  h' = act(h W + b)  with W stored like Keras stores a Dense kernel: [in][out].
 //
-// mlp_forward_kernel: a CTA takes 32 rows through every layer.  Activations live in ONE shared-memory buffer, k-major
+// mlp_forward_kernel: a CTA takes up to 32 rows through every layer (the host picks 8..32 so that every SM has a tile in each wave).  Activations live in ONE shared-memory buffer, k-major
 // ([feature][32 rows]: the row values of one input feature are eight 16-byte broadcast loads); a layer's outputs stay in
 // registers until every thread has finished reading its input, then overwrite it; the weights
 // (6.4 MB for the reference's sizes) stay in L2 and are streamed once per CTA with loads that are coalesced along the output
@@ -20,7 +20,7 @@
 
 namespace asr {
 
-constexpr int kMlpRowsMax = 32;       // rows per CTA: 32, or 16 when the input is too wide for 32 rows of it in shared memory
+constexpr int kMlpRowsMax = 32;       // rows per CTA: 8..32 in steps of 4 (shared memory for the widest activation, one tile per SM and wave)
 constexpr int kMlpThreads = 256;
 constexpr int kMlpMaxCols = 4;        // output features per thread: layers up to 1024 wide
 constexpr int kMlpMaxLayers = 8;
@@ -199,21 +199,35 @@ extern "C" int asr_mlp_forward(const float* x_dev, int64_t n_rows, int64_t ld_x,
   mp.ld_x = ld_x;
   mp.logits = logits_dev; mp.probs = probs_dev; mp.argmax = argmax_dev;
   const int widest = std::max(wa, wb);
-  const int rows = static_cast<long long>(widest) * kMlpRowsMax * 4 <= kMaxSmemBytes ? kMlpRowsMax : 16;
-  const long long smem_ll = static_cast<long long>(widest) * rows * static_cast<long long>(sizeof(float));
-  if (smem_ll > kMaxSmemBytes) return bad("the widest activation (16 rows of it) does not fit one SM's shared memory");
-  const int smem_bytes = static_cast<int>(smem_ll);
+  // rows per CTA: as many as fit (fewer weight passes over L2), but no more than it takes to give every SM a tile in each wave
+  int dev = 0, sms = 148;
+  ASR_CUDA_TRY(cudaGetDevice(&dev));
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) { cudaGetLastError(); sms = 148; }
+  int cap = kMlpRowsMax;
+  while (cap > 8 && static_cast<long long>(widest) * cap * 4 > kMaxSmemBytes) cap -= 4;
+  if (static_cast<long long>(widest) * cap * 4 > kMaxSmemBytes) return bad("the widest activation (8 rows of it) does not fit one SM's shared memory");
+  const long long waves = (n_rows + static_cast<long long>(sms) * cap - 1) / (static_cast<long long>(sms) * cap);
+  long long want = (n_rows + sms * waves - 1) / (sms * waves);
+  int rows = static_cast<int>(std::min<long long>(cap, std::max<long long>(8, (want + 3) / 4 * 4)));
+  const int smem_bytes = static_cast<int>(static_cast<long long>(widest) * rows * 4);
   const long long tiles = (n_rows + rows - 1) / rows;
   if (tiles > 0x7fffffffLL) return bad("too many rows");
-  if (rows == 32) {
-    static int granted[kMaxDevices] = {0};
-    ASR_CUDA_TRY(ensure_dyn_smem(mlp_forward_kernel<32>, smem_bytes, 48 * 1024, granted));
-    mlp_forward_kernel<32><<<static_cast<unsigned>(tiles), kMlpThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(mp);
-  } else {
-    static int granted[kMaxDevices] = {0};
-    ASR_CUDA_TRY(ensure_dyn_smem(mlp_forward_kernel<16>, smem_bytes, 48 * 1024, granted));
-    mlp_forward_kernel<16><<<static_cast<unsigned>(tiles), kMlpThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(mp);
+  const cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ASR_MLP_LAUNCH(R)                                                                             \
+  case R: {                                                                                           \
+    static int granted[kMaxDevices] = {0};                                                            \
+    ASR_CUDA_TRY(ensure_dyn_smem(mlp_forward_kernel<R>, smem_bytes, 48 * 1024, granted));             \
+    mlp_forward_kernel<R><<<static_cast<unsigned>(tiles), kMlpThreads, smem_bytes, st>>>(mp);          \
+  } break;
+  switch (rows) {
+    ASR_MLP_LAUNCH(8) ASR_MLP_LAUNCH(12) ASR_MLP_LAUNCH(16) ASR_MLP_LAUNCH(20) ASR_MLP_LAUNCH(24) ASR_MLP_LAUNCH(28)
+    default: {
+      static int granted[kMaxDevices] = {0};
+      ASR_CUDA_TRY(ensure_dyn_smem(mlp_forward_kernel<32>, smem_bytes, 48 * 1024, granted));
+      mlp_forward_kernel<32><<<static_cast<unsigned>(tiles), kMlpThreads, smem_bytes, st>>>(mp);
+    } break;
   }
+#undef ASR_MLP_LAUNCH
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }
