@@ -64,6 +64,8 @@ SIGNATURES = {
     "asr_cmvn_local_message": (C.c_int, [_vp, C.c_size_t, _i32, _i32, _i64, _i32, _vp, _vp]),
     "asr_cmvn_merge": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "asr_cmvn_exchange_nccl": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
+    "asr_cmvn_p2p_region_bytes": (C.c_size_t, [_i32, _i32]),
+    "asr_cmvn_exchange_p2p": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "asr_cmvn_apply2": (C.c_int, [_vp, _i32, _i64, _i32, _i64, C.POINTER(NoiseC), _vp, C.c_size_t, _i32, _i32, _i64, _vp, _vp, _vp,
                                   _vp, _i32, _vp]),
     "asr_tc_selftest": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

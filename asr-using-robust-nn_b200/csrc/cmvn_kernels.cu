@@ -374,6 +374,43 @@ __global__ void __launch_bounds__(kColTile * kRowLanes) apply2_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The path's one exchange as a one-shot all-gather over PEER MEMORY (NVLink / NVSwitch), no NCCL call: every rank owns a
+// symmetric region [2][world][M] float64 receive slots (double-buffered by step parity) + world uint32 flags, mapped into every
+// peer.  CTA p of rank r: store r's message into peer p's slot [parity][r] (remote stores), fence, raise p's flag[r] to the step
+// number; wait until OUR flag[p] has reached the step number; copy slot [parity][p] of our region into the local msgs[p].
+// Step numbers are per-peer counters in local memory (state[p]), so the kernel takes no per-step argument and can sit inside
+// a CUDA graph.  A slot of parity e & 1 is rewritten at step e + 2, which the writer reaches only after it has seen our flag of
+// step e + 1, i.e. after our step-e kernel (which read the slot) has finished.
+__global__ void __launch_bounds__(256) exchange_p2p_kernel(const double* __restrict__ msg, const int M, const int rank, const int world,
+                                                           void* const* __restrict__ regions, unsigned* __restrict__ state,
+                                                           double* __restrict__ msgs, const long long flags_off) {
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const unsigned e = state[p] + 1u;
+  const unsigned par = e & 1u;
+  char* const peer = static_cast<char*>(regions[p]);
+  char* const own = static_cast<char*>(regions[rank]);
+  double* const dst = reinterpret_cast<double*>(peer) + (static_cast<size_t>(par) * world + rank) * M;
+  for (int i = tid; i < M; i += blockDim.x) dst[i] = msg[i];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();                               // the message before the flag, system-wide
+    *reinterpret_cast<volatile unsigned*>(peer + flags_off + 4 * rank) = e;
+    const volatile unsigned* mine = reinterpret_cast<const volatile unsigned*>(own + flags_off + 4 * p);
+    unsigned long long spins = 0;
+    while (static_cast<int>(*mine - e) < 0) {             // peer p's message of this step has not landed yet
+      __nanosleep(64);
+      if (++spins > (1ull << 28)) __trap();               // ~20 s: a peer that never arrives fails the launch instead of hanging
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const double* src = reinterpret_cast<const double*>(own) + (static_cast<size_t>(par) * world + p) * M;
+  for (int i = tid; i < M; i += blockDim.x) msgs[static_cast<size_t>(p) * M + i] = __ldcv(src + i);   // written by a peer: not through L1
+  __syncthreads();
+  if (tid == 0) state[p] = e;
+}
+
 static void slab_shape(int64_t n_rows, int n_cols, int64_t* slabs, int64_t* rows_per_slab) {
   const int col_blocks = (n_cols + kColTile - 1) / kColTile;
   int64_t s = (148 * 8 + col_blocks - 1) / col_blocks;
@@ -581,6 +618,26 @@ extern "C" int asr_cmvn_apply2(const void* x_dev, int32_t dtype, int64_t n_rows,
   else { if (fused) ASR_APPLY2_N(ASR_F64, true); else ASR_APPLY2_N(ASR_F64, false); }
 #undef ASR_APPLY2_N
 #undef ASR_APPLY2
+  ASR_CUDA_TRY(cudaGetLastError());
+  return ASR_OK;
+}
+
+// Region a rank exports to its peers for asr_cmvn_exchange_p2p: [2][world][3*n_cols+1] float64 + world uint32 flags.
+extern "C" size_t asr_cmvn_p2p_region_bytes(int32_t world, int32_t n_cols) {
+  if (world < 1 || n_cols < 1) return 0;
+  const size_t m = 3 * static_cast<size_t>(n_cols) + 1;
+  return ((2 * static_cast<size_t>(world) * m * sizeof(double) + 4 * static_cast<size_t>(world)) + 255) & ~static_cast<size_t>(255);
+}
+
+extern "C" int asr_cmvn_exchange_p2p(const double* msg_dev, int32_t n_cols, int32_t rank, int32_t world, void* const* peer_regions_dev,
+                                     uint32_t* state_dev, double* msgs_dev, void* stream) {
+  if (!msg_dev || !peer_regions_dev || !state_dev || !msgs_dev || n_cols < 1 || world < 1 || rank < 0 || rank >= world) {
+    set_error("asr_cmvn_exchange_p2p: invalid argument");
+    return ASR_ERR_INVALID;
+  }
+  const int M = 3 * n_cols + 1;
+  const long long flags_off = 2LL * world * M * static_cast<long long>(sizeof(double));
+  exchange_p2p_kernel<<<world, 256, 0, as_stream(stream)>>>(msg_dev, M, rank, world, peer_regions_dev, state_dev, msgs_dev, flags_off);
   ASR_CUDA_TRY(cudaGetLastError());
   return ASR_OK;
 }

@@ -9,6 +9,7 @@ reference's ``(N, n_mfcc*T)`` feature layout out.  torch is plumbing only
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -498,6 +499,14 @@ class Standardizer:
         self._ws: Optional[torch.Tensor] = None
         self._slabs = (0, 0)
         self._n_local = 0
+        # transport of the one exchange: "p2p" (one-shot all-gather over peer memory, asr_cmvn_exchange_p2p: no NCCL call,
+        # capturable in a CUDA graph) when the ranks' symmetric regions can be set up, else "nccl" (torch.distributed all-gather)
+        self.exchange_transport = "none"
+        self._p2p = None
+        if distributed:
+            self.exchange_transport = "nccl"
+            if os.environ.get("ASR_B200_P2P_EXCHANGE", "1") != "0":
+                self._setup_p2p()
 
     @property
     def n_total(self) -> int:
@@ -558,10 +567,43 @@ class Standardizer:
             check(lib.asr_cmvn_local_message(ws.data_ptr(), ws.numel(), self._slabs[0], self._slabs[1], self._n_local, self.n_cols,
                                              self.msg.data_ptr(), _stream()), "asr_cmvn_local_message")
 
+    def _setup_p2p(self) -> None:
+        """Symmetric regions of all ranks mapped into this process (torch's symmetric memory is the plumbing: allocation,
+        handle exchange, peer mapping); any failure leaves the NCCL transport in place."""
+        import torch.distributed as dist
+        try:
+            if dist.get_backend(self.group) != "nccl" or self.device.type != "cuda":
+                return
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else dist.group.WORLD
+            w, r = dist.get_world_size(grp), dist.get_rank(grp)
+            nbytes = int(lib.asr_cmvn_p2p_region_bytes(w, self.n_cols))
+            region = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            region.zero_()
+            torch.cuda.synchronize(self.device)
+            hdl = symm.rendezvous(region, grp)
+            state = torch.zeros(w, dtype=torch.int32, device=self.device)
+            msgs = torch.zeros((w, self.msg.numel()), dtype=torch.float64, device=self.device)
+            ptrs = torch.tensor([int(a) for a in hdl.buffer_ptrs], dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(grp)                                   # every region is zeroed and mapped before anybody writes
+            self._p2p = {"region": region, "hdl": hdl, "state": state, "ptrs": ptrs, "rank": r, "world": w}
+            self.msgs = msgs
+            self.exchange_transport = "p2p"
+        except Exception as e:                                  # noqa: BLE001
+            self._p2p = None
+            self._p2p_error = str(e).splitlines()[0][:200] if str(e) else type(e).__name__
+
     def exchange(self) -> None:
         """The one collective of the path: every rank's message to every rank."""
         if not self.distributed:
             self.msgs = self.msg.view(1, -1)
+            return
+        if self._p2p is not None:
+            q = self._p2p
+            with torch.cuda.device(self.device):
+                check(lib.asr_cmvn_exchange_p2p(self.msg.data_ptr(), self.n_cols, q["rank"], q["world"], q["ptrs"].data_ptr(),
+                                                q["state"].data_ptr(), self.msgs.data_ptr(), _stream()), "asr_cmvn_exchange_p2p")
             return
         import torch.distributed as dist
         w = self._world()

@@ -15,9 +15,10 @@ enqueued in front of THIS step's MFCC launch, so the host chain of step i+1 runs
 ``sigma_mode="device"`` evaluates the chain in float64 on the device (within 1 ulp of the host chain, not equal).
 
 The launches of one step are short (tens of microseconds each) and their number is fixed, so the step is
-captured once per batch buffers in CUDA graphs and replayed: a single graph for the whole step on one GPU; when clips are
-sharded over several GPUs two graphs separated by the ONE collective of the path, the all-gather of the ranks'
-standardisation messages (`Standardizer.exchange`).
+captured once per batch buffers in CUDA graphs and replayed: a single graph for the whole step, on one GPU and when clips
+are sharded over several GPUs - the ONE exchange of the path, the all-gather of the ranks' standardisation messages
+(`Standardizer.exchange`), is then a peer-memory kernel of this library inside the graph (with the NCCL fallback transport:
+two graphs with the collective between them).
 """
 from __future__ import annotations
 
@@ -35,7 +36,7 @@ from .params import MfccParams
 # standardisation: pass 1, pass 2, apply (single GPU; sharded: + message and merge); + power (and the sigma kernel in
 # device mode, the babble stream with babble noise) when noisy; the e2e step adds randn
 LAUNCHES_CMVN = 3
-LAUNCHES_CMVN_SHARDED = 5
+LAUNCHES_CMVN_SHARDED = 6       # pass 1, pass 2, message, peer-memory exchange, merge, apply
 LAUNCHES_NOISE = 1
 
 
@@ -60,9 +61,11 @@ class NoisyFeaturePipeline:
         self.distributed = distributed
         self.std = Standardizer(self.D, device=self.device, group=group, distributed=distributed)
         self.use_graphs = use_graphs
-        # opt-in (ASR_B200_CAPTURE_COLLECTIVES=1): capture the NCCL all-reduces inside the step's graph.  Measured: identical
-        # rows, no gain at 8 GPUs (0.891 vs 0.888 ms per step) and the process group then takes minutes to tear down at exit.
+        # NCCL transport, opt-in (ASR_B200_CAPTURE_COLLECTIVES=1): capture the all-gather inside the step's graph.  Measured:
+        # identical rows, no gain at 8 GPUs and the process group then takes minutes to tear down at exit.
         self.capture_collectives = os.environ.get("ASR_B200_CAPTURE_COLLECTIVES", "0") == "1"
+        if self.std.exchange_transport == "p2p":
+            self.capture_collectives = True     # the peer-memory exchange is one kernel of this library: the sharded step is ONE graph
         if sigma_mode not in ("host", "device"):
             raise ValueError("sigma_mode must be 'host' (the reference's chain, bit-exact) or 'device'")
         self.sigma_mode = sigma_mode

@@ -289,6 +289,16 @@ int asr_cmvn_local_message(const void* workspace_dev, size_t workspace_bytes, in
  * cannot mix; ASR_ERR_INVALID if no NCCL is loaded.  Replaces the reduction hidden in StandardScaler().fit of
  * standardize_dataset (VDR/attacks.py:48-69) when the rows are sharded over GPUs. */
 int asr_cmvn_exchange_nccl(void* nccl_comm, const double* msg_dev, double* msgs_dev, int32_t n_cols, void* stream);
+/* The exchange without NCCL: a one-shot all-gather over PEER MEMORY (NVLink / NVSwitch), one small kernel, capturable in a
+ * CUDA graph (it takes no per-step argument).  Every rank allocates a region of asr_cmvn_p2p_region_bytes(world, n_cols) bytes,
+ * ZEROED once, and maps it into its peers (cudaIpc*, cuMem fabric handles, or torch's symmetric memory - the caller's
+ * plumbing); `peer_regions_dev` is a DEVICE array [world] with every rank's region as addressed from this process (entry
+ * `rank` = the own region).  `state_dev`: this rank's LOCAL uint32[world] step counters, zeroed once together with the regions
+ * (all ranks must have zeroed before the first call: one barrier at set-up).  Every rank calls this once per step; on return
+ * (in stream order) msgs_dev[world][3*n_cols+1] holds all messages in rank order, like asr_cmvn_exchange_nccl. */
+size_t asr_cmvn_p2p_region_bytes(int32_t world, int32_t n_cols);
+int asr_cmvn_exchange_p2p(const double* msg_dev, int32_t n_cols, int32_t rank, int32_t world, void* const* peer_regions_dev,
+                          uint32_t* state_dev, double* msgs_dev, void* stream);
 int asr_cmvn_merge(const double* msgs_dev, int32_t world, int32_t n_cols, double* mean_dev, double* var_dev,
                    double* scale_dev, double* n_total_dev /* may be NULL */, void* stream);
 int asr_cmvn_apply2(const void* x_dev, int32_t dtype, int64_t n_rows, int32_t n_cols, int64_t ld, const asr_noise* row_noise,

@@ -52,7 +52,7 @@ for noisy in (False, True):
         m2, v2 = pipe.std.mean.double(), pipe.std.var.double()
         rm = ((m1 - m2).abs() / (m1.abs() + 1e-300)).max().item()
         rv = ((v1 - v2).abs() / (v1.abs() + 1e-300)).max().item()
-        print(f"world={world} noisy={noisy} clips={N}: max |sharded - single| over rows = {d:.3e}; "
+        print(f"world={world} noisy={noisy} clips={N} exchange={pipe.std.exchange_transport} graphs/step={len(next(iter(pipe._cache.values())).graphs)}: max |sharded - single| over rows = {d:.3e}; "
               f"mean rel diff {rm:.2e}, var rel diff {rv:.2e}; rows bit-equal: {bool(torch.equal(got, ref))}", flush=True)
         assert d <= 1e-5 and rv <= 1e-9, "sharded rows differ from the single-GPU rows"
     dist.barrier()
