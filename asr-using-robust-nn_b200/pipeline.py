@@ -76,7 +76,8 @@ class NoisyFeaturePipeline:
 
     def launches_per_step(self, noisy: bool, standardize: bool = True) -> int:
         noise = (LAUNCHES_NOISE + (1 if self.sigma_mode == "device" else 0)) if noisy else 0
-        cmvn = (LAUNCHES_CMVN_SHARDED if self.distributed else LAUNCHES_CMVN) if standardize else 0
+        sharded = LAUNCHES_CMVN_SHARDED - (0 if self.std.exchange_transport == "p2p" else 1)   # the NCCL all-gather is not a kernel of this library
+        cmvn = (sharded if self.distributed else LAUNCHES_CMVN) if standardize else 0
         return self.plan.launches(noisy) + noise + cmvn
 
     # ---- sigma: device power -> host chain -> device sigma, one step ahead when the caller prefetches -----------
