@@ -571,9 +571,9 @@ class Standardizer:
         """Symmetric regions of all ranks mapped into this process (torch's symmetric memory is the plumbing: allocation,
         handle exchange, peer mapping); any failure leaves the NCCL transport in place."""
         import torch.distributed as dist
+        if dist.get_backend(self.group) != "nccl" or self.device.type != "cuda":
+            return
         try:
-            if dist.get_backend(self.group) != "nccl" or self.device.type != "cuda":
-                return
             import torch.distributed._symmetric_memory as symm
             grp = self.group if self.group is not None else dist.group.WORLD
             w, r = dist.get_world_size(grp), dist.get_rank(grp)
@@ -593,6 +593,17 @@ class Standardizer:
         except Exception as e:                                  # noqa: BLE001
             self._p2p = None
             self._p2p_error = str(e).splitlines()[0][:200] if str(e) else type(e).__name__
+        # every rank must use the same transport: agree (a rank whose set-up failed takes everybody to NCCL)
+        try:
+            ok = torch.tensor([1 if self._p2p is not None else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self._p2p = None
+        except Exception:                                       # noqa: BLE001
+            self._p2p = None
+        if self._p2p is None:
+            self.exchange_transport = "nccl"
+            self.msgs = self.msg.view(1, -1)
 
     def exchange(self) -> None:
         """The one collective of the path: every rank's message to every rank."""
