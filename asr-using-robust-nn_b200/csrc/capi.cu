@@ -1049,6 +1049,33 @@ bool tiles_path_usable(const asr_plan* plan, int n_clips, int max_length, int dt
   return tiles_layout(plan, dtype, noise_mode, lo);
 }
 
+// Per-clip kernel (mfcc_kernel.cu): dynamic shared memory of one CTA that keeps the log-mel rows of t_cap frames
+long long clip_smem_bytes(const asr_plan* plan, int t_cap, bool want_cbuf) {
+  const asr_mfcc_params& p = plan->prm;
+  const int half = p.delta_orders > 0 ? p.delta_width / 2 : 0;
+  long long off = plan->blob_floats;
+  off += static_cast<long long>(plan->fb) * plan->frame_stride;
+  off += static_cast<long long>(plan->fb) * plan->part_pitch;
+  off += static_cast<long long>(t_cap) * plan->lm_pitch;
+  off += want_cbuf ? static_cast<long long>(p.n_mfcc) * round4(t_cap + 2 * half + 1) : 0;
+  off += 32;
+  return off * 4;
+}
+// Clips whose log-mel matrix does not fit one CTA: chunks of frames per CTA + the cepstra kernels of the block-pipelined
+// paths (through the log-mel workspace) instead of a thread-block cluster per clip.  `chunk` = frames per CTA (0: not used).
+int clip_chunk_frames(const asr_plan* plan, int max_length) {
+  const asr_mfcc_params& p = plan->prm;
+  if (!plan->cep_dev || p.n_mfcc > 40) return 0;                          // no cepstra tables for the workspace kernels
+  if (std::getenv("ASR_B200_CLIP_CLUSTERS")) return 0;                    // experiments: the cluster form
+  const int t_all = std::max(1, asr_plan_num_frames(plan, max_length));
+  if (clip_smem_bytes(plan, t_all, p.delta_orders > 0) <= kMaxSmemBytes) return 0;   // one CTA per clip is enough
+  const int n_chunks = (t_all + 127) / 128;
+  int fc = (t_all + n_chunks - 1) / n_chunks;
+  fc = (fc + 15) & ~15;                                                    // whole warp iterations (8 warps x 2 frames)
+  while (fc > 16 && clip_smem_bytes(plan, fc, false) > kMaxSmemBytes) fc -= 16;
+  return clip_smem_bytes(plan, fc, false) <= kMaxSmemBytes ? fc : 0;
+}
+
 }  // namespace
 
 extern "C" size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips, int32_t max_length) {
@@ -1060,7 +1087,8 @@ extern "C" size_t asr_mfcc_workspace_bytes(const asr_plan* plan, int32_t n_clips
   if (tcdft_path_usable(plan, n_clips, max_length, ASR_NOISE_NONE, &dfl)) return ws_layout(plan, n_clips, max_length).bytes;
   if (!frames_path_usable(plan, n_clips, max_length, ASR_F64, ASR_NOISE_NONE, false, &lo) &&
       !tiles_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tlo) &&
-      !tc_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tcl)) return 0;
+      !tc_path_usable(plan, n_clips, max_length, ASR_I16, ASR_NOISE_NONE, true, &tcl))
+    return clip_chunk_frames(plan, max_length) > 0 ? ws_layout(plan, n_clips, max_length).bytes : 0;
   return ws_layout(plan, n_clips, max_length).bytes;
 }
 
@@ -1386,6 +1414,55 @@ static int launch_common(const asr_plan* plan, const void* audio_dev, int32_t dt
     k.cluster_size = cs;
     return static_cast<long long>(off) * 4;
   };
+  // ---- long clips: chunks of frames per CTA, log-mel rows through the workspace, cepstra kernels of the pipelined paths ----
+  if (const int fc = clip_chunk_frames(plan, max_length)) {
+    const long long frames = static_cast<long long>(n_clips) * t_all;
+    if (frames < (1ll << 31) - 64) {
+      const WsLayout wl = ws_layout(plan, n_clips, max_length);
+      char* ws = static_cast<char*>(workspace_dev);
+      if (ws) {
+        if (workspace_bytes < wl.bytes || (reinterpret_cast<uintptr_t>(ws) & 15)) return bad("workspace too small or not 16-byte aligned");
+      } else {
+        asr_plan* mp = const_cast<asr_plan*>(plan);                // plan-owned scratch (documented: no concurrent launches)
+        if (mp->ws_bytes < wl.bytes) {
+          if (mp->ws_dev) ASR_CUDA_TRY(cudaFree(mp->ws_dev));
+          mp->ws_dev = nullptr; mp->ws_bytes = 0;
+          ASR_CUDA_TRY(cudaMalloc(&mp->ws_dev, wl.bytes));
+          mp->ws_bytes = wl.bytes;
+        }
+        ws = static_cast<char*>(mp->ws_dev);
+      }
+      FParams fp;
+      std::memset(&fp, 0, sizeof(fp));
+      fp.audio = audio_dev; fp.offsets = kp.offsets; fp.lengths = lengths_dev; fp.dtype = dtype; fp.n_clips = n_clips;
+      fp.noise_mode = ASR_NOISE_NONE;
+      fp.out = out_dev; fp.out_f64 = out_dtype == ASR_F64; fp.out_frames = out_frames;
+      fp.out_rows = p.n_mfcc * (1 + p.delta_orders); fp.logmel_only = logmel_only; fp.status = status_dev;
+      fp.n_fft = p.n_fft; fp.hop = p.hop_length; fp.pad = plan->pad; fp.pad_mode = p.pad_mode;
+      fp.n_mels = p.n_mels; fp.n_mfcc = p.n_mfcc; fp.delta_orders = p.delta_orders; fp.delta_width = p.delta_width;
+      fp.top_db = p.top_db; fp.amin = p.amin; fp.preemph = p.preemph;
+      fp.fstart = reinterpret_cast<int*>(ws + wl.off_fstart);
+      fp.nframes = reinterpret_cast<int*>(ws + wl.off_nframes);
+      fp.clipmax = reinterpret_cast<float*>(ws + wl.off_clipmax);
+      fp.lm = reinterpret_cast<float*>(ws + wl.off_lm);
+      fp.lm_stride = static_cast<int>((frames + 31) & ~31LL);
+      fp.cep_blob = reinterpret_cast<const float4*>(plan->cep_dev);
+      fp.cep_tab_f4 = plan->cep_tab_f4; fp.cep_off_cbuf = plan->cep_off_cbuf; fp.cep_off_taps = plan->cep_off_taps;
+      fp.cep_off_col = plan->cep_smem_bytes / 4;
+      fp.cep_small = (p.n_mels <= 32 && plan->h_dct_t.size() <= static_cast<size_t>(kCepSmallTab) && p.delta_orders == 0 && !logmel_only) ? 1 : 0;
+      if (fp.cep_small) std::memcpy(fp.cep_dct, plan->h_dct_t.data(), plan->h_dct_t.size() * sizeof(float));
+      layout(1, kp);                                               // offsets of the fixed parts
+      kp.t_cap = fc; kp.cluster_size = 1;
+      kp.sm_cbuf = kp.sm_lm + fc * plan->lm_pitch; kp.sm_red = kp.sm_cbuf;       // (no cepstra buffer in this mode)
+      kp.chunk_mode = 1; kp.n_chunks = (t_all + fc - 1) / fc;
+      kp.lm_global = fp.lm; kp.lm_stride = fp.lm_stride; kp.fstart = fp.fstart;
+      const long long chunk_smem = clip_smem_bytes(plan, fc, false);
+      ASR_CUDA_TRY(launch_frame_prefix(fp, as_stream(stream)));
+      ASR_CUDA_TRY(launch_mfcc(kp, static_cast<int>(chunk_smem), as_stream(stream)));
+      ASR_CUDA_TRY(launch_cepstra_tail(fp, plan->cep_smem_bytes + 4 * 128 * p.n_mels, t_all, as_stream(stream)));
+      return ASR_OK;
+    }
+  }
   int cs = 1;
   long long smem_bytes = layout(cs, kp);
   while (smem_bytes > kMaxSmemBytes && cs < 16) { cs *= 2; smem_bytes = layout(cs, kp); }

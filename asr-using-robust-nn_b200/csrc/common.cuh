@@ -88,6 +88,14 @@ struct KParams {
   int sm_frames, sm_part, sm_lm, sm_cbuf, sm_red;
   int t_cap;          // frame capacity of one CTA's log-mel buffer
   int cluster_size;   // CTAs per clip (thread-block cluster), 1..16
+  // chunk mode (clips whose log-mel matrix exceeds one CTA's shared memory): grid (clip, chunk of `t_cap` frames), no cluster;
+  // a CTA writes its chunk's log-mel rows to the transposed workspace lm_global[filter][fstart[clip] + frame] and the
+  // cepstra kernels of the block-pipelined paths finish the clip (clip maximum, clamp, DCT, deltas, padding)
+  int chunk_mode;
+  int n_chunks;       // chunks per clip of the longest clip
+  float* lm_global;
+  int lm_stride;
+  const int* fstart;
   int vec_ok;         // audio (and noise) pointers are 16-byte aligned: vector staging allowed
   int cbuf_pitch;
 };

@@ -237,9 +237,9 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(c
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cs = kp.cluster_size;
-  const int rank = cs > 1 ? static_cast<int>(cluster.block_rank()) : 0;
-  const int b = blockIdx.x / cs;
+  const int cs = kp.chunk_mode ? 1 : kp.cluster_size;
+  const int rank = kp.chunk_mode ? static_cast<int>(blockIdx.x % kp.n_chunks) : (cs > 1 ? static_cast<int>(cluster.block_rank()) : 0);
+  const int b = kp.chunk_mode ? static_cast<int>(blockIdx.x / kp.n_chunks) : static_cast<int>(blockIdx.x / cs);
   const int L = kp.lengths[b];
   const long long base = kp.offsets[b];
   const int rows = kp.logmel_only ? kp.n_mels : kp.out_rows;
@@ -254,13 +254,15 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(c
     st = ASR_CLIP_TOO_FEW_FRAMES;
   if (tid == 0 && rank == 0 && kp.status) kp.status[b] = st;
   if (st != ASR_CLIP_OK) {
+    if (kp.chunk_mode) return;                      // the cepstra kernel writes the zero rows of a clip without frames
     if (rank == 0)
       for (int i = tid; i < rows * kp.out_frames; i += kThreads) store_out(kp, out_base + i, 0.0f);
     return;
   }
-  const int FC = (T + cs - 1) / cs;                 // frames per CTA of this clip
+  const int FC = kp.chunk_mode ? kp.t_cap : (T + cs - 1) / cs;   // frames per CTA of this clip
   const int f0 = min(T, rank * FC), f1 = min(T, f0 + FC);
   const int nF = f1 - f0;
+  if (kp.chunk_mode && nF <= 0) return;              // (uniform over the CTA) a clip shorter than this chunk's first frame
 
   // ---- tables: global blob -> shared ----
   {
@@ -393,6 +395,16 @@ __global__ void __launch_bounds__(kThreads, (NFFT == 512 ? 3 : 1)) mfcc_kernel(c
     __syncwarp();                                     // partials / frame buffers are reused next iteration
   }
 
+  if (kp.chunk_mode) {
+    // ---- chunk mode: the chunk's log-mel rows -> transposed workspace (threads <-> frames: coalesced along time) ----
+    __syncthreads();
+    const long long g0 = static_cast<long long>(kp.fstart[b]) + f0;
+    for (int i = warp; i < kp.n_mels; i += kWarps) {
+      float* dst = kp.lm_global + static_cast<long long>(i) * kp.lm_stride + g0;
+      for (int t = lane; t < nF; t += 32) dst[t] = s_lm[t * kp.lm_pitch + i];
+    }
+    return;
+  }
   // ---- clip-wide max (power_to_db top_db spans every frame of the call) ----
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
@@ -565,7 +577,7 @@ template <int NFFT, int DT>
 static cudaError_t launch_one(const KParams& kp, int smem_bytes, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(static_cast<unsigned>(kp.n_clips) * kp.cluster_size);
+  cfg.gridDim = dim3(static_cast<unsigned>(kp.n_clips) * (kp.chunk_mode ? kp.n_chunks : kp.cluster_size));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;

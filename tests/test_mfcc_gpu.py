@@ -296,13 +296,20 @@ def test_unaligned_packing(noisy):
         _close(out[i:i + 1, :, :r.shape[1]].cpu().numpy(), r[None], atol=3e-3)
 
 
+@pytest.mark.parametrize("form", ["chunks", "clusters"])
 @pytest.mark.parametrize("variant", ["mfcc", "logmel", "no_delta"])
-def test_c5_full_length_cluster_path(variant):
+def test_c5_full_length_cluster_path(variant, form, monkeypatch):
     """BASELINE configs[4] at its stated size: 10 s clips (160 000 samples, 1001 frames x 80 mel = 320 KB of log-mel rows,
-    more than one SM holds) - the per-clip kernel spreads a clip over a thread-block cluster (clip maximum and delta halo
-    through distributed shared memory).  Plus one shorter clip in the same batch (ragged: its cluster has idle CTAs)."""
+    more than one SM holds).  Default form ("chunks"): the per-clip kernel takes chunks of frames per CTA, writes the log-mel
+    rows to the workspace and the cepstra kernels of the pipelined paths finish the clip.  "clusters"
+    (ASR_B200_CLIP_CLUSTERS): a clip spread over a thread-block cluster, clip maximum and delta halo through distributed
+    shared memory.  Plus one shorter clip in the same batch (ragged: idle chunks / idle CTAs of its cluster)."""
     import asr_b200 as A
     lr = _o()
+    if form == "clusters":
+        monkeypatch.setenv("ASR_B200_CLIP_CLUSTERS", "1")
+    else:
+        monkeypatch.delenv("ASR_B200_CLIP_CLUSTERS", raising=False)
     clips = synth_clips(3, 160000, 16000, 55, lengths=[160000, 160000, 47111])
     P = A.C5 if variant != "no_delta" else A.C5.replace(delta_orders=0)
     Pr = lr.C5 if variant != "no_delta" else lr.C5.replace(delta_orders=0)
