@@ -40,6 +40,17 @@ def test_library_exports_every_declared_symbol(lib):
     assert not missing, f"declared in the header but not exported: {missing}"
 
 
+def test_checking_build_is_not_stale():
+    """libasr_b200_dbg.so (make debug, loaded by tests/test_tile_debug_gpu.py) exports the same surface as the product library."""
+    dbg = os.path.join(os.path.dirname(LIB), "libasr_b200_dbg.so")
+    if not os.path.exists(dbg):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.dirname(LIB), "-j4", "debug"], check=True)
+    d = ctypes.CDLL(dbg)
+    missing = [n for n in declared_functions() if not hasattr(d, n)]
+    assert not missing, f"stale checking build (make -C asr-using-robust-nn_b200 debug): {missing}"
+
+
 def test_ctypes_binding_matches_header():
     from asr_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_functions()
