@@ -7,8 +7,8 @@ Drop-in for the data-parallel hot path of fmazilu/ASR-using-robust-NN:
 * ``asr_b200.speaker.*`` mirror ``Speaker recognition/*``;
 * ``asr_b200.frontend`` is the batched array-in API they delegate to;
 * all arithmetic of the hot path runs in ``libasr_b200.so`` (hand-written CUDA, C-ABI in ``include/asr_b200.h``);
-* ``asr_b200.mlp`` is the classifier's forward pass for the accuracy-vs-SNR sweep (plain
-  library GEMMs, BatchNorm folded).
+* ``asr_b200.mlp`` is the classifier's forward pass for the accuracy-vs-SNR sweep (BatchNorm
+  folded, one fused launch of ``asr_mlp_forward``).
 """
 from ._lib import AsrError, LIB_PATH  # noqa: F401
 from .params import MfccParams, REF_VDR, REF_SR, C1, C3, C5, PRESETS  # noqa: F401

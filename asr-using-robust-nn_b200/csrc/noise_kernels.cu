@@ -19,7 +19,9 @@ namespace asr {
 // lanes, lane j of a group owning numpy's accumulator r[j] - and folds the leaf sums with a
 // (value, depth) stack: two entries of equal depth are siblings and merge into their parent, which is
 // exactly the order numpy adds them in.  No shared-memory staging, no CTA barriers.
-constexpr int kPowWarps = 12;
+constexpr int kPowWarpsWide = 12;  // CTA shapes of clip_power_kernel: one CTA of 12 warps per SM, or three of 4 (same warps per SM, finer grain)
+constexpr int kPowWarpsNarrow = 4;
+constexpr int kPowDefaultWarps = kPowWarpsNarrow;   // measured: 0.062 ms against 0.073 ms per 8192 one-second clips stand-alone, and the better partner of a step's tail kernels (profiles/r2_power_overlap_ab.txt)
 constexpr int kPowStack = 40;     // > depth of the tree for any int32 length
 
 struct PowScratch {               // per warp
@@ -455,7 +457,7 @@ __device__ void clip_power_perfect(const void* __restrict__ audio, const long lo
 }
 
 // Persistent CTAs: the leaf table is built once per CTA, every warp then takes clips b0 + warp, b0 + 8 * gridDim.x ...
-template <int DT>
+template <int DT, int kPowWarps>
 __global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* __restrict__ audio,
                                                                      const long long* __restrict__ offsets,
                                                                      const int* __restrict__ lengths,
@@ -694,6 +696,22 @@ using namespace asr;
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+template <int NW>
+static int launch_clip_power(const void* audio_dev, int32_t dtype, const long long* off, const int32_t* lengths_dev, int32_t n_clips,
+                             float* power_dev, int aligned, void* stream) {
+  const int blocks = std::min((n_clips + NW - 1) / NW, 148 * (kPowWarpsWide / NW));   // persistent: the SMs' worth of CTAs
+  constexpr int smem = NW * 2 * kPowPerfTile * static_cast<int>(sizeof(float));
+  static int granted_i16[kMaxDevices] = {0}, granted_f32[kMaxDevices] = {0};
+  ASR_CUDA_TRY(ensure_dyn_smem(clip_power_kernel<ASR_I16, NW>, smem, 0, granted_i16));
+  ASR_CUDA_TRY(ensure_dyn_smem(clip_power_kernel<ASR_F32, NW>, smem, 0, granted_f32));
+  if (dtype == ASR_I16)
+    clip_power_kernel<ASR_I16, NW><<<blocks, NW * 32, smem, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
+  else
+    clip_power_kernel<ASR_F32, NW><<<blocks, NW * 32, smem, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
+  ASR_CUDA_TRY(cudaGetLastError());
+  return ASR_OK;
+}
+
 extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev,
                               const int32_t* lengths_dev, int32_t n_clips, float* power_dev, void* stream) {
   if (!audio_dev || !offsets_dev || !lengths_dev || !power_dev || n_clips < 0) {
@@ -705,19 +723,14 @@ extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_
     return ASR_ERR_INVALID;
   }
   if (n_clips == 0) return ASR_OK;
-  const int blocks = std::min((n_clips + kPowWarps - 1) / kPowWarps, 148);          // persistent: one CTA per SM
   const long long* off = reinterpret_cast<const long long*>(offsets_dev);
   const int aligned = (reinterpret_cast<uintptr_t>(audio_dev) & 15) == 0 ? 1 : 0;
-  constexpr int smem = kPowWarps * 2 * kPowPerfTile * static_cast<int>(sizeof(float));
-  static int granted_i16[kMaxDevices] = {0}, granted_f32[kMaxDevices] = {0};
-  ASR_CUDA_TRY(ensure_dyn_smem(clip_power_kernel<ASR_I16>, smem, 0, granted_i16));
-  ASR_CUDA_TRY(ensure_dyn_smem(clip_power_kernel<ASR_F32>, smem, 0, granted_f32));
-  if (dtype == ASR_I16)
-    clip_power_kernel<ASR_I16><<<blocks, kPowWarps * 32, smem, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
-  else
-    clip_power_kernel<ASR_F32><<<blocks, kPowWarps * 32, smem, as_stream(stream)>>>(audio_dev, off, lengths_dev, power_dev, n_clips, aligned);
-  ASR_CUDA_TRY(cudaGetLastError());
-  return ASR_OK;
+  // CTA shape: 12 warps x one CTA per SM, or 4 warps x three CTAs per SM - the same warps per SM; the narrow shape needs a
+  // third of the shared memory per CTA, so its CTAs find room beside the tail kernels of a step when the pass runs on a side
+  // stream (asr_b200.pipeline).  ASR_B200_POW_WARPS = 12 | 4 overrides the default.
+  static const int shape = [] { const char* e = std::getenv("ASR_B200_POW_WARPS"); return e ? std::atoi(e) : kPowDefaultWarps; }();
+  if (shape == kPowWarpsNarrow) return launch_clip_power<kPowWarpsNarrow>(audio_dev, dtype, off, lengths_dev, n_clips, power_dev, aligned, stream);
+  return launch_clip_power<kPowWarpsWide>(audio_dev, dtype, off, lengths_dev, n_clips, power_dev, aligned, stream);
 }
 
 extern "C" int asr_snr_sigma(const float* power_dev, float target_snr_db, double* sigma_dev, int32_t n_clips,

@@ -11,7 +11,9 @@ for bit, its 4*B bytes go to pinned host memory, ``frontend.snr_sigma_host`` run
 ``attacks.py:235-241`` on it (numpy's log10, libm's powf) and sigma goes back - np.log10 / powf are not correctly
 rounded and differ between hosts, so only the host can reproduce them.  To keep that round trip off the critical
 path a caller that knows its next batch passes ``prefetch=``: the power launch and read-back of the NEXT step are
-enqueued in front of THIS step's MFCC launch, so the host chain of step i+1 runs while the GPU is busy with step i.
+enqueued on a side stream right after THIS step's launches (``ASR_B200_POWER_STREAM=0``: on the caller's stream, in front
+of this step's MFCC launch), so the host chain of step i+1 runs while the GPU is busy with step i and the power pass -
+a streaming read of the audio - shares the device with the step's launches instead of standing in front of them.
 ``sigma_mode="device"`` evaluates the chain in float64 on the device (within 1 ulp of the host chain, not equal).
 
 The launches of one step are short (tens of microseconds each) and their number is fixed, so the step is
@@ -44,7 +46,8 @@ class _StepGraphs:
     """Captured launch groups of one step for fixed buffers."""
 
     def __init__(self):
-        self.graphs = []       # [g1] or [g1, g2, g3]
+        self.graphs = []       # replayed in order
+        self.exchange_after = -1   # index of the graph followed by the (uncaptured) NCCL all-gather
         self.out = None
         self.keep = None       # tensors the graphs reference
 
@@ -70,6 +73,16 @@ class NoisyFeaturePipeline:
             raise ValueError("sigma_mode must be 'host' (the reference's chain, bit-exact) or 'device'")
         self.sigma_mode = sigma_mode
         self._sig = None             # host-sigma state: two pinned slots, one device sigma vector
+        # the power pass of a prefetched batch: 1 (default) = on a side stream, free to start as soon as the step has been
+        # launched; 0 = on the caller's stream, in front of the step's MFCC launch.  Measured on the default step
+        # (profiles/r2_power_overlap_ab.txt): 0.813 against 0.846 ms; releasing the pass only behind the step's MFCC launches
+        # (two graphs with an event between them) 0.830; a 2-warp launch shaped to sit beside the persistent MFCC kernel > 1.5
+        self._pow_mode = int(os.environ.get("ASR_B200_POWER_STREAM", "1"))
+        if self._pow_mode not in (0, 1):
+            raise ValueError("ASR_B200_POWER_STREAM must be 0 or 1")
+        self._pow_stream = torch.cuda.Stream(self.device) if self._pow_mode != 0 else None
+        self._pow_entry = torch.cuda.Event()
+        self._pow_last = None        # event of the last side-stream power pass (join())
         self._feats = None
         self._cache: dict = {}
         self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch (eager steps only)
@@ -88,12 +101,13 @@ class NoisyFeaturePipeline:
     def _sig_state(self, B: int):
         st = self._sig
         if st is None or st["cap"] < B:
+            # three slots: the pass being consumed, and up to two prefetched ones (a caller may run two steps ahead)
             st = {"cap": B, "turn": 0, "pending": {},
                   "sigma_dev": torch.empty(B, dtype=torch.float64, device=self.device),
                   "slots": [{"P_dev": torch.empty(B, dtype=torch.float32, device=self.device),
                              "P_host": torch.empty(B, dtype=torch.float32).pin_memory(),
                              "sig_host": torch.empty(B, dtype=torch.float64).pin_memory(),
-                             "event": torch.cuda.Event()} for _ in range(2)]}
+                             "event": torch.cuda.Event()} for _ in range(3)]}
             self._sig = st
             self._cache.clear()                            # captured graphs reference the old sigma vector
         return st
@@ -102,11 +116,16 @@ class NoisyFeaturePipeline:
         """Enqueue power (+ the babble stream and its power) and the read-back of `batch` on the current stream; returns the slot."""
         st = self._sig_state(batch.n_clips)
         k = st["turn"]
-        st["turn"] ^= 1
-        for key in [key for key, v in st["pending"].items() if v == k]:
-            del st["pending"][key]                         # a prefetch that was never consumed loses its slot
+        st["turn"] = (k + 1) % len(st["slots"])
+        for key in list(st["pending"]):
+            q = [v for v in st["pending"][key] if v != k]  # a prefetch that was never consumed loses its slot
+            if q:
+                st["pending"][key] = q
+            else:
+                del st["pending"][key]
         sl = st["slots"][k]
         B = batch.n_clips
+        torch.cuda.current_stream(self.device).wait_event(sl["event"])   # an earlier pass into this slot (possibly on the other stream) is over
         clip_power(batch, out=sl["P_dev"])
         sl["P_host"][:B].copy_(sl["P_dev"][:B], non_blocking=True)
         if babble:
@@ -120,11 +139,31 @@ class NoisyFeaturePipeline:
         sl["event"].record()
         return k
 
-    def prefetch_power(self, batch, babble: bool = False) -> None:
-        """Enqueue the power pass of a batch a later `run_device(..., snr_db)` will use (host sigma mode)."""
-        if self.sigma_mode == "host" or babble:
-            self._sig_state(batch.n_clips)
-            self._sig["pending"][self._bkey(batch) + (babble,)] = self._submit_power(batch, babble)
+    def prefetch_power(self, batch, babble: bool = False, after: Optional[torch.cuda.Event] = None) -> None:
+        """Enqueue the power pass of a batch a later `run_device(..., snr_db)` will use (host sigma mode).  With the side
+        stream the pass starts once `after` (an event of the caller's stream: everything the batch depends on) has
+        completed and runs beside whatever the caller's stream holds from then on."""
+        if not (self.sigma_mode == "host" or babble):
+            return
+        self._sig_state(batch.n_clips)
+        key = self._bkey(batch) + (babble,)
+        if self._pow_stream is None:
+            k = self._submit_power(batch, babble)
+            self._sig["pending"].setdefault(key, []).append(k)
+            return
+        if after is None:
+            after = self._pow_entry
+            after.record(torch.cuda.current_stream(self.device))
+        self._pow_stream.wait_event(after)
+        with torch.cuda.stream(self._pow_stream):
+            k = self._submit_power(batch, babble)
+        self._sig["pending"].setdefault(key, []).append(k)
+        self._pow_last = self._sig["slots"][k]["event"]
+
+    def join(self) -> None:
+        """The caller's stream waits for the last prefetched power pass (a timed region ends with it)."""
+        if self._pow_last is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._pow_last)
 
     def _sigma_for(self, batch, snr_db, prefetch, babble: bool = False):
         """(device sigma vector, noise stream or None) for this step, valid in stream order until the next call.  White
@@ -133,10 +172,16 @@ class NoisyFeaturePipeline:
         if self.sigma_mode == "device" and not babble:
             return snr_sigma_device(clip_power(batch), snr_db), None
         st = self._sig_state(batch.n_clips)
-        k = st["pending"].pop(self._bkey(batch) + (babble,), None)
+        key = self._bkey(batch) + (babble,)
+        q = st["pending"].get(key)
+        k = None
+        if q:
+            k = q.pop(0)                                    # the oldest prefetched pass of this batch
+            if not q:
+                del st["pending"][key]
         if k is None:
             k = self._submit_power(batch, babble)
-        if prefetch is not None:
+        if prefetch is not None and self._pow_stream is None:
             self.prefetch_power(prefetch, babble)           # in front of this step's MFCC launch
             st = self._sig
         sl = st["slots"][k]
@@ -177,18 +222,24 @@ class NoisyFeaturePipeline:
         standard-normal stream) or "babble" (z is ignored: the noise is the sum of six other clips of the batch)."""
         sigma = None
         babble = noise_kind == "babble"
+        side = snr_db is not None and (self.sigma_mode == "host" or babble) and prefetch is not None and self._pow_stream is not None
+        if side:
+            self._pow_entry.record(torch.cuda.current_stream(self.device))   # what the prefetched batch may depend on
         if snr_db is not None and (self.sigma_mode == "host" or babble):
             sigma, zb = self._sigma_for(batch, snr_db, prefetch, babble)
             if babble:
                 z = zb
         if self.use_graphs and self.ev_mfcc is None:
-            return self._run_graphed(batch, z, snr_db, standardize, out_dtype, sigma)
-        feats = self._feat_buffer(batch.n_clips)
-        self._group1(batch, z, snr_db, feats, sigma)
-        flat = feats.view(batch.n_clips, self.D)
-        if not standardize:
-            return flat
-        return self.std.fit_transform(flat, out_dtype=out_dtype)
+            out = self._run_graphed(batch, z, snr_db, standardize, out_dtype, sigma)
+        else:
+            feats = self._feat_buffer(batch.n_clips)
+            self._group1(batch, z, snr_db, feats, sigma)
+            out = feats.view(batch.n_clips, self.D)
+            if standardize:
+                out = self.std.fit_transform(out, out_dtype=out_dtype)
+        if side:
+            self.prefetch_power(prefetch, babble, after=self._pow_entry)     # behind this step's launches, on the side stream
+        return out
 
     def _run_graphed(self, batch, z, snr_db, standardize, out_dtype, sigma=None):
         # host sigma mode: the graph reads the (fixed) device sigma vector, so one capture serves every SNR
@@ -200,17 +251,14 @@ class NoisyFeaturePipeline:
                 self._cache.clear()
             sg = self._capture(batch, z, snr_db, standardize, out_dtype, sigma)
             self._cache[key] = sg
-        if len(sg.graphs) == 1:
-            sg.graphs[0].replay()
-        else:
-            sg.graphs[0].replay()
-            self.std.exchange()                            # the one collective of the step
-            sg.graphs[1].replay()
+        for i, g in enumerate(sg.graphs):
+            g.replay()
+            if i == sg.exchange_after:
+                self.std.exchange()                        # the one collective of the step (NCCL transport)
         return sg.out
 
     def _capture(self, batch, z, snr_db, standardize, out_dtype, sigma=None) -> _StepGraphs:
         B = batch.n_clips
-        n_total = B * self.world_size
         sg = _StepGraphs()
         feats = torch.empty((B, self.rows, self.out_frames), dtype=torch.float32, device=self.device)
         flat = feats.view(B, self.D)
@@ -223,37 +271,44 @@ class NoisyFeaturePipeline:
         torch.cuda.synchronize(self.device)
         pool = torch.cuda.graph_pool_handle()
 
-        def cap(fn):
+        def cap(fns):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
-                fn()
+                for fn in fns:
+                    fn()
             sg.graphs.append(g)
 
-        def g1():                                           # sharded: everything up to this rank's message
+        def mfcc():
             self._group1(batch, z, snr_db, feats, sigma)
+
+        def message():                                      # sharded: this rank's statistics message
             self.std.local_stats([flat])
             self.std.local_message()
 
-        def g2():                                           # sharded: after the all-gather
+        def finish():                                       # sharded: after the all-gather
             self.std.merge()
             self.std.transform(flat, out=out)
 
+        # segments of the step: one graph, or two around the exchange when the collective is an NCCL call that is not captured
         if not standardize:
-            cap(lambda: self._group1(batch, z, snr_db, feats, sigma))
+            segs = [[mfcc]]
         elif self.distributed:
-            # default: two graphs with the one NCCL all-gather launched between them; opt-in: one graph for the whole
-            # step with the collective captured inside it
+            segs = None
             if self.capture_collectives:
                 try:
-                    cap(lambda: (g1(), self.std.exchange(), g2()))
+                    cap([mfcc, message, self.std.exchange, finish])
+                    segs = []
                 except Exception:                       # noqa: BLE001  (capture errors surface as RuntimeError subclasses)
                     sg.graphs.clear()
                     self.capture_collectives = False
                     torch.cuda.synchronize(self.device)
-            if not sg.graphs:
-                cap(g1); cap(g2)
+            if segs is None:
+                segs = [[mfcc, message], [finish]]
+                sg.exchange_after = 0
         else:
-            cap(lambda: (self._group1(batch, z, snr_db, feats, sigma), self.std.fit_transform(flat, out=out)))
+            segs = [[mfcc, lambda: self.std.fit_transform(flat, out=out)]]
+        for seg in segs:
+            cap(seg)
         return sg
 
     def run_corpus(self, batches, n_local: int, out_dtype=torch.float32):
@@ -271,9 +326,14 @@ class NoisyFeaturePipeline:
             nxt = next(it, None)                             # one batch of look-ahead: its power pass goes in front
             batch, z, snr_db = cur
             sigma = None
+            ahead = nxt[0] if nxt is not None and nxt[2] is not None else None
+            if ahead is not None and self._pow_stream is not None:
+                self._pow_entry.record(torch.cuda.current_stream(self.device))
             if snr_db is not None and self.sigma_mode == "host":
-                sigma, _ = self._sigma_for(batch, snr_db, nxt[0] if nxt is not None and nxt[2] is not None else None)
+                sigma, _ = self._sigma_for(batch, snr_db, ahead)
             self._group1(batch, z, snr_db, feats[done:done + batch.n_clips], sigma)
+            if ahead is not None and self._pow_stream is not None:
+                self.prefetch_power(ahead, after=self._pow_entry)   # beside this batch's MFCC launch
             done += batch.n_clips
             cur = nxt
         if done != n_local:

@@ -41,6 +41,30 @@ def test_clip_power_bit_exact_equal_length_batches(L):
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
+def test_clip_power_narrow_cta_shape_bit_exact():
+    """ASR_B200_POW_WARPS=4 (three 4-warp CTAs per SM instead of one of 12: the shape whose CTAs fit beside a step's tail
+    kernels) is read when the library first launches the power pass, so it is checked in a fresh process: same bits."""
+    import subprocess, sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import asr_b200 as A\nfrom synth import synth_clips, to_f32\n"
+        "for L in (7, 129, 1000, 16000, 22050, 90000):\n"
+        "    c16 = synth_clips(301, L, 16000, 30 + L)\n"
+        "    ref = np.array([np.mean(c ** 2) for c in to_f32(c16)], dtype=np.float32)\n"
+        "    for clips in (c16, to_f32(c16)):\n"
+        "        got = A.clip_power(A.ClipBatch.from_arrays(clips)).cpu().numpy()\n"
+        "        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), L\n"
+        "lengths = [1, 2, 7, 8, 9, 100, 127, 128, 129, 257, 1000, 4097, 16000, 16385, 40001]\n"
+        "c16 = synth_clips(len(lengths), 0, 16000, 21, lengths=lengths)\n"
+        "ref = np.array([np.mean(c ** 2) for c in to_f32(c16)], dtype=np.float32)\n"
+        "got = A.clip_power(A.ClipBatch.from_arrays(c16)).cpu().numpy()\n"
+        "assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))\nprint('narrow ok')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    for shape in ("4", "12"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, ASR_B200_POW_WARPS=shape), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "narrow ok" in r.stdout, (shape, r.stdout[-1500:], r.stderr[-1500:])
+
+
 def test_snr_sigma_device_matches_host_chain():
     import asr_b200 as A
     from oracle import noise_ref as nr

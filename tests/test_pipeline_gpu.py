@@ -103,6 +103,37 @@ def test_benchmarked_step_uses_the_reference_sigma_chain():
     assert torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_power_prefetch_modes_give_the_same_rows(mode, monkeypatch):
+    """ASR_B200_POWER_STREAM: the prefetched power pass in front of the step (0) or on a side stream behind the step's
+    launches (1, the default) - two alternating batches, passes issued two steps ahead, white and babble noise: every
+    step's rows equal the rows of a pipeline that never prefetches."""
+    import asr_b200 as A
+    from asr_b200.pipeline import NoisyFeaturePipeline
+    B, L = 64, 16000
+    batches, zs = [], []
+    for k in range(2):
+        audio = torch.from_numpy(np.stack(synth_clips(B, L, 16000, 400 + k))).cuda()
+        batches.append(A.ClipBatch.from_matrix(audio))
+        zs.append(A.randn(5 + k, 0, B * L))
+    monkeypatch.setenv("ASR_B200_POWER_STREAM", "0")
+    plain = NoisyFeaturePipeline(A.C1, 101)
+    monkeypatch.setenv("ASR_B200_POWER_STREAM", mode)
+    pipe = NoisyFeaturePipeline(A.C1, 101)
+    assert pipe._pow_mode == int(mode) and (pipe._pow_stream is None) == (mode == "0")
+    for kind in ("white", "babble"):
+        babble = kind == "babble"
+        pipe.prefetch_power(batches[0], babble=babble)
+        pipe.prefetch_power(batches[1], babble=babble)
+        for i, snr in enumerate((0, 5, 10, 20, 10, 5, 0)):
+            b, z = batches[i % 2], zs[i % 2]
+            got = pipe.run_device(b, None if babble else z, snr, prefetch=b, noise_kind=kind).clone()
+            want = plain.run_device(b, None if babble else z, snr, noise_kind=kind)
+            assert torch.equal(got, want), (kind, i, snr)
+        pipe.join()
+    torch.cuda.synchronize()
+
+
 def test_babble_step_matches_oracle():
     """The C2 step with babble instead of white noise: features of the oracle's babble mix, standardised."""
     import asr_b200 as A
