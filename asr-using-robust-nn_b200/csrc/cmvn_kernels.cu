@@ -215,7 +215,7 @@ __device__ __forceinline__ double slab_sum(const double* __restrict__ part, cons
 }
 
 template <bool CENTERED, int DT, bool NOISE>
-__global__ void __launch_bounds__(kColTile * kRowLanes) colsum2_kernel(
+__global__ void __launch_bounds__(kColTile * kRowLanes, NOISE ? 1 : 8) colsum2_kernel(   // clean: 8 CTAs per SM (32 registers), the grid of slab_shape() is ONE wave
     const void* __restrict__ x, const long long n_rows, const int n_cols, const long long ld, const RowNoise nz,
     const double* __restrict__ part1, const int n_slabs1, const double n_local, const long long rows_per_slab,
     double* __restrict__ out_part, const int slab_base) {
@@ -601,7 +601,8 @@ extern "C" int asr_cmvn_apply2(const void* x_dev, int32_t dtype, int64_t n_rows,
   }
   if (n_rows == 0) return ASR_OK;
   const int col_blocks = (n_cols + kColTile - 1) / kColTile;
-  int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((148 * 8 + col_blocks - 1) / col_blocks, (n_rows + 31) / 32));
+  // apply2_kernel holds 4 CTAs per SM (62 registers for the float64 division): at most 148 x 4 CTAs = ONE wave
+  int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((148 * 4) / col_blocks, (n_rows + 31) / 32));
   const int64_t rps = (n_rows + slabs - 1) / slabs;
   slabs = (n_rows + rps - 1) / rps;
   const dim3 grid(col_blocks, static_cast<unsigned>(slabs));
