@@ -78,6 +78,7 @@ SIGNATURES = {
     "asr_plan_set_path": (C.c_int, [_vp, _i32]),
     "asr_plan_path_used": (_i32, [_vp, _i32, _i32]),
     "asr_clip_power": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "asr_copy_mapped": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "asr_snr_sigma": (C.c_int, [_vp, _f32, _vp, _i32, _vp]),
     "asr_snr_sigma_host": (C.c_int, [_vp, _vp, _f32, _vp, _i32]),
     "asr_babble_workspace_bytes": (C.c_size_t, [_i32, _i32]),

@@ -495,6 +495,15 @@ __global__ void __launch_bounds__(kPowWarps * 32) clip_power_kernel(const void* 
   }
 }
 
+// Small transfers between MAPPED pinned host memory and device memory as a kernel (loads / stores over PCIe) instead of a
+// copy-engine operation: a DMA copy of a few KB queues behind whatever bulk copy the engine of its direction is busy with
+// (the 262 MB audio upload of the next batch), which put the 4*B-byte power read-back and the 8*B-byte sigma upload of a step
+// behind 4.8 ms of unrelated traffic (scripts/e2e_timeline.py).
+__global__ void copy_words_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, const size_t n_words) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_words; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
 __global__ void snr_sigma_kernel(const float* __restrict__ power, const float snr_db, double* __restrict__ sigma,
                                  const int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -731,6 +740,20 @@ extern "C" int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_
   static const int shape = [] { const char* e = std::getenv("ASR_B200_POW_WARPS"); return e ? std::atoi(e) : kPowDefaultWarps; }();
   if (shape == kPowWarpsNarrow) return launch_clip_power<kPowWarpsNarrow>(audio_dev, dtype, off, lengths_dev, n_clips, power_dev, aligned, stream);
   return launch_clip_power<kPowWarpsWide>(audio_dev, dtype, off, lengths_dev, n_clips, power_dev, aligned, stream);
+}
+
+extern "C" int asr_copy_mapped(const void* src, void* dst, size_t bytes, void* stream) {
+  if ((!src || !dst) && bytes != 0) { set_error("asr_copy_mapped: null pointer"); return ASR_ERR_INVALID; }
+  if ((bytes & 3) != 0 || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) != 0) {
+    set_error("asr_copy_mapped: pointers and byte count must be multiples of 4");
+    return ASR_ERR_INVALID;
+  }
+  if (bytes == 0) return ASR_OK;
+  const size_t n = bytes / 4;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 64));
+  copy_words_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const unsigned*>(src), static_cast<unsigned*>(dst), n);
+  ASR_CUDA_TRY(cudaGetLastError());
+  return ASR_OK;
 }
 
 extern "C" int asr_snr_sigma(const float* power_dev, float target_snr_db, double* sigma_dev, int32_t n_clips,

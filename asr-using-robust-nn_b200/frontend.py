@@ -299,6 +299,19 @@ def clip_power(batch: ClipBatch, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
+def copy_mapped(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """``dst.copy_(src)`` for a SMALL transfer between a pinned host tensor and a CUDA tensor (either direction) as a kernel
+    on the current stream instead of a copy-engine operation, so that it does not queue behind a bulk upload / download."""
+    if dst.dtype != src.dtype or dst.numel() != src.numel() or not dst.is_contiguous() or not src.is_contiguous():
+        raise ValueError("copy_mapped: contiguous tensors of one dtype and size")
+    for t in (dst, src):
+        if not (t.is_cuda or t.is_pinned()):
+            raise ValueError("copy_mapped: tensors must be CUDA or pinned host tensors")
+    dev = dst.device if dst.is_cuda else src.device
+    with torch.cuda.device(dev):
+        check(lib.asr_copy_mapped(src.data_ptr(), dst.data_ptr(), src.numel() * src.element_size(), _stream()), "asr_copy_mapped")
+
+
 def snr_sigma_host_scalar(power: np.ndarray, target_snr_db) -> np.ndarray:
     """The reference's own scalar lines (VDR/attacks.py:235-241) run clip by clip on ``P`` - the definition of the
     bit-exact sigma (numpy scalar semantics keep every step in float32 for float32 audio).  Slow: a Python loop."""

@@ -31,7 +31,7 @@ from typing import Optional
 import torch
 
 from .frontend import (ClipBatch, MfccPlan, Noise, Standardizer, clip_power, snr_sigma_device, snr_sigma_host, randn,
-                       babble_stream, babble_gain_host)
+                       babble_stream, babble_gain_host, copy_mapped)
 from .params import MfccParams
 
 # kernels of libasr_b200 launched by one `run_device` step besides the MFCC launches (`plan.launches`):
@@ -127,7 +127,7 @@ class NoisyFeaturePipeline:
         B = batch.n_clips
         torch.cuda.current_stream(self.device).wait_event(sl["event"])   # an earlier pass into this slot (possibly on the other stream) is over
         clip_power(batch, out=sl["P_dev"])
-        sl["P_host"][:B].copy_(sl["P_dev"][:B], non_blocking=True)
+        copy_mapped(sl["P_host"][:B], sl["P_dev"][:B])     # a kernel, not a DMA copy: never behind a bulk transfer of its direction
         if babble:
             n = batch.audio.shape[0]
             if sl.get("b_dev") is None or sl["b_dev"].numel() < n:
@@ -135,7 +135,7 @@ class NoisyFeaturePipeline:
                 sl["Pb_dev"] = torch.empty(st["cap"], dtype=torch.float64, device=self.device)
                 sl["Pb_host"] = torch.empty(st["cap"], dtype=torch.float64).pin_memory()
             babble_stream(batch, out=sl["b_dev"], power=sl["Pb_dev"])
-            sl["Pb_host"][:B].copy_(sl["Pb_dev"][:B], non_blocking=True)
+            copy_mapped(sl["Pb_host"][:B], sl["Pb_dev"][:B])
         sl["event"].record()
         return k
 
@@ -161,9 +161,13 @@ class NoisyFeaturePipeline:
         self._pow_last = self._sig["slots"][k]["event"]
 
     def join(self) -> None:
-        """The caller's stream waits for the last prefetched power pass (a timed region ends with it)."""
+        """The caller's stream waits for the last prefetched power pass and for the uploads `run_host` has issued ahead
+        (a timed region ends with them)."""
+        cur = torch.cuda.current_stream(self.device)
         if self._pow_last is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._pow_last)
+            cur.wait_event(self._pow_last)
+        if getattr(self, "_hs", None) is not None:
+            cur.wait_stream(self._s_h2d)
 
     def _sigma_for(self, batch, snr_db, prefetch, babble: bool = False):
         """(device sigma vector, noise stream or None) for this step, valid in stream order until the next call.  White
@@ -191,7 +195,7 @@ class NoisyFeaturePipeline:
         snr_sigma_host(sl["P_host"].numpy()[:B], snr_db, out=sig)
         if babble:
             sig[:] = babble_gain_host(sig, sl["Pb_host"].numpy()[:B])
-        st["sigma_dev"][:B].copy_(sl["sig_host"][:B], non_blocking=True)
+        copy_mapped(st["sigma_dev"][:B], sl["sig_host"][:B])
         return st["sigma_dev"][:B], (sl["b_dev"] if babble else None)
 
     def _feat_buffer(self, B: int) -> torch.Tensor:
@@ -342,7 +346,8 @@ class NoisyFeaturePipeline:
         return self.std.fit_transform(flat, out_dtype=out_dtype)
 
     def run_host(self, audio_host: torch.Tensor, snr_db: Optional[float], seed: int, out_host: torch.Tensor,
-                 first_index: int = 0, layout: Optional[ClipBatch] = None, noise_kind: str = "white") -> torch.Tensor:
+                 first_index: int = 0, layout: Optional[ClipBatch] = None, noise_kind: str = "white",
+                 next_audio_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """End to end from PINNED host memory: (B, L) int16/float32/float64 host tensor in - or, with ``layout`` (a
         ``ClipBatch`` whose offsets / lengths describe it), a packed 1-D host tensor of ragged clips -, standardised
         float32 (B, D) rows written to the pinned `out_host`.  The noise stream is generated on the device from `seed`
@@ -351,21 +356,39 @@ class NoisyFeaturePipeline:
         Three streams (host->device copy, compute, device->host copy) and two sets of device buffers: the
         upload of call i+1 overlaps the kernels of call i and the download of call i-1.  The caller's current
         stream is made to wait for this call's download, so `torch.cuda.current_stream().synchronize()` (or
-        an event recorded after the call) covers it."""
+        an event recorded after the call) covers it.
+
+        ``next_audio_host``: the host tensor of the NEXT call (same shape / dtype / layout; its samples must be in place now
+        and stay untouched until that call).  Its upload is enqueued BEFORE this call waits for its own sigma (in host
+        sigma mode the call blocks on the power of its batch, i.e. on its own upload), and its power pass behind this
+        call's kernels - the copy engine then never idles between calls and the next call finds its power ready.  Without
+        it every call pays upload -> power -> host chain serially before the next upload can start."""
         hs = self._host_slots(audio_host)
-        k = self._host_turn
-        self._host_turn ^= 1
+        hkey = (audio_host.data_ptr(), tuple(audio_host.shape), audio_host.dtype)
+        k = self._host_pre.pop(hkey, None)                 # already uploaded by the previous call?
+        if k is None:
+            k = self._host_turn
+            self._upload(hs[k], audio_host)
+        self._host_pre = {key: v for key, v in self._host_pre.items() if v != k}   # a stale announcement loses its slot
+        self._host_turn = k ^ 1
         sl = hs[k]
         cur = torch.cuda.current_stream(self.device)
-        self._s_h2d.wait_event(sl["computed"])            # the kernels of the call that last used this slot are done
-        with torch.cuda.stream(self._s_h2d):
-            sl["audio"].copy_(audio_host, non_blocking=True)
-            sl["uploaded"].record()
+        babble = noise_kind == "babble"
+        nxt = None
+        if next_audio_host is not None:
+            if next_audio_host.shape != audio_host.shape or next_audio_host.dtype != audio_host.dtype:
+                raise ValueError("next_audio_host must have the shape and dtype of audio_host")
+            nxt = hs[k ^ 1]
+            self._upload(nxt, next_audio_host)             # waits (on the device) for the kernels that last read that slot
+            self._host_pre[(next_audio_host.data_ptr(), tuple(next_audio_host.shape), next_audio_host.dtype)] = k ^ 1
         self._s_comp.wait_event(sl["uploaded"])
         self._s_comp.wait_event(sl["downloaded"])          # this slot's output buffer has been read back
         with torch.cuda.stream(self._s_comp):
             batch = ClipBatch.from_matrix(sl["audio"]) if layout is None else layout.like(sl["audio"])
             z = None
+            if snr_db is not None and (self.sigma_mode == "host" or babble) and self._pow_stream is not None \
+                    and not (self._sig is not None and self._sig["pending"].get(self._bkey(batch) + (babble,))):
+                self.prefetch_power(batch, babble)         # not announced: the power pass beside (not behind) the noise generator
             if snr_db is not None and noise_kind == "white":
                 if sl["z"] is None:
                     sl["z"] = torch.empty(sl["audio"].numel(), dtype=torch.float64, device=self.device)
@@ -373,6 +396,10 @@ class NoisyFeaturePipeline:
                 randn(seed, first_index, z.numel(), device=self.device, out=z)
             out = self.run_device(batch, z, snr_db, noise_kind=noise_kind)
             sl["computed"].record()
+            if nxt is not None and snr_db is not None:
+                # the next call's power pass: behind this call's kernels, as soon as its samples have arrived
+                self._s_comp.wait_event(nxt["uploaded"])
+                self.prefetch_power(ClipBatch.from_matrix(nxt["audio"]) if layout is None else layout.like(nxt["audio"]), babble)
         self._s_d2h.wait_event(sl["computed"])
         with torch.cuda.stream(self._s_d2h):
             out_host.copy_(out, non_blocking=True)
@@ -382,6 +409,16 @@ class NoisyFeaturePipeline:
             sl["downloaded"].record()
         cur.wait_event(sl["downloaded"])
         return out_host
+
+    def _upload(self, sl, audio_host: torch.Tensor) -> None:
+        if self._sig is not None:                          # a power pass of the slot's OLD content must not be taken for the new one
+            ptr = sl["audio"].data_ptr()
+            for key in [key for key in self._sig["pending"] if key[0] == ptr]:
+                del self._sig["pending"][key]
+        self._s_h2d.wait_event(sl["computed"])            # the kernels of the call that last used this slot are done
+        with torch.cuda.stream(self._s_h2d):
+            sl["audio"].copy_(audio_host, non_blocking=True)
+            sl["uploaded"].record()
 
     def _host_slots(self, audio_host: torch.Tensor):
         hs = getattr(self, "_hs", None)
@@ -394,4 +431,5 @@ class NoisyFeaturePipeline:
                            "uploaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "downloaded": torch.cuda.Event()})
             self._hs = hs
             self._host_turn = 0
+            self._host_pre = {}                            # host tensor announced by `next_audio_host` -> slot holding it
         return hs

@@ -197,6 +197,13 @@ int asr_logmel_batch(const asr_plan* plan, const void* audio_dev, int32_t dtype,
 int asr_clip_power(const void* audio_dev, int32_t dtype, const int64_t* offsets_dev, const int32_t* lengths_dev,
                    int32_t n_clips, float* power_dev, void* stream);
 
+/* A small transfer between MAPPED pinned host memory (cudaHostAlloc / cudaMallocHost: device-accessible at the same
+ * address under unified addressing) and device memory, in either direction, done by a kernel instead of a copy-engine
+ * operation.  The 4*B-byte power read-back and the 8*B-byte sigma upload between asr_clip_power and the noisy asr_mfcc_batch
+ * (the host evaluates VDR/attacks.py:235-241 in between) otherwise queue behind the bulk audio upload of the next batch on
+ * the same DMA engine.  Pointers and byte count must be multiples of 4; asynchronous on `stream`. */
+int asr_copy_mapped(const void* src, void* dst, size_t bytes, void* stream);
+
 /* sigma[b] = sqrt(10**((10*log10(P[b]) - snr_db)/10)) with every step rounded to float32
  * (VDR/attacks.py:235-241 under numpy >= 2 scalar rules), evaluated on the device in float64
  * and rounded; the host-exact alternative is to run those four numpy lines on P. */

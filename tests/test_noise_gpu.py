@@ -65,6 +65,26 @@ def test_clip_power_narrow_cta_shape_bit_exact():
         assert r.returncode == 0 and "narrow ok" in r.stdout, (shape, r.stdout[-1500:], r.stderr[-1500:])
 
 
+def test_copy_mapped_both_directions():
+    """asr_copy_mapped: the small power read-back / sigma upload as a kernel over mapped pinned memory (no DMA-engine queueing)."""
+    import asr_b200 as A
+    from asr_b200.frontend import copy_mapped
+    for dtype in (torch.float32, torch.float64):
+        for n in (1, 3, 257, 8192):
+            src = torch.randn(n, dtype=dtype)
+            host_in = src.clone().pin_memory()
+            dev = torch.zeros(n, dtype=dtype, device="cuda")
+            copy_mapped(dev, host_in)
+            host_out = torch.zeros(n, dtype=dtype).pin_memory()
+            copy_mapped(host_out, dev)
+            torch.cuda.current_stream().synchronize()
+            assert torch.equal(dev.cpu(), src) and torch.equal(host_out, src)
+    with pytest.raises(ValueError):
+        copy_mapped(torch.zeros(4, device="cuda"), torch.zeros(4))          # pageable host memory is not device-accessible
+    with pytest.raises(ValueError):
+        copy_mapped(torch.zeros(4, device="cuda"), torch.zeros(5).pin_memory())
+
+
 def test_snr_sigma_device_matches_host_chain():
     import asr_b200 as A
     from oracle import noise_ref as nr

@@ -61,6 +61,31 @@ def test_host_pipeline_slots_do_not_race():
         assert torch.equal(outs[i], want), i
 
 
+@pytest.mark.parametrize("kind", ["white", "babble"])
+def test_host_pipeline_with_announced_next_batch(kind):
+    """run_host(next_audio_host=...): the next call's upload and power pass are issued ahead; announced, unannounced and
+    wrongly announced calls in one sequence, clean and noisy - every result equals the eager device step."""
+    import asr_b200 as A
+    from asr_b200.pipeline import NoisyFeaturePipeline
+    B, L = 64, 16000
+    pipe = NoisyFeaturePipeline(A.C1, 101)
+    eager = NoisyFeaturePipeline(A.C1, 101, use_graphs=False)
+    hosts = [torch.from_numpy(np.stack(synth_clips(B, L, 16000, 700 + i))).pin_memory() for i in range(4)]
+    seq = [0, 1, 2, 3, 3, 0, 2, 1, 1]
+    snrs = [0, 5, 10, None, 20, 5, 0, 10, 5]
+    announce = [1, 2, 3, 3, None, 1, 1, 1, None]            # call 5 announces batch 1 but batch 2 follows (a stale announcement)
+    outs = [torch.empty((B, pipe.D), dtype=torch.float32).pin_memory() for _ in seq]
+    for i, (h, snr, a) in enumerate(zip(seq, snrs, announce)):
+        pipe.run_host(hosts[h], snr, 99, outs[i], first_index=1000 * i, noise_kind=kind,
+                      next_audio_host=None if a is None else hosts[a])
+    torch.cuda.current_stream().synchronize()
+    for i, (h, snr) in enumerate(zip(seq, snrs)):
+        dev = hosts[h].cuda()
+        z = A.randn(99, 1000 * i, B * L) if (snr is not None and kind == "white") else None
+        want = eager.run_device(A.ClipBatch.from_matrix(dev), z, snr, noise_kind=kind).cpu()
+        assert torch.equal(outs[i], want), (i, h, snr)
+
+
 def test_corpus_in_batches_equals_one_shot():
     """configs[3] shape: the corpus arrives in batches, statistics are taken once over all rows."""
     import asr_b200 as A
