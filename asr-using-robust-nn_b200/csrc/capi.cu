@@ -1553,6 +1553,7 @@ struct Slot {
   double* z = nullptr;        size_t z_cap = 0;
   void* ws = nullptr;         size_t ws_cap = 0;
   long long* reb_pinned = nullptr; size_t reb_cap = 0;     // rebased offsets of the chunk in flight (pinned: no sync after the copy)
+  int* len_pinned = nullptr;                               // its lengths (the caller's array may be pageable: that copy would block)
   cudaEvent_t uploaded = nullptr;                          // the chunk's descriptors have left reb_pinned
   template <typename T>
   static cudaError_t grow(T** p, size_t* cap, size_t need) {
@@ -1574,6 +1575,7 @@ struct Slot {
     if (sigma) cudaFree(sigma);
     if (z) cudaFree(z);
     if (reb_pinned) cudaFreeHost(reb_pinned);
+    if (len_pinned) cudaFreeHost(len_pinned);
     if (uploaded) cudaEventDestroy(uploaded);
     if (st) cudaStreamDestroy(st);
   }
@@ -1582,6 +1584,9 @@ struct HostState {
   std::mutex mu;
   Slot slots[2];
   int device = -1;
+  // per-clip status of the whole call, pinned: a device-to-host copy into the caller's (pageable) array would block the
+  // host until the chunk has finished, i.e. serialise upload / kernels / download of consecutive chunks
+  int* status_pinned = nullptr; size_t status_cap = 0;
 };
 }  // namespace
 
@@ -1589,6 +1594,7 @@ void free_host_state(asr_plan* plan) {
   if (!plan || !plan->host_state) return;
   HostState* hs = static_cast<HostState*>(plan->host_state);
   for (int s = 0; s < 2; ++s) hs->slots[s].release();
+  if (hs->status_pinned) cudaFreeHost(hs->status_pinned);
   delete hs;
   plan->host_state = nullptr;
 }
@@ -1682,11 +1688,19 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
     if (e == cudaSuccess && ws_bytes) e = Slot::grow(&sl.ws, &sl.ws_cap, ws_bytes);
     if (e == cudaSuccess && static_cast<size_t>(max_clips) > sl.reb_cap) {
       if (sl.reb_pinned) cudaFreeHost(sl.reb_pinned);
-      sl.reb_pinned = nullptr; sl.reb_cap = 0;
+      if (sl.len_pinned) cudaFreeHost(sl.len_pinned);
+      sl.reb_pinned = nullptr; sl.len_pinned = nullptr; sl.reb_cap = 0;
       e = cudaHostAlloc(reinterpret_cast<void**>(&sl.reb_pinned), sizeof(long long) * max_clips, cudaHostAllocDefault);
+      if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&sl.len_pinned), sizeof(int) * max_clips, cudaHostAllocDefault);
       if (e == cudaSuccess) sl.reb_cap = static_cast<size_t>(max_clips);
     }
     if (e != cudaSuccess) fail(e, "asr_mfcc_batch_host (allocation)");
+  }
+  if (rc == ASR_OK && status_host && static_cast<size_t>(n_clips) > hs->status_cap) {
+    if (hs->status_pinned) cudaFreeHost(hs->status_pinned);
+    hs->status_pinned = nullptr; hs->status_cap = 0;
+    const cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&hs->status_pinned), sizeof(int) * n_clips, cudaHostAllocDefault);
+    if (e == cudaSuccess) hs->status_cap = static_cast<size_t>(n_clips); else fail(e, "asr_mfcc_batch_host (allocation)");
   }
   for (size_t k = 0; k + 1 < cuts.size() && rc == ASR_OK; ++k) {
     Slot& sl = slots[k & 1];
@@ -1697,11 +1711,11 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
     // slot's stream, so nothing else has to be waited for here: chunk k's upload overlaps chunk k-1's kernels / download
     cudaError_t e = k >= 2 ? cudaEventSynchronize(sl.uploaded) : cudaSuccess;
     if (e != cudaSuccess) { fail(e, "event sync"); break; }
-    for (int i = 0; i < nc; ++i) sl.reb_pinned[i] = offsets_host[a + i] - first;
+    for (int i = 0; i < nc; ++i) { sl.reb_pinned[i] = offsets_host[a + i] - first; sl.len_pinned[i] = lengths_host[a + i]; }
     e = cudaMemcpyAsync(sl.audio, static_cast<const char*>(audio_host) + first * esz, span * esz,
                         cudaMemcpyHostToDevice, sl.st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(sl.offsets, sl.reb_pinned, sizeof(long long) * nc, cudaMemcpyHostToDevice, sl.st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.lengths, lengths_host + a, sizeof(int) * nc, cudaMemcpyHostToDevice, sl.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.lengths, sl.len_pinned, sizeof(int) * nc, cudaMemcpyHostToDevice, sl.st);
     if (e == cudaSuccess) e = cudaEventRecord(sl.uploaded, sl.st);
     if (e != cudaSuccess) { fail(e, "H2D copy"); break; }
     asr_noise nz;
@@ -1719,7 +1733,7 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
     e = cudaMemcpyAsync(static_cast<char*>(out_host) + static_cast<size_t>(a) * out_per_clip * osz, sl.out,
                         out_per_clip * osz * nc, cudaMemcpyDeviceToHost, sl.st);
     if (e == cudaSuccess && status_host)
-      e = cudaMemcpyAsync(status_host + a, sl.status, sizeof(int) * nc, cudaMemcpyDeviceToHost, sl.st);
+      e = cudaMemcpyAsync(hs->status_pinned + a, sl.status, sizeof(int) * nc, cudaMemcpyDeviceToHost, sl.st);
     if (e != cudaSuccess) { fail(e, "D2H copy"); break; }
   }
   for (int s = 0; s < 2; ++s)
@@ -1727,5 +1741,6 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
       const cudaError_t e = cudaStreamSynchronize(slots[s].st);
       if (e != cudaSuccess && rc == ASR_OK) fail(e, "final sync");
     }
+  if (rc == ASR_OK && status_host) std::memcpy(status_host, hs->status_pinned, sizeof(int) * n_clips);
   return rc;
 }
