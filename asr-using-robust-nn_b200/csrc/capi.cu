@@ -1617,8 +1617,9 @@ extern "C" int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host,
   const size_t osz = out_dtype == ASR_F64 ? 8 : 4;
   const int rows = asr_plan_feature_rows(plan);
   const size_t out_per_clip = static_cast<size_t>(rows) * out_frames;
-  // chunks of consecutive clips: <= 64 MiB of samples and <= 4096 clips; offsets must be ascending & disjoint
-  const int64_t kChunkSamples = (64ll << 20) / static_cast<int64_t>(esz);
+  // chunks of consecutive clips: <= 32 MiB of samples (ASR_B200_HOST_CHUNK_MIB) and <= 4096 clips; offsets must be ascending & disjoint
+  static const int64_t chunk_mib = [] { const char* e = std::getenv("ASR_B200_HOST_CHUNK_MIB"); const int v = e ? std::atoi(e) : 0; return static_cast<int64_t>(v > 0 ? v : 32); }();   // 32 MiB: 5.17 ms per 8192 one-second clips against 5.40 (64) / 5.18 (16) / 5.58 (8), scripts/host_call_time.py
+  const int64_t kChunkSamples = (chunk_mib << 20) / static_cast<int64_t>(esz);
   const int kChunkClips = 4096;
   std::vector<int> cuts{0};
   {
