@@ -39,7 +39,7 @@ from .params import MfccParams
 # device mode, the babble stream with babble noise) when noisy; the e2e step adds randn
 LAUNCHES_CMVN = 3
 LAUNCHES_CMVN_SHARDED = 6       # pass 1, pass 2, message, peer-memory exchange, merge, apply
-LAUNCHES_NOISE = 1
+LAUNCHES_NOISE = 1              # the power pass; host sigma mode adds the two small copy kernels (power out, sigma in), device mode the sigma kernel
 
 
 class _StepGraphs:
@@ -88,7 +88,7 @@ class NoisyFeaturePipeline:
         self.ev_mfcc = None          # optional (start, end) CUDA events around the MFCC launch (eager steps only)
 
     def launches_per_step(self, noisy: bool, standardize: bool = True) -> int:
-        noise = (LAUNCHES_NOISE + (1 if self.sigma_mode == "device" else 0)) if noisy else 0
+        noise = (LAUNCHES_NOISE + (1 if self.sigma_mode == "device" else 2)) if noisy else 0
         sharded = LAUNCHES_CMVN_SHARDED - (0 if self.std.exchange_transport == "p2p" else 1)   # the NCCL all-gather is not a kernel of this library
         cmvn = (sharded if self.distributed else LAUNCHES_CMVN) if standardize else 0
         return self.plan.launches(noisy) + noise + cmvn
