@@ -7,7 +7,7 @@ of ``Voice digit recogniton/attacks.py:402-407`` (``black_box_attack_on_audio_da
 ``standardize_dataset``).
 
 Sigma is the reference's own chain (``sigma_mode="host"``, the default): the device computes ``P = mean(x**2)`` bit
-for bit, its 4*B bytes go to pinned host memory, ``frontend.snr_sigma_host`` runs the four lines of
+for bit, its 4*B bytes go to pinned host memory (``frontend.copy_mapped``: a kernel, not a DMA copy), ``frontend.snr_sigma_host`` runs the four lines of
 ``attacks.py:235-241`` on it (numpy's log10, libm's powf) and sigma goes back - np.log10 / powf are not correctly
 rounded and differ between hosts, so only the host can reproduce them.  To keep that round trip off the critical
 path a caller that knows its next batch passes ``prefetch=``: the power launch and read-back of the NEXT step are
@@ -72,7 +72,7 @@ class NoisyFeaturePipeline:
         if sigma_mode not in ("host", "device"):
             raise ValueError("sigma_mode must be 'host' (the reference's chain, bit-exact) or 'device'")
         self.sigma_mode = sigma_mode
-        self._sig = None             # host-sigma state: two pinned slots, one device sigma vector
+        self._sig = None             # host-sigma state: three pinned result slots, one device sigma vector
         # the power pass of a prefetched batch: 1 (default) = on a side stream, free to start as soon as the step has been
         # launched; 0 = on the caller's stream, in front of the step's MFCC launch.  Measured on the default step
         # (profiles/r2_power_overlap_ab.txt): 0.813 against 0.846 ms; releasing the pass only behind the step's MFCC launches
@@ -93,7 +93,7 @@ class NoisyFeaturePipeline:
         cmvn = (sharded if self.distributed else LAUNCHES_CMVN) if standardize else 0
         return self.plan.launches(noisy) + noise + cmvn
 
-    # ---- sigma: device power -> host chain -> device sigma, one step ahead when the caller prefetches -----------
+    # ---- sigma: device power -> host chain -> device sigma, one or two steps ahead when the caller prefetches ----
     @staticmethod
     def _bkey(batch):
         return (batch.audio.data_ptr(), batch.n_clips, batch.max_length)
