@@ -366,7 +366,9 @@ int asr_tc_selftest(const void* a1_dev, const void* b1_dev, const void* a2_dev, 
 /* compute_mfcc_all_files (VDR/extract...py:144-150) on decoded waveforms: out_host is
  * [n_clips][rows*out_frames] of out_dtype (ASR_F64 = the reference's np.zeros float64 rows).
  * snr_mode: 0 none; 1 = add_white_noise_with_snr with target_snr_db and the seeded device
- * normal stream (seed, clip b uses indices offsets[b]..); sigma chain evaluated on the device. */
+ * normal stream (seed, clip b uses indices offsets[b]..); sigma chain evaluated on the device.
+ * audio_host / out_host should be page-locked (cudaHostRegister) for the copies to overlap the kernels; offsets, lengths
+ * and status may be pageable (staged in pinned memory of the plan).  Chunks of <= 32 MiB of samples / 4096 clips. */
 int asr_mfcc_batch_host(const asr_plan* plan, const void* audio_host, int32_t dtype, const int64_t* offsets_host,
                         const int32_t* lengths_host, int32_t n_clips, int32_t snr_mode, float target_snr_db,
                         uint64_t seed, void* out_host, int32_t out_dtype, int32_t out_frames,
