@@ -90,3 +90,21 @@ def test_invalid_parameters_are_rejected_before_any_cuda_call(lib):
         pc = bad.to_c()
         assert _lib.lib.asr_plan_create(ctypes.byref(pc), ctypes.byref(h)) == -1
         assert _lib.lib.asr_last_error().startswith(b"asr_plan_create")
+
+
+def test_copy_mapped_rejects_bad_arguments_before_any_cuda_call(lib):
+    """asr_copy_mapped: argument checks come first (no device needed); a zero-byte transfer is a no-op."""
+    import torch
+    from asr_b200 import _lib
+    from asr_b200.frontend import copy_mapped
+    f = _lib.lib.asr_copy_mapped
+    assert f(None, None, 0, None) == 0
+    assert f(None, None, 8, None) == -1 and b"null" in _lib.lib.asr_last_error()
+    buf = (ctypes.c_char * 64)()
+    base = ctypes.addressof(buf)
+    assert f(base + 1, base + 8, 8, None) == -1            # misaligned pointer
+    assert f(base, base + 8, 6, None) == -1                # byte count not a multiple of 4
+    with pytest.raises(ValueError):
+        copy_mapped(torch.zeros(4), torch.zeros(4))         # neither CUDA nor pinned
+    with pytest.raises(ValueError):
+        copy_mapped(torch.zeros(4), torch.zeros(4, dtype=torch.float64))
