@@ -2,7 +2,11 @@
 
 TEST INFRASTRUCTURE - see ``oracle/__init__.py``.  PARITY UNPINNED: librosa is
 not in the image; this file restates its published algorithm and follows the
-dtype flow librosa has for float32 / float64 input.
+dtype flow librosa has for float32 / float64 input.  What IS pinned to librosa's
+own published known answers: the Slaney mel scale (``hz_to_mel``, ``mel_to_hz``,
+the 40 values of ``mel_frequencies(n_mels=40)``) and the corner values of
+``librosa.filters.mel(sr=22050, n_fft=2048)`` - the docstring examples of librosa
+0.9, ``tests/test_oracle.py::test_oracle_reproduces_librosa_docstring_examples``.
 
 Reference call sites this restates the callee of:
   * ``Voice digit recogniton/extract_features_construct_dataset.py:30``

@@ -252,3 +252,27 @@ def test_log_mel_vs_transformers_audio_utils(name):
         got = lr.log_mel(x, p)
         assert got.shape == want.shape
         np.testing.assert_allclose(got, want, rtol=0, atol=1e-4)    # measured 9e-6 dB: float32 storage of |D|^2 in the oracle (librosa's dtype flow)
+
+
+def test_oracle_reproduces_librosa_docstring_examples():
+    """Known answers PUBLISHED by the dependency that holds the algorithm (librosa 0.9 docstrings; librosa itself is not in
+    the image): `librosa.hz_to_mel(60)` -> 0.9, `hz_to_mel([110, 220, 440])` -> [1.65, 3.3, 6.6]; `librosa.mel_to_hz(3)` ->
+    200., `mel_to_hz([1, 2, 3, 4, 5])` -> [66.667, 133.333, 200., 266.667, 333.333]; `librosa.mel_frequencies(n_mels=40)`
+    (fmin = 0, fmax = 11025) -> the 40 values below; `librosa.filters.mel(sr=22050, n_fft=2048)` prints
+    `[[0., 0.016, ..., 0., 0.], ...]` (128 x 1025).  These pin the Slaney mel scale and the filter bank of the reference's
+    own call (VDR/extract_features_construct_dataset.py:30 uses exactly sr = 22050, n_fft = 2048, 128 filters) to the
+    printed precision; the STFT / dB / DCT stages stay pinned only through the independent implementations above."""
+    assert np.allclose(lr.hz_to_mel(np.array([60.0])), [0.9], atol=5e-4)
+    assert np.allclose(lr.hz_to_mel(np.array([110.0, 220.0, 440.0])), [1.65, 3.3, 6.6], atol=5e-4)
+    assert np.allclose(lr.mel_to_hz(np.array([3.0])), [200.0], atol=5e-4)
+    assert np.allclose(lr.mel_to_hz(np.array([1.0, 2, 3, 4, 5])), [66.667, 133.333, 200.0, 266.667, 333.333], atol=5e-4)
+    doc = np.array([0., 85.317, 170.635, 255.952, 341.269, 426.586, 511.904, 597.221, 682.538, 767.855, 853.173, 938.49,
+                    1024.856, 1119.114, 1222.042, 1334.436, 1457.167, 1591.187, 1737.532, 1897.337, 2071.84, 2262.393,
+                    2470.47, 2697.686, 2945.799, 3216.731, 3512.582, 3835.643, 4188.417, 4573.636, 4994.285, 5453.621,
+                    5955.205, 6502.92, 7101.009, 7754.107, 8467.272, 9246.028, 10096.408, 11025.])
+    mels = np.linspace(lr.hz_to_mel(np.array([0.0]))[0], lr.hz_to_mel(np.array([11025.0]))[0], 40)
+    assert np.allclose(lr.mel_to_hz(mels), doc, atol=6e-4)
+    fb = lr.mel_filterbank(lr.PRESETS["ref_vdr"])
+    assert fb.shape == (128, 1025)
+    assert [round(float(v), 3) + 0.0 for v in (fb[0, 0], fb[0, 1], fb[0, -2], fb[0, -1])] == [0.0, 0.016, 0.0, 0.0]
+    assert not np.round(fb[[1, -2, -1]][:, [0, 1, -2, -1]], 3).any()      # the other printed corners: 0. to three decimals
