@@ -108,3 +108,27 @@ def test_copy_mapped_rejects_bad_arguments_before_any_cuda_call(lib):
         copy_mapped(torch.zeros(4), torch.zeros(4))         # neither CUDA nor pinned
     with pytest.raises(ValueError):
         copy_mapped(torch.zeros(4), torch.zeros(4, dtype=torch.float64))
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/asr_b200.h is valid strict C99 (-Wall -Wextra -Werror) and the library links and runs from a plain C program
+    (examples/mfcc_from_c.c: the reference's compute_mfcc_all_files through asr_mfcc_batch_host).  With a CUDA device it
+    prints features (exit 0; `profiles/r2_mfcc_from_c.txt` keeps a B200 run, equal to the oracle to 1.1e-3); without one the
+    library reports ASR_ERR_CUDA - no CPU fallback - and the program exits 3."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "mfcc_from_c")
+    libdir = os.path.dirname(LIB)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "mfcc_from_c.c"), "-L", libdir, "-lasr_b200", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode in (0, 3), (r.returncode, r.stdout[-1000:], r.stderr[-1000:])
+    if r.returncode == 3:
+        assert "no CPU fallback" in r.stdout
+    else:
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("clip ")]
+        assert len(lines) == 4 and all("status 0, 44 frames" in ln for ln in lines)
